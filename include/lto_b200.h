@@ -1,0 +1,178 @@
+/* lto_b200.h -- C ABI of liblto_b200.so: B200 (sm_100a) segment propagation for
+ * LowThrustOpt's multiple-shooting solvers.
+ *
+ * The library replaces, and only replaces, the four inner closures of the reference
+ * (citations relative to the reference repository root):
+ *
+ *   direct   defectCalc    src/multiShoot_CRTBP_direct.jl:66-109    -> lto_direct_defect[_traj]
+ *   direct   jacobianCalc  src/multiShoot_CRTBP_direct.jl:111-143   -> lto_direct_defect_jac[_traj]
+ *            (the dense Jac_temp blocks; the band scatter :146-162 stays on the host)
+ *   indirect defectCalc    src/multiShoot_CRTBP_indirect.jl:63-90   -> lto_indirect_defect[_traj]
+ *   indirect jacobianCalc  src/multiShoot_CRTBP_indirect.jl:93-124  -> lto_indirect_defect_jac[_traj]
+ *            (the Phi_i blocks of hcat(Phi_i, -I) :123; scatter/pinning :128-142 stay on the host)
+ *
+ * and beneath them the integrator hooks  ode7_8 (GeneralCode/ode.jl:773-953),
+ * ode78 (GeneralCode/ode.jl:364-544), solve(prob, Vern8(), reltol, abstol)
+ * (multiShoot_CRTBP_indirect.jl:78-79,107-110) and ForwardDiff.jacobian (:121), with the
+ * right-hand sides CRTBP_prop_EP_deriv (src/CRTBP_prop_EP_deriv.jl:8-61) and
+ * CRTBP_stateCostate_deriv! (src/CRTBP_stateCostate_deriv.jl:9-90) compiled in.
+ *
+ * Conventions
+ *  - All arrays are Float64, laid out exactly as Julia lays out the reference's
+ *    arrays (column-major): X_all is nstate x n_nodes, so node i's state is the
+ *    contiguous run X_all + i*nstate.  "pairs" entry points take one row of
+ *    (a, b) node data per segment in the same per-node layout.
+ *  - Caller owns every buffer; nothing is retained after return.  Buffers may be
+ *    ordinary (pageable) memory or memory from lto_host_alloc (pinned: faster copies).
+ *  - Return value: 0 ok, negative = library failure (see lto_last_error).  Numerical
+ *    trouble is per segment in status[] (LTO_ST_*), never a failure.
+ *  - A handle is bound to one CUDA device and is not re-entrant.
+ *  - There is no CPU fallback: without a usable sm_100 device lto_init fails.
+ */
+#ifndef LTO_B200_H
+#define LTO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTO_B200_VERSION 100
+
+/* per-segment status codes */
+enum { LTO_ST_OK = 0, LTO_ST_NAN = 1, LTO_ST_HMIN = 2, LTO_ST_MAXSTEPS = 3, LTO_ST_BADP = 4 };
+/* return codes */
+enum { LTO_SUCCESS = 0, LTO_ERR_CUDA = -1, LTO_ERR_ARG = -2, LTO_ERR_NODEVICE = -3, LTO_ERR_NOMEM = -4 };
+/* direct integration mode */
+enum { LTO_FIXED = 0,      /* ode7_8: fixed grid LinRange(t_i, t_mid, nsteps) -- what the reference runs */
+       LTO_ADAPTIVE = 1 }; /* ode78 controller (ode.jl:477-534) on every leg */
+/* indirect controller */
+enum { LTO_CTRL_RMS = 0,   /* OrdinaryDiffEq-style: scaled RMS error, reltol/abstol (stands in for Vern8) */
+       LTO_CTRL_ODE78 = 1 };/* the reference's own ode78 controller, tol = reltol */
+/* which components the step-size controller's norms span */
+enum { LTO_NORM_STATE = 0, LTO_NORM_STATE_SENS = 1 };
+/* kernel selection */
+enum { LTO_KERNEL_AUTO = 0, LTO_KERNEL_GENERIC = 1, LTO_KERNEL_FAST = 2 };
+
+typedef struct lto_handle lto_handle;
+
+/* Free variables / arguments of the direct closures (multiShoot_CRTBP_direct.jl:66,86). */
+typedef struct lto_direct_params {
+    double MU, DU, TU;     /* src/LowThrustOpt.jl:24-26 */
+    double Isp;            /* s */
+    double g0;             /* 9.81 (CRTBP_prop_EP_deriv.jl:41) */
+    double default_mass;   /* 1000 kg when nstate == 6 (CRTBP_prop_EP_deriv.jl:20) */
+    double tol;            /* LTO_ADAPTIVE only */
+    int32_t mode;          /* LTO_FIXED | LTO_ADAPTIVE */
+    int32_t err_norm;      /* LTO_ADAPTIVE only: LTO_NORM_* */
+    int32_t max_attempts;  /* LTO_ADAPTIVE only; 0 -> 100000 */
+    int32_t kernel;        /* LTO_KERNEL_* */
+} lto_direct_params;
+
+/* The params tuple of the indirect solver (multiShoot_CRTBP_indirect.jl:260) + tolerances (:79). */
+typedef struct lto_indirect_params {
+    double MU, DU, TU;
+    double thrustLimit;    /* N */
+    double mass;           /* kg (ndim == 12: constant mass) */
+    double time_direction; /* +1 / -1 */
+    double p, rho;         /* control law (CRTBP_stateCostate_deriv.jl:36-53) */
+    double Isp, g0;        /* ndim == 14 only */
+    double reltol, abstol; /* 1e-13 in the reference */
+    int32_t controller;    /* LTO_CTRL_* */
+    int32_t err_norm;      /* LTO_NORM_*; jac calls default to STATE_SENS (ForwardDiff semantics) */
+    int32_t max_attempts;  /* 0 -> 100000 */
+    int32_t kernel;        /* LTO_KERNEL_* */
+} lto_indirect_params;
+
+void lto_direct_params_default(lto_direct_params* p);      /* Earth-Moon constants, Isp 2000, FIXED */
+void lto_indirect_params_default(lto_indirect_params* p);  /* Earth-Moon constants, 1e-13, p=1, rho=1 */
+
+/* ---- lifetime ---------------------------------------------------------- */
+int lto_version(void);
+int lto_device_count(void);
+int lto_init(int device, lto_handle** h);      /* LTO_ERR_NODEVICE when no sm_100 GPU */
+void lto_destroy(lto_handle* h);
+const char* lto_last_error(const lto_handle* h);
+void* lto_host_alloc(size_t bytes);            /* pinned host memory (NULL on failure) */
+void lto_host_free(void* p);
+/* counters since init / last reset: kernels launched, device ms of the last call's kernels */
+int64_t lto_kernel_launches(const lto_handle* h);
+double lto_last_kernel_ms(const lto_handle* h);
+void* lto_stream(lto_handle* h);               /* cudaStream_t the *_dev entry points launch on */
+
+/* ---- direct method, host buffers ---------------------------------------
+ * pairs form: segment s goes from node a (Xa + s*nstate, ua + s*3, ta[s]) to node b.
+ *   defect   nstate x n_seg            defect1[:, s]     (:101)
+ *   errors   n_seg                     errors[s]         (:104)   (FIXED; 0 in ADAPTIVE)
+ *   status   n_seg  (may be NULL)
+ *   jac      per segment nstate x 2(nstate+3) column-major, column order
+ *            [X_a, X_b, u_a, u_b] = rows (s-1)n+1..sn of Jac_temp (:125,:139-140)
+ */
+int lto_direct_defect(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps,
+                      const double* Xa, const double* Xb, const double* ua, const double* ub,
+                      const double* ta, const double* tb,
+                      double* defect, double* errors, int32_t* status);
+int lto_direct_defect_jac(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps,
+                          const double* Xa, const double* Xb, const double* ua, const double* ub,
+                          const double* ta, const double* tb,
+                          double* defect, double* errors, int32_t* status, double* jac);
+/* trajectory form: n_traj trajectories of n_nodes nodes each, stored back to back exactly
+ * as the reference's X_all (nstate x n_nodes), u_all (3 x n_nodes), t_TU (n_nodes).
+ * Segment (j, i) = trajectory j, nodes i -> i+1; outputs are indexed j*(n_nodes-1)+i. */
+int lto_direct_defect_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate,
+                           int nsteps, const double* X_all, const double* u_all, const double* t_TU,
+                           double* defect, double* errors, int32_t* status);
+int lto_direct_defect_jac_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate,
+                               int nsteps, const double* X_all, const double* u_all, const double* t_TU,
+                               double* defect, double* errors, int32_t* status, double* jac);
+
+/* ---- indirect method, host buffers -------------------------------------
+ *   x0        ndim x n_seg   (ndim = 12: [r v lr lv]; 14: [r v m lr lv lm])
+ *   x_target  ndim x n_seg or NULL; defect = x(t1) - x_target (:82), x(t1) itself if NULL
+ *   thrustLimit_seg, rho_seg: optional per-segment overrides of p->thrustLimit / p->rho
+ *   status, nsteps_out (2 x n_seg: accepted, attempted) may be NULL
+ *   phi       per segment ndim x ndim column-major = ForwardDiff.jacobian(f, x0) (:121)
+ */
+int lto_indirect_defect(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim,
+                        const double* x0, const double* t0, const double* t1, const double* x_target,
+                        const double* thrustLimit_seg, const double* rho_seg,
+                        double* defect, int32_t* status, int32_t* nsteps_out);
+int lto_indirect_defect_jac(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim,
+                            const double* x0, const double* t0, const double* t1, const double* x_target,
+                            const double* thrustLimit_seg, const double* rho_seg,
+                            double* defect, int32_t* status, int32_t* nsteps_out, double* phi);
+/* trajectory form: XC_all (ndim x n_nodes) per trajectory, t_TU (n_nodes) per trajectory;
+ * thrustLimit_traj / rho_traj: optional per-TRAJECTORY overrides (continuation batches). */
+int lto_indirect_defect_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
+                             const double* XC_all, const double* t_TU,
+                             const double* thrustLimit_traj, const double* rho_traj,
+                             double* defect, int32_t* status, int32_t* nsteps_out);
+int lto_indirect_defect_jac_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
+                                 const double* XC_all, const double* t_TU,
+                                 const double* thrustLimit_traj, const double* rho_traj,
+                                 double* defect, int32_t* status, int32_t* nsteps_out, double* phi);
+
+/* ---- device-resident variants ------------------------------------------
+ * Same meaning, but every pointer is a DEVICE pointer on the handle's device and the
+ * call only enqueues work on lto_stream(h) (no copies, no synchronisation).  n_nodes = 0
+ * selects the pairs form (Xb/ub/tb used), n_nodes > 0 the trajectory form (Xb/ub/tb
+ * ignored; n_seg = n_traj*(n_nodes-1)).  Optional outputs may be NULL; jac/phi NULL
+ * selects the defect-only kernels. */
+int lto_direct_dev(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int n_nodes, int nstate, int nsteps,
+                   const double* Xa, const double* Xb, const double* ua, const double* ub,
+                   const double* ta, const double* tb,
+                   double* defect, double* errors, int32_t* status, double* jac);
+int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int n_nodes, int ndim,
+                     const double* x0, const double* t0, const double* t1, const double* x_target,
+                     const double* thrustLimit_arr, const double* rho_arr,
+                     double* defect, int32_t* status, int32_t* nsteps_out, double* phi);
+int lto_sync(lto_handle* h);   /* cudaStreamSynchronize(lto_stream(h)) */
+
+/* FP64 issue-rate probe used by bench.py for the roofline denominator: runs a
+ * register-resident DFMA loop on every SM and returns achieved FLOP/s (FMA = 2). */
+int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTO_B200_H */

@@ -1,0 +1,287 @@
+"""ctypes binding of liblto_b200.so (include/lto_b200.h).
+
+This is the only way Python reaches the propagation path.  There is no fallback: if the
+shared object is missing or no sm_100 device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblto_b200.so")
+
+# src/LowThrustOpt.jl:24-29
+MU = 0.012150585609624037
+DU = 384747.96285603708
+TU = 375699.81732246041
+DAY = 86400.0
+
+LTO_FIXED, LTO_ADAPTIVE = 0, 1
+LTO_CTRL_RMS, LTO_CTRL_ODE78 = 0, 1
+LTO_NORM_STATE, LTO_NORM_STATE_SENS = 0, 1
+LTO_KERNEL_AUTO, LTO_KERNEL_GENERIC, LTO_KERNEL_FAST = 0, 1, 2
+
+EXPORTS = [
+    "lto_version", "lto_device_count", "lto_init", "lto_destroy", "lto_last_error", "lto_host_alloc", "lto_host_free",
+    "lto_kernel_launches", "lto_last_kernel_ms", "lto_stream", "lto_sync",
+    "lto_direct_params_default", "lto_indirect_params_default",
+    "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
+    "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
+    "lto_direct_dev", "lto_indirect_dev", "lto_fp64_peak_probe",
+]
+
+
+class DirectParams(C.Structure):
+    _fields_ = [("MU", C.c_double), ("DU", C.c_double), ("TU", C.c_double), ("Isp", C.c_double), ("g0", C.c_double),
+                ("default_mass", C.c_double), ("tol", C.c_double), ("mode", C.c_int32), ("err_norm", C.c_int32),
+                ("max_attempts", C.c_int32), ("kernel", C.c_int32)]
+
+
+class IndirectParams(C.Structure):
+    _fields_ = [("MU", C.c_double), ("DU", C.c_double), ("TU", C.c_double), ("thrustLimit", C.c_double),
+                ("mass", C.c_double), ("time_direction", C.c_double), ("p", C.c_double), ("rho", C.c_double),
+                ("Isp", C.c_double), ("g0", C.c_double), ("reltol", C.c_double), ("abstol", C.c_double),
+                ("controller", C.c_int32), ("err_norm", C.c_int32), ("max_attempts", C.c_int32), ("kernel", C.c_int32)]
+
+
+class LtoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load liblto_b200.so; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LtoError("%s is missing: build it with `python -m lowthrustopt_b200.build` "
+                           "(there is no non-CUDA implementation of the propagation path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.lto_last_error.restype = C.c_char_p
+        L.lto_last_error.argtypes = [C.c_void_p]
+        L.lto_host_alloc.restype = C.c_void_p
+        L.lto_host_alloc.argtypes = [C.c_size_t]
+        L.lto_host_free.argtypes = [C.c_void_p]
+        L.lto_kernel_launches.restype = C.c_int64
+        L.lto_kernel_launches.argtypes = [C.c_void_p]
+        L.lto_last_kernel_ms.restype = C.c_double
+        L.lto_last_kernel_ms.argtypes = [C.c_void_p]
+        L.lto_stream.restype = C.c_void_p
+        L.lto_stream.argtypes = [C.c_void_p]
+        L.lto_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.lto_destroy.argtypes = [C.c_void_p]
+        L.lto_sync.argtypes = [C.c_void_p]
+        vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
+        L.lto_direct_defect.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 3
+        L.lto_direct_defect_jac.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
+        L.lto_direct_defect_traj.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 3 + [vp] * 3
+        L.lto_direct_defect_jac_traj.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 3 + [vp] * 4
+        L.lto_indirect_defect.argtypes = [vp, vp, i64, ci] + [vp] * 6 + [vp] * 3
+        L.lto_indirect_defect_jac.argtypes = [vp, vp, i64, ci] + [vp] * 6 + [vp] * 4
+        L.lto_indirect_defect_traj.argtypes = [vp, vp, i64, ci, ci] + [vp] * 4 + [vp] * 3
+        L.lto_indirect_defect_jac_traj.argtypes = [vp, vp, i64, ci, ci] + [vp] * 4 + [vp] * 4
+        L.lto_direct_dev.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 6 + [vp] * 4
+        L.lto_indirect_dev.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
+        L.lto_fp64_peak_probe.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def direct_params(Isp=2000.0, mode=LTO_FIXED, tol=1e-13, err_norm=LTO_NORM_STATE, kernel=LTO_KERNEL_AUTO,
+                  MU_=MU, DU_=DU, TU_=TU):
+    p = DirectParams()
+    lib().lto_direct_params_default(C.byref(p))
+    p.MU, p.DU, p.TU, p.Isp, p.mode, p.tol, p.err_norm, p.kernel = MU_, DU_, TU_, Isp, mode, tol, err_norm, kernel
+    return p
+
+
+def indirect_params(thrustLimit=0.05, mass=1000.0, time_direction=1.0, p=1.0, rho=1.0, Isp=2000.0, reltol=1e-13,
+                    abstol=1e-13, controller=LTO_CTRL_RMS, err_norm=LTO_NORM_STATE_SENS, kernel=LTO_KERNEL_AUTO,
+                    MU_=MU, DU_=DU, TU_=TU):
+    q = IndirectParams()
+    lib().lto_indirect_params_default(C.byref(q))
+    q.MU, q.DU, q.TU = MU_, DU_, TU_
+    q.thrustLimit, q.mass, q.time_direction, q.p, q.rho, q.Isp = thrustLimit, mass, time_direction, p, rho, Isp
+    q.reltol, q.abstol, q.controller, q.err_norm, q.kernel = reltol, abstol, controller, err_norm, kernel
+    return q
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)      # raw address (device pointer / pinned buffer)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class PinnedBuffer:
+    """Pinned host memory from lto_host_alloc, viewed as a numpy array."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().lto_host_alloc(max(nbytes, 1))
+        if not self.ptr:
+            raise LtoError("lto_host_alloc(%d) failed" % nbytes)
+        buf = (C.c_char * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().lto_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Handle:
+    """One lto_handle (one CUDA device).  Methods take numpy arrays with one ROW per node /
+    segment, i.e. the transpose view of the reference's nstate x n_nodes Julia arrays
+    (identical memory)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().lto_init(int(device), C.byref(self._h))
+        if rc != 0:
+            raise LtoError("lto_init(%d) failed (%d): %s" % (device, rc, lib().lto_last_error(None).decode()))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().lto_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LtoError("liblto_b200 error %d: %s" % (rc, lib().lto_last_error(self._h).decode()))
+
+    @property
+    def launches(self):
+        return int(lib().lto_kernel_launches(self._h))
+
+    @property
+    def last_kernel_ms(self):
+        return float(lib().lto_last_kernel_ms(self._h))
+
+    @property
+    def stream(self):
+        return lib().lto_stream(self._h)
+
+    def sync(self):
+        self._ck(lib().lto_sync(self._h))
+
+    def fp64_peak_probe(self, iters=4096):
+        f = C.c_double(); ms = C.c_double()
+        self._ck(lib().lto_fp64_peak_probe(self._h, int(iters), C.byref(f), C.byref(ms)))
+        return f.value, ms.value
+
+    # ---- direct ---------------------------------------------------------
+    def direct(self, Xa, Xb, ua, ub, ta, tb, nsteps=10, params=None, jac=True, out=None):
+        """pairs form.  Xa, Xb: (n_seg, nstate); ua, ub: (n_seg, 3); ta, tb: (n_seg,).
+        Returns dict(defect (n_seg,nstate), errors, status, jac (n_seg, 2(nstate+3), nstate) = column-major blocks)."""
+        p = params or direct_params()
+        Xa, Xb, ua, ub, ta, tb = map(_f64, (Xa, Xb, ua, ub, ta, tb))
+        n_seg, ns = Xa.shape if Xa.ndim == 2 else (0, 0)
+        if Xa.ndim != 2:
+            raise ValueError("Xa must be (n_seg, nstate)")
+        nv = 2 * (ns + 3)
+        o = out or {}
+        defect = o.get("defect", np.empty((n_seg, ns))); errors = o.get("errors", np.empty(n_seg))
+        status = o.get("status", np.empty(n_seg, dtype=np.int32))
+        if jac:
+            J = o.get("jac", np.empty((n_seg, nv, ns)))
+            self._ck(lib().lto_direct_defect_jac(self._h, C.addressof(p), n_seg, ns, int(nsteps), _ptr(Xa), _ptr(Xb), _ptr(ua),
+                                                 _ptr(ub), _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status), _ptr(J)))
+            return dict(defect=defect, errors=errors, status=status, jac=J)
+        self._ck(lib().lto_direct_defect(self._h, C.addressof(p), n_seg, ns, int(nsteps), _ptr(Xa), _ptr(Xb), _ptr(ua), _ptr(ub),
+                                         _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status)))
+        return dict(defect=defect, errors=errors, status=status)
+
+    def direct_traj(self, X_all, u_all, t_TU, nsteps=10, params=None, jac=True):
+        """trajectory form.  X_all: (n_traj, n_nodes, nstate) (or (n_nodes, nstate)), u_all: (.., n_nodes, 3), t_TU: (.., n_nodes)."""
+        p = params or direct_params()
+        X_all, u_all, t_TU = map(_f64, (X_all, u_all, t_TU))
+        if X_all.ndim == 2:
+            X_all, u_all, t_TU = X_all[None], u_all[None], t_TU[None]
+        n_traj, n_nodes, ns = X_all.shape
+        n_seg = n_traj * (n_nodes - 1); nv = 2 * (ns + 3)
+        defect = np.empty((n_seg, ns)); errors = np.empty(n_seg); status = np.empty(n_seg, dtype=np.int32)
+        if jac:
+            J = np.empty((n_seg, nv, ns))
+            self._ck(lib().lto_direct_defect_jac_traj(self._h, C.addressof(p), n_traj, n_nodes, ns, int(nsteps), _ptr(X_all),
+                                                      _ptr(u_all), _ptr(t_TU), _ptr(defect), _ptr(errors), _ptr(status), _ptr(J)))
+            return dict(defect=defect, errors=errors, status=status, jac=J)
+        self._ck(lib().lto_direct_defect_traj(self._h, C.addressof(p), n_traj, n_nodes, ns, int(nsteps), _ptr(X_all), _ptr(u_all),
+                                              _ptr(t_TU), _ptr(defect), _ptr(errors), _ptr(status)))
+        return dict(defect=defect, errors=errors, status=status)
+
+    # ---- indirect -------------------------------------------------------
+    def indirect(self, x0, t0, t1, x_target=None, params=None, thrustLimit=None, rho=None, jac=True):
+        """pairs form.  x0: (n_seg, ndim).  Returns dict(defect, status, nsteps (n_seg,2), phi (n_seg, ndim, ndim) column-major)."""
+        p = params or indirect_params()
+        x0, t0, t1 = map(_f64, (x0, t0, t1))
+        if x0.ndim != 2:
+            raise ValueError("x0 must be (n_seg, ndim)")
+        n_seg, nd = x0.shape
+        xt = None if x_target is None else _f64(x_target)
+        tl = None if thrustLimit is None else _f64(thrustLimit)
+        rh = None if rho is None else _f64(rho)
+        defect = np.empty((n_seg, nd)); status = np.empty(n_seg, dtype=np.int32); nst = np.empty((n_seg, 2), dtype=np.int32)
+        if jac:
+            phi = np.empty((n_seg, nd, nd))
+            self._ck(lib().lto_indirect_defect_jac(self._h, C.addressof(p), n_seg, nd, _ptr(x0), _ptr(t0), _ptr(t1), _ptr(xt),
+                                                   _ptr(tl), _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst), _ptr(phi)))
+            return dict(defect=defect, status=status, nsteps=nst, phi=phi)
+        self._ck(lib().lto_indirect_defect(self._h, C.addressof(p), n_seg, nd, _ptr(x0), _ptr(t0), _ptr(t1), _ptr(xt), _ptr(tl),
+                                           _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst)))
+        return dict(defect=defect, status=status, nsteps=nst)
+
+    def indirect_traj(self, XC_all, t_TU, params=None, thrustLimit=None, rho=None, jac=True):
+        """trajectory form.  XC_all: (n_traj, n_nodes, ndim) or (n_nodes, ndim); thrustLimit/rho: optional (n_traj,)."""
+        p = params or indirect_params()
+        XC_all, t_TU = _f64(XC_all), _f64(t_TU)
+        if XC_all.ndim == 2:
+            XC_all, t_TU = XC_all[None], t_TU[None]
+        n_traj, n_nodes, nd = XC_all.shape
+        n_seg = n_traj * (n_nodes - 1)
+        tl = None if thrustLimit is None else _f64(thrustLimit)
+        rh = None if rho is None else _f64(rho)
+        defect = np.empty((n_seg, nd)); status = np.empty(n_seg, dtype=np.int32); nst = np.empty((n_seg, 2), dtype=np.int32)
+        if jac:
+            phi = np.empty((n_seg, nd, nd))
+            self._ck(lib().lto_indirect_defect_jac_traj(self._h, C.addressof(p), n_traj, n_nodes, nd, _ptr(XC_all), _ptr(t_TU),
+                                                        _ptr(tl), _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst), _ptr(phi)))
+            return dict(defect=defect, status=status, nsteps=nst, phi=phi)
+        self._ck(lib().lto_indirect_defect_traj(self._h, C.addressof(p), n_traj, n_nodes, nd, _ptr(XC_all), _ptr(t_TU), _ptr(tl),
+                                                _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst)))
+        return dict(defect=defect, status=status, nsteps=nst)
+
+    # ---- device-resident (raw device addresses, e.g. torch .data_ptr()) --
+    def direct_dev(self, params, n_seg, n_nodes, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, jac):
+        self._ck(lib().lto_direct_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(nstate), int(nsteps), _ptr(Xa),
+                                      _ptr(Xb), _ptr(ua), _ptr(ub), _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status),
+                                      _ptr(jac)))
+
+    def indirect_dev(self, params, n_seg, n_nodes, ndim, x0, t0, t1, x_target, thrustLimit, rho, defect, status, nsteps_out, phi):
+        self._ck(lib().lto_indirect_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(ndim), _ptr(x0), _ptr(t0),
+                                        _ptr(t1), _ptr(x_target), _ptr(thrustLimit), _ptr(rho), _ptr(defect), _ptr(status),
+                                        _ptr(nsteps_out), _ptr(phi)))

@@ -1,0 +1,450 @@
+// lto_capi.cu -- the C ABI of liblto_b200.so (include/lto_b200.h): handle, device
+// scratch, host<->device pipelining and kernel dispatch.  No torch, no C++ types
+// across the boundary, no exceptions, no CPU fallback.
+#include "../../include/lto_b200.h"
+#include "lto_internal.h"
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+#include <algorithm>
+
+using namespace lto;
+
+static char g_err[512] = "";
+
+struct lto_handle {
+    int device;
+    int n_sm;
+    cudaStream_t s_compute, s_copy;
+    cudaEvent_t ev_in, ev_t0, ev_t1;
+    cudaEvent_t ev_chunk[8];
+    void* d_in; size_t d_in_cap;
+    void* d_out; size_t d_out_cap;
+    int64_t launches;
+    double last_ms;
+    char err[512];
+};
+
+static int fail(lto_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    if (h) snprintf(h->err, sizeof h->err, "%s", buf);
+    return code;
+}
+#define CK(h, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(h, LTO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+static int ensure(lto_handle* h, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) { cudaError_t e = cudaFree(*p); *p = nullptr; *cap = 0; if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
+    size_t want = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) { *p = nullptr; return fail(h, LTO_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); }
+    *cap = want;
+    return 0;
+}
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" {
+
+int lto_version(void) { return LTO_B200_VERSION; }
+
+void lto_direct_params_default(lto_direct_params* p) {
+    memset(p, 0, sizeof *p);
+    p->MU = 0.012150585609624037; p->DU = 384747.96285603708; p->TU = 375699.81732246041;   // LowThrustOpt.jl:24-26
+    p->Isp = 2000.0; p->g0 = 9.81; p->default_mass = 1000.0; p->tol = 1e-13;
+    p->mode = LTO_FIXED; p->err_norm = LTO_NORM_STATE; p->max_attempts = 0; p->kernel = LTO_KERNEL_AUTO;
+}
+void lto_indirect_params_default(lto_indirect_params* p) {
+    memset(p, 0, sizeof *p);
+    p->MU = 0.012150585609624037; p->DU = 384747.96285603708; p->TU = 375699.81732246041;
+    p->thrustLimit = 0.05; p->mass = 1000.0; p->time_direction = 1.0; p->p = 1.0; p->rho = 1.0;
+    p->Isp = 2000.0; p->g0 = 9.81; p->reltol = 1e-13; p->abstol = 1e-13;                      // multiShoot_CRTBP_indirect.jl:79
+    p->controller = LTO_CTRL_RMS; p->err_norm = LTO_NORM_STATE_SENS; p->max_attempts = 0; p->kernel = LTO_KERNEL_AUTO;
+}
+
+int lto_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lto_init(int device, lto_handle** out) {
+    if (!out) return fail(nullptr, LTO_ERR_ARG, "lto_init: null handle pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, LTO_ERR_NODEVICE, "lto_init: no CUDA device (%s); liblto_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, LTO_ERR_ARG, "lto_init: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, LTO_ERR_NODEVICE, "lto_init: device %d is sm_%d%d; this library carries sm_100a code only", device,
+                    prop.major, prop.minor);
+    CK(nullptr, cudaSetDevice(device));
+    lto_handle* h = (lto_handle*)calloc(1, sizeof(lto_handle));
+    if (!h) return fail(nullptr, LTO_ERR_NOMEM, "lto_init: out of host memory");
+    h->device = device; h->n_sm = prop.multiProcessorCount;
+    CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    CK(h, cudaEventCreate(&h->ev_t0));
+    CK(h, cudaEventCreate(&h->ev_t1));
+    for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    *out = h;
+    return LTO_SUCCESS;
+}
+
+void lto_destroy(lto_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_out) cudaFree(h->d_out);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
+    cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
+    cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
+    free(h);
+}
+
+const char* lto_last_error(const lto_handle* h) { return h ? h->err : g_err; }
+
+void* lto_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void lto_host_free(void* p) { if (p) cudaFreeHost(p); }
+int64_t lto_kernel_launches(const lto_handle* h) { return h ? h->launches : 0; }
+double lto_last_kernel_ms(const lto_handle* h) { return h ? h->last_ms : 0.0; }
+void* lto_stream(lto_handle* h) { return h ? (void*)h->s_compute : nullptr; }
+int lto_sync(lto_handle* h) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    return LTO_SUCCESS;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// parameter translation
+// ---------------------------------------------------------------------------
+static int make_direct(lto_handle* h, const lto_direct_params* p, int nstate, int nsteps, DirectArgs* a) {
+    if (!p) return fail(h, LTO_ERR_ARG, "null params");
+    if (nstate != 6 && nstate != 7) return fail(h, LTO_ERR_ARG, "nstate must be 6 or 7 (got %d)", nstate);
+    if (p->mode != LTO_FIXED && p->mode != LTO_ADAPTIVE) return fail(h, LTO_ERR_ARG, "bad mode %d", p->mode);
+    if (p->mode == LTO_FIXED && nsteps < 2) return fail(h, LTO_ERR_ARG, "nsteps must be >= 2 (got %d)", nsteps);
+    const double g0 = p->g0 > 0 ? p->g0 : 9.81;
+    a->c.mu = p->MU; a->c.m1 = 1.0 - p->MU;
+    a->c.kthr = p->TU * p->TU / p->DU / 1e3;
+    a->c.cmdot = p->TU / (p->Isp * g0);
+    a->c.default_mass = p->default_mass > 0 ? p->default_mass : 1000.0;
+    a->cfg.mode = p->mode; a->cfg.nsteps = nsteps; a->cfg.tol = p->tol > 0 ? p->tol : 1e-13;
+    a->cfg.err_norm = p->err_norm; a->cfg.max_attempts = p->max_attempts > 0 ? p->max_attempts : 100000;
+    return 0;
+}
+static int make_indirect(lto_handle* h, const lto_indirect_params* p, int ndim, bool sens, IndirectArgs* a) {
+    if (!p) return fail(h, LTO_ERR_ARG, "null params");
+    if (ndim != 12 && ndim != 14) return fail(h, LTO_ERR_ARG, "ndim must be 12 or 14 (got %d)", ndim);
+    if (!(p->p == 0.0 || p->p >= 1.0)) return fail(h, LTO_ERR_ARG, "Invalid value of p!");   // CRTBP_stateCostate_deriv.jl:52
+    const double g0 = p->g0 > 0 ? p->g0 : 9.81;
+    a->c.mu = p->MU; a->c.m1 = 1.0 - p->MU;
+    a->c.kthr = p->TU * p->TU / p->DU / 1e3;
+    a->c.thrustLimit = p->thrustLimit; a->c.mass = p->mass; a->c.omega = p->time_direction;
+    a->c.p = p->p; a->c.rho = p->rho;
+    a->c.cm = p->TU / (a->c.kthr * (p->Isp > 0 ? p->Isp : 2000.0) * g0);
+    a->cfg.atol = p->abstol > 0 ? p->abstol : 1e-13; a->cfg.rtol = p->reltol > 0 ? p->reltol : 1e-13;
+    a->cfg.controller = p->controller; a->cfg.err_norm = sens ? p->err_norm : 0;
+    a->cfg.max_attempts = p->max_attempts > 0 ? p->max_attempts : 100000;
+    return 0;
+}
+
+static int dispatch_direct(lto_handle* h, const DirectArgs& a, int nstate, int kernel) {
+    int nl = 0;
+    cudaError_t e = cudaErrorNotSupported;
+    if (kernel != LTO_KERNEL_GENERIC) e = launch_direct_fast(a, nstate, h->s_compute, &nl);
+    if (e == cudaErrorNotSupported) {
+        if (kernel == LTO_KERNEL_FAST) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
+        e = launch_direct_generic(a, nstate, h->s_compute, &nl);
+    }
+    h->launches += nl;
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "direct kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+static int dispatch_indirect(lto_handle* h, const IndirectArgs& a, int ndim, int kernel) {
+    int nl = 0;
+    cudaError_t e = cudaErrorNotSupported;
+    if (kernel != LTO_KERNEL_GENERIC) e = launch_indirect_fast(a, ndim, h->s_compute, &nl);
+    if (e == cudaErrorNotSupported) {
+        if (kernel == LTO_KERNEL_FAST) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
+        e = launch_indirect_generic(a, ndim, h->s_compute, &nl);
+    }
+    h->launches += nl;
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "indirect kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Chunk size (segments) of the compute / D2H pipeline of the host entry points.
+static long long pick_chunk(long long n_seg, size_t out_bytes_per_seg) {
+    if (n_seg * (long long)out_bytes_per_seg <= (8ll << 20)) return n_seg;       // small: one shot
+    long long c = (long long)((16ll << 20) / (long long)out_bytes_per_seg);      // ~16 MiB of output per chunk
+    c = std::max<long long>(c, 2048);
+    c = (c + 2047) / 2048 * 2048;
+    return std::min(c, n_seg);
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer direct call
+// ---------------------------------------------------------------------------
+static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_seg, int npt, long long n_nodes_total,
+                       int nstate, int nsteps, const double* Xa, const double* Xb, const double* ua, const double* ub,
+                       const double* ta, const double* tb, double* defect, double* errors, int32_t* status, double* jac,
+                       bool want_jac) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (n_seg < 0) return fail(h, LTO_ERR_ARG, "negative segment count");
+    DirectArgs a; memset(&a, 0, sizeof a);
+    int rc = make_direct(h, p, nstate, nsteps, &a);
+    if (rc) return rc;
+    if (n_seg == 0) return LTO_SUCCESS;
+    if (!Xa || !ua || !ta || !defect || (npt == 0 && (!Xb || !ub || !tb)) || (want_jac && !jac))
+        return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    const int NS = nstate, NV = 2 * (NS + 3);
+    const long long rows = npt > 0 ? n_nodes_total : n_seg;       // rows of each input array
+    // ---- device input block
+    const size_t bX = al(rows * NS * 8), bU = al(rows * 3 * 8), bT = al(rows * 8);
+    const size_t in_bytes = (npt > 0 ? 1 : 2) * (bX + bU + bT);
+    rc = ensure(h, &h->d_in, &h->d_in_cap, in_bytes); if (rc) return rc;
+    char* di = (char*)h->d_in;
+    double* dXa = (double*)di; di += bX; double* dua = (double*)di; di += bU; double* dta = (double*)di; di += bT;
+    double *dXb, *dub, *dtb;
+    if (npt > 0) { dXb = dXa + NS; dub = dua + 3; dtb = dta + 1; }
+    else { dXb = (double*)di; di += bX; dub = (double*)di; di += bU; dtb = (double*)di; di += bT; }
+    // ---- device output block
+    const size_t bD = al(n_seg * NS * 8), bE = al(n_seg * 8), bS = al(n_seg * 4), bJ = want_jac ? al(n_seg * NS * NV * 8) : 0;
+    rc = ensure(h, &h->d_out, &h->d_out_cap, bD + bE + bS + bJ); if (rc) return rc;
+    char* dq = (char*)h->d_out;
+    double* dD = (double*)dq; dq += bD; double* dE = (double*)dq; dq += bE; int32_t* dS = (int32_t*)dq; dq += bS;
+    double* dJ = want_jac ? (double*)dq : nullptr;
+    // ---- H2D
+    CK(h, cudaMemcpyAsync(dXa, Xa, rows * NS * 8, cudaMemcpyHostToDevice, h->s_copy));
+    CK(h, cudaMemcpyAsync(dua, ua, rows * 3 * 8, cudaMemcpyHostToDevice, h->s_copy));
+    CK(h, cudaMemcpyAsync(dta, ta, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
+    if (npt == 0) {
+        CK(h, cudaMemcpyAsync(dXb, Xb, rows * NS * 8, cudaMemcpyHostToDevice, h->s_copy));
+        CK(h, cudaMemcpyAsync(dub, ub, rows * 3 * 8, cudaMemcpyHostToDevice, h->s_copy));
+        CK(h, cudaMemcpyAsync(dtb, tb, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
+    }
+    CK(h, cudaEventRecord(h->ev_in, h->s_copy));
+    CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_in, 0));
+    CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    // ---- chunked compute + D2H pipeline
+    const size_t per_seg = (size_t)NS * 8 + 8 + 4 + (want_jac ? (size_t)NS * NV * 8 : 0);
+    long long chunk = pick_chunk(n_seg, per_seg);
+    if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }   // whole trajectories
+    int ci = 0;
+    for (long long s0 = 0; s0 < n_seg; s0 += chunk, ++ci) {
+        const long long ns = std::min(chunk, n_seg - s0);
+        const long long r0 = lto_node_a(s0, npt);
+        a.Xa = dXa + r0 * NS; a.Xb = dXb + r0 * NS; a.ua = dua + r0 * 3; a.ub = dub + r0 * 3; a.ta = dta + r0; a.tb = dtb + r0;
+        a.defect = dD + s0 * NS; a.errors = dE + s0; a.status = dS + s0; a.jac = want_jac ? dJ + s0 * NS * NV : nullptr;
+        a.n_seg = ns; a.npt = npt;
+        rc = dispatch_direct(h, a, nstate, p->kernel); if (rc) return rc;
+        cudaEvent_t ev = h->ev_chunk[ci & 7];
+        CK(h, cudaEventRecord(ev, h->s_compute));
+        CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
+        CK(h, cudaMemcpyAsync(defect + s0 * NS, dD + s0 * NS, ns * NS * 8, cudaMemcpyDeviceToHost, h->s_copy));
+        if (errors) CK(h, cudaMemcpyAsync(errors + s0, dE + s0, ns * 8, cudaMemcpyDeviceToHost, h->s_copy));
+        if (status) CK(h, cudaMemcpyAsync(status + s0, dS + s0, ns * 4, cudaMemcpyDeviceToHost, h->s_copy));
+        if (want_jac) CK(h, cudaMemcpyAsync(jac + s0 * NS * NV, dJ + s0 * NS * NV, ns * NS * NV * 8, cudaMemcpyDeviceToHost, h->s_copy));
+    }
+    CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_copy));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    return LTO_SUCCESS;
+}
+
+static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long n_seg, int npt, long long n_nodes_total,
+                         long long n_traj, int ndim, const double* x0, const double* t0, const double* t1,
+                         const double* x_target, const double* tl_arr, const double* rho_arr, double* defect,
+                         int32_t* status, int32_t* nsteps_out, double* phi, bool want_jac) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (n_seg < 0) return fail(h, LTO_ERR_ARG, "negative segment count");
+    IndirectArgs a; memset(&a, 0, sizeof a);
+    int rc = make_indirect(h, p, ndim, want_jac, &a);
+    if (rc) return rc;
+    if (n_seg == 0) return LTO_SUCCESS;
+    if (!x0 || !t0 || !defect || (npt == 0 && !t1) || (want_jac && !phi)) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    const int ND = ndim;
+    const long long rows = npt > 0 ? n_nodes_total : n_seg;
+    const long long prow = npt > 0 ? n_traj : n_seg;              // rows of the per-segment/per-trajectory parameter arrays
+    const bool sep_target = (npt == 0 && x_target != nullptr);
+    const size_t bX = al(rows * ND * 8), bT = al(rows * 8), bP = al(prow * 8);
+    const size_t in_bytes = bX + bT + (npt == 0 ? bT : 0) + (sep_target ? bX : 0) + (tl_arr ? bP : 0) + (rho_arr ? bP : 0);
+    rc = ensure(h, &h->d_in, &h->d_in_cap, in_bytes); if (rc) return rc;
+    char* di = (char*)h->d_in;
+    double* dX = (double*)di; di += bX; double* dT0 = (double*)di; di += bT;
+    double* dT1; if (npt > 0) dT1 = dT0 + 1; else { dT1 = (double*)di; di += bT; }
+    double* dXT = nullptr; if (npt > 0) dXT = dX + ND; else if (sep_target) { dXT = (double*)di; di += bX; }
+    double* dTL = nullptr; if (tl_arr) { dTL = (double*)di; di += bP; }
+    double* dRH = nullptr; if (rho_arr) { dRH = (double*)di; di += bP; }
+    const size_t bD = al(n_seg * ND * 8), bS = al(n_seg * 4), bN = al(n_seg * 8), bJ = want_jac ? al(n_seg * ND * ND * 8) : 0;
+    rc = ensure(h, &h->d_out, &h->d_out_cap, bD + bS + bN + bJ); if (rc) return rc;
+    char* dq = (char*)h->d_out;
+    double* dD = (double*)dq; dq += bD; int32_t* dS = (int32_t*)dq; dq += bS; int32_t* dN = (int32_t*)dq; dq += bN;
+    double* dJ = want_jac ? (double*)dq : nullptr;
+    CK(h, cudaMemcpyAsync(dX, x0, rows * ND * 8, cudaMemcpyHostToDevice, h->s_copy));
+    CK(h, cudaMemcpyAsync(dT0, t0, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
+    if (npt == 0) CK(h, cudaMemcpyAsync(dT1, t1, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
+    if (sep_target) CK(h, cudaMemcpyAsync(dXT, x_target, rows * ND * 8, cudaMemcpyHostToDevice, h->s_copy));
+    if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_copy));
+    if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_copy));
+    CK(h, cudaEventRecord(h->ev_in, h->s_copy));
+    CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_in, 0));
+    CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    const size_t per_seg = (size_t)ND * 8 + 12 + (want_jac ? (size_t)ND * ND * 8 : 0);
+    long long chunk = pick_chunk(n_seg, per_seg);
+    if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }
+    int ci = 0;
+    for (long long s0 = 0; s0 < n_seg; s0 += chunk, ++ci) {
+        const long long ns = std::min(chunk, n_seg - s0);
+        const long long r0 = lto_node_a(s0, npt);
+        const long long p0 = lto_traj_of(s0, npt);
+        a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
+        a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
+        a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
+        a.n_seg = ns; a.npt = npt;
+        rc = dispatch_indirect(h, a, ndim, p->kernel); if (rc) return rc;
+        cudaEvent_t ev = h->ev_chunk[ci & 7];
+        CK(h, cudaEventRecord(ev, h->s_compute));
+        CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
+        CK(h, cudaMemcpyAsync(defect + s0 * ND, dD + s0 * ND, ns * ND * 8, cudaMemcpyDeviceToHost, h->s_copy));
+        if (status) CK(h, cudaMemcpyAsync(status + s0, dS + s0, ns * 4, cudaMemcpyDeviceToHost, h->s_copy));
+        if (nsteps_out) CK(h, cudaMemcpyAsync(nsteps_out + 2 * s0, dN + 2 * s0, ns * 8, cudaMemcpyDeviceToHost, h->s_copy));
+        if (want_jac) CK(h, cudaMemcpyAsync(phi + s0 * ND * ND, dJ + s0 * ND * ND, ns * ND * ND * 8, cudaMemcpyDeviceToHost, h->s_copy));
+    }
+    CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_copy));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    return LTO_SUCCESS;
+}
+
+extern "C" {
+
+int lto_direct_defect(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps, const double* Xa,
+                      const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,
+                      double* defect, double* errors, int32_t* status) {
+    return direct_host(h, p, n_seg, 0, 0, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, nullptr, false);
+}
+int lto_direct_defect_jac(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps,
+                          const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta,
+                          const double* tb, double* defect, double* errors, int32_t* status, double* jac) {
+    return direct_host(h, p, n_seg, 0, 0, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, jac, true);
+}
+int lto_direct_defect_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate, int nsteps,
+                           const double* X_all, const double* u_all, const double* t_TU, double* defect, double* errors,
+                           int32_t* status) {
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    return direct_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, nstate, nsteps, X_all, nullptr, u_all, nullptr,
+                       t_TU, nullptr, defect, errors, status, nullptr, false);
+}
+int lto_direct_defect_jac_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate,
+                               int nsteps, const double* X_all, const double* u_all, const double* t_TU, double* defect,
+                               double* errors, int32_t* status, double* jac) {
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    return direct_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, nstate, nsteps, X_all, nullptr, u_all, nullptr,
+                       t_TU, nullptr, defect, errors, status, jac, true);
+}
+
+int lto_indirect_defect(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim, const double* x0,
+                        const double* t0, const double* t1, const double* x_target, const double* thrustLimit_seg,
+                        const double* rho_seg, double* defect, int32_t* status, int32_t* nsteps_out) {
+    return indirect_host(h, p, n_seg, 0, 0, 0, ndim, x0, t0, t1, x_target, thrustLimit_seg, rho_seg, defect, status, nsteps_out,
+                         nullptr, false);
+}
+int lto_indirect_defect_jac(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim, const double* x0,
+                            const double* t0, const double* t1, const double* x_target, const double* thrustLimit_seg,
+                            const double* rho_seg, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    return indirect_host(h, p, n_seg, 0, 0, 0, ndim, x0, t0, t1, x_target, thrustLimit_seg, rho_seg, defect, status, nsteps_out,
+                         phi, true);
+}
+int lto_indirect_defect_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
+                             const double* XC_all, const double* t_TU, const double* thrustLimit_traj, const double* rho_traj,
+                             double* defect, int32_t* status, int32_t* nsteps_out) {
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    return indirect_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, n_traj, ndim, XC_all, t_TU, nullptr, nullptr,
+                         thrustLimit_traj, rho_traj, defect, status, nsteps_out, nullptr, false);
+}
+int lto_indirect_defect_jac_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
+                                 const double* XC_all, const double* t_TU, const double* thrustLimit_traj,
+                                 const double* rho_traj, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    return indirect_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, n_traj, ndim, XC_all, t_TU, nullptr, nullptr,
+                         thrustLimit_traj, rho_traj, defect, status, nsteps_out, phi, true);
+}
+
+int lto_direct_dev(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int n_nodes, int nstate, int nsteps,
+                   const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,
+                   double* defect, double* errors, int32_t* status, double* jac) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    DirectArgs a; memset(&a, 0, sizeof a);
+    int rc = make_direct(h, p, nstate, nsteps, &a); if (rc) return rc;
+    if (n_seg <= 0) return n_seg == 0 ? LTO_SUCCESS : fail(h, LTO_ERR_ARG, "negative segment count");
+    if (n_nodes == 1 || n_nodes < 0) return fail(h, LTO_ERR_ARG, "n_nodes must be 0 (pairs) or >= 2");
+    if (!Xa || !ua || !ta || !defect || (n_nodes == 0 && (!Xb || !ub || !tb))) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    a.Xa = Xa; a.ua = ua; a.ta = ta;
+    if (n_nodes > 0) { a.Xb = Xa + nstate; a.ub = ua + 3; a.tb = ta + 1; } else { a.Xb = Xb; a.ub = ub; a.tb = tb; }
+    a.defect = defect; a.errors = errors; a.status = status; a.jac = jac; a.n_seg = n_seg; a.npt = n_nodes;
+    return dispatch_direct(h, a, nstate, p->kernel);
+}
+int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int n_nodes, int ndim, const double* x0,
+                     const double* t0, const double* t1, const double* x_target, const double* thrustLimit_arr,
+                     const double* rho_arr, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    IndirectArgs a; memset(&a, 0, sizeof a);
+    int rc = make_indirect(h, p, ndim, phi != nullptr, &a); if (rc) return rc;
+    if (n_seg <= 0) return n_seg == 0 ? LTO_SUCCESS : fail(h, LTO_ERR_ARG, "negative segment count");
+    if (n_nodes == 1 || n_nodes < 0) return fail(h, LTO_ERR_ARG, "n_nodes must be 0 (pairs) or >= 2");
+    if (!x0 || !t0 || !defect || (n_nodes == 0 && !t1)) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    a.x0 = x0; a.t0 = t0;
+    if (n_nodes > 0) { a.t1 = t0 + 1; a.x_target = x0 + ndim; } else { a.t1 = t1; a.x_target = x_target; }
+    a.thrustLimit_arr = thrustLimit_arr; a.rho_arr = rho_arr;
+    a.defect = defect; a.status = status; a.nsteps_out = nsteps_out; a.phi = phi; a.n_seg = n_seg; a.npt = n_nodes;
+    return dispatch_indirect(h, a, ndim, p->kernel);
+}
+
+int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms_out) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    CK(h, cudaSetDevice(h->device));
+    int rc = ensure(h, &h->d_out, &h->d_out_cap, 4096); if (rc) return rc;
+    long long nthreads = 0; int fmas = 0;
+    cudaError_t e = launch_fp64_probe(16, (double*)h->d_out, h->n_sm, h->s_compute, &nthreads, &fmas);   // warm-up
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
+    CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    e = launch_fp64_probe(iters, (double*)h->d_out, h->n_sm, h->s_compute, &nthreads, &fmas);
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "probe launch: %s", cudaGetErrorString(e));
+    CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    h->launches += 2;
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    if (ms_out) *ms_out = ms;
+    if (flops_per_s) *flops_per_s = 2.0 * (double)nthreads * (double)iters * (double)fmas / ((double)ms * 1e-3);
+    return LTO_SUCCESS;
+}
+
+}  // extern "C"

@@ -1,0 +1,18 @@
+// lto_kernels_fast.cu -- dispatch of the throughput kernels (filled in per configuration).
+#include "lto_internal.h"
+
+namespace lto {
+
+cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch);
+
+cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
+    *n_launch = 0;
+    return cudaErrorNotSupported;
+}
+
+cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
+    *n_launch = 0;
+    return cudaErrorNotSupported;
+}
+
+}  // namespace lto

@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/lto_b200.h declares, and
+refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from lowthrustopt_b200 import build, capi as c
+    build.build_lib()
+    return c
+
+
+def test_exports_every_declared_symbol(capi):
+    hdr = open(os.path.join(ROOT, "include", "lto_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lto_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 24
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert set(capi.EXPORTS) == declared
+    assert L.lto_version() == 100
+
+
+def test_struct_layout_matches_header(capi):
+    p = capi.direct_params()
+    assert (p.MU, p.DU, p.TU) == (0.012150585609624037, 384747.96285603708, 375699.81732246041)   # LowThrustOpt.jl:24-26
+    assert p.g0 == 9.81 and p.default_mass == 1000.0 and p.mode == capi.LTO_FIXED
+    q = capi.indirect_params()
+    assert q.reltol == 1e-13 and q.abstol == 1e-13 and q.err_norm == capi.LTO_NORM_STATE_SENS
+    assert C.sizeof(capi.DirectParams) == 7 * 8 + 4 * 4 and C.sizeof(capi.IndirectParams) == 12 * 8 + 4 * 4
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert capi.lib().lto_device_count() == 0
+    with pytest.raises(capi.LtoError, match="no CPU fallback"):
+        capi.Handle(0)
+    from lowthrustopt_b200 import direct
+    direct.set_handle(None)
+    with pytest.raises(capi.LtoError):
+        direct.defectCalc(np.zeros((6, 3)), np.zeros((3, 3)), np.arange(3.0), 6, 3, 10, 2000.0)
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ (only tests, smoke() and bench.py's cpu legs may)."""
+    pkg = os.path.join(ROOT, "lowthrustopt_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(d, f)).read()
+                assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(d, f)
