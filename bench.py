@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- segment-propagations/s (fp64 state + STM) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic segments.  Default
+workload (BASELINE.json configs[2]): 65,536 direct-method segments per GPU, 7-state + STM
++ control sensitivities, the reference's FIXED RKF7(8) grid (nsteps = 10, what
+multiShoot_CRTBP_direct actually runs; `--workload direct7_adaptive` runs the ode78
+controller instead).  Weak scaling: every rank owns its own 65,536 segments, no data-path
+collective (segments are independent).
+
+Prints ONE JSON line (rank 0).  `value` times the kernel(s) with inputs resident in HBM
+(CUDA events on the launching stream, L2 flushed between iterations); `e2e` times the
+C-ABI host-buffer call (pinned host memory, H2D + kernels + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Algorithmic FLOPs per unit (sparsity-exploiting minimal formulation; DESIGN.md "Measurement")
+FLOPS_PER_SEG = {"direct7": 284040.0, "direct6": 217836.0}
+FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 55000.0}
+# Algorithmic HBM bytes per unit
+BYTES_PER_SEG = {"direct7": 1360.0, "direct6": (2 * 6 + 6 + 2 + 6 + 1 + 6 * 18) * 8.0, 12: 1360.0, 14: 1808.0}
+
+WORKLOADS = ["direct7_fixed", "direct6_fixed", "direct7_adaptive", "indirect12", "indirect14"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="direct7_fixed", choices=WORKLOADS)
+    ap.add_argument("--n-seg", type=int, default=0, help="segments per GPU (default: 65536 direct / 131072 indirect)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    return ap.parse_args()
+
+
+def make_batch(workload, n_seg, rank):
+    from lowthrustopt_b200 import synthetic as S
+    if workload.startswith("direct"):
+        ns = 7 if workload.startswith("direct7") else 6
+        return S.direct_batch(n_seg, nstate=ns, seed=20180001 + rank)
+    nd = 12 if workload == "indirect12" else 14
+    return S.indirect_batch(n_seg, ndim=nd, seed=20180002 + rank)
+
+
+class ClockSampler(threading.Thread):
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index; self.rows = []; self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
+def cpu_reference_pass(workload, batch, n, nthreads):
+    """One pass of the REFERENCE ALGORITHM on the host: direct = defectCalc + forward-FD jacobianCalc
+    (multiShoot_CRTBP_direct.jl:66-143, pert 1e-8, both legs re-propagated per variable); indirect = dual numbers
+    through the adaptive solver (multiShoot_CRTBP_indirect.jl:93-124).  Returns seconds."""
+    from oracle import oracle as O
+    t = time.perf_counter()
+    if workload.startswith("direct"):
+        sl = {k: v[:n] for k, v in batch.items()}
+        mode = 1 if workload.endswith("adaptive") else 0
+        d, e, st, _ = O.direct_defect(sl["Xa"], sl["Xb"], sl["ua"], sl["ub"], sl["ta"], sl["tb"], mode=mode, nthreads=nthreads)
+        O.direct_jac_fd(sl["Xa"], sl["Xb"], sl["ua"], sl["ub"], sl["ta"], sl["tb"], d, mode=mode, nthreads=nthreads)
+    else:
+        ip = O.iparams(0.05, p=1.0, rho=1.0)
+        O.indirect_prop_jac(batch["x0"][:n], batch["t0"][:n], batch["t1"][:n], ip, nthreads=nthreads)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(workload, batch, sample):
+    from oracle import oracle as O
+    O.build()
+    nthreads = O.num_threads()
+    n = min(sample, len(next(iter(batch.values()))))
+    cpu_reference_pass(workload, batch, min(n, 256), nthreads)        # warm the thread pool
+    dt = cpu_reference_pass(workload, batch, n, nthreads)
+    return {"value": n / dt, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
+            "sample": "%d segments of the same batch, reference algorithm (%s) restated in C++ (oracle/), OpenMP over segments, %.1f s"
+                      % (n, "defectCalc + forward-FD jacobianCalc, pert 1e-8" if workload.startswith("direct") else
+                         "dual numbers through the adaptive RK8", dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    nthreads = O.num_threads()
+    n_seg = args.n_seg or (65536 if args.workload.startswith("direct") else 131072)
+    sample = args.cpu_sample or (16384 if args.workload.startswith("direct") else 4096)
+    batch = make_batch(args.workload, sample, 0)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_pass(args.workload, batch, min(sample, 512), nthreads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_reference_pass(args.workload, batch, sample, nthreads)
+    v = sample * args.steps / t
+    line = {"impl": "reference", "metric": "segment-propagations/s (fp64 state+STM)", "value": v, "unit": "segment-propagations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, n_seg, args.gpus),
+            "cpu_baseline": {"value": v, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
+                             "sample": "%d segments per step; the reference is Julia (not installed here or on the GPU box), so this is its "
+                                       "algorithm restated in C++ (oracle/), OpenMP over segments on all host threads" % sample},
+            "e2e": {"value": v, "unit": "segment-propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n_seg, n_gpus):
+    desc = {
+        "direct7_fixed": "BASELINE configs[2]: synthetic batch of 65,536 direct-method segments per GPU, nstate 7 + STM + control "
+                         "sensitivities (7x20 Jacobian block), FIXED RKF7(8) grid nsteps=10 both legs (reference ode7_8 path)",
+        "direct6_fixed": "direct-method segments, nstate 6 (the demo's size), FIXED RKF7(8) nsteps=10",
+        "direct7_adaptive": "BASELINE configs[2] with the ode78 adaptive controller, tol 1e-13",
+        "indirect12": "BASELINE configs[3] (12-dim reference RHS): perturbed indirect-shooting guesses, adaptive RK8 1e-13, 12x12 STM",
+        "indirect14": "BASELINE configs[3] (14-dim extension): adaptive RK8 1e-13, 14x14 STM",
+    }[workload]
+    return {"workload": workload, "description": desc, "segments_per_gpu": n_seg, "segments_total": n_seg * n_gpus,
+            "l2": "flushed between timed iterations (256 MiB write)", "parallelism": "segments sharded across %d GPU(s), no collective" % n_gpus}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from lowthrustopt_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    h = capi.Handle(local)
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    kern = {"auto": capi.LTO_KERNEL_AUTO, "generic": capi.LTO_KERNEL_GENERIC, "fast": capi.LTO_KERNEL_FAST}[args.kernel]
+
+    wl = args.workload
+    direct = wl.startswith("direct")
+    n_seg = args.n_seg or (65536 if direct else 131072)
+    batch = make_batch(wl, n_seg, rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    if direct:
+        ns = 7 if wl.startswith("direct7") else 6
+        nv = 2 * (ns + 3)
+        p = capi.direct_params(mode=capi.LTO_ADAPTIVE if wl.endswith("adaptive") else capi.LTO_FIXED, tol=1e-13, kernel=kern)
+        din = {k: torch.from_numpy(v).to(dev) for k, v in batch.items()}
+        d_def = torch.empty((n_seg, ns), dtype=torch.float64, device=dev)
+        d_err = torch.empty(n_seg, dtype=torch.float64, device=dev)
+        d_st = torch.empty(n_seg, dtype=torch.int32, device=dev)
+        d_jac = torch.empty((n_seg, nv, ns), dtype=torch.float64, device=dev)
+
+        def step_dev():
+            h.direct_dev(p, n_seg, 0, ns, 10, din["Xa"].data_ptr(), din["Xb"].data_ptr(), din["ua"].data_ptr(), din["ub"].data_ptr(),
+                         din["ta"].data_ptr(), din["tb"].data_ptr(), d_def.data_ptr(), d_err.data_ptr(), d_st.data_ptr(), d_jac.data_ptr())
+        # e2e: pinned host buffers through the host-pointer C ABI
+        pin_in = {k: capi.PinnedBuffer(v.shape) for k, v in batch.items()}
+        for k, v in batch.items():
+            pin_in[k].array[...] = v
+        pin_out = {"defect": capi.PinnedBuffer((n_seg, ns)), "errors": capi.PinnedBuffer((n_seg,)),
+                   "status": capi.PinnedBuffer((n_seg,), np.int32), "jac": capi.PinnedBuffer((n_seg, nv, ns))}
+        out_arrays = {k: b.array for k, b in pin_out.items()}
+        a_in = {k: b.array for k, b in pin_in.items()}
+
+        def step_e2e():
+            r = h.direct(a_in["Xa"], a_in["Xb"], a_in["ua"], a_in["ub"], a_in["ta"], a_in["tb"], nsteps=10, params=p, jac=True, out=out_arrays)
+            return float(r["defect"][0, 0])
+        h2d = sum(v.nbytes for v in batch.values())
+        d2h = sum(b.array.nbytes for b in pin_out.values())
+        flops_unit = FLOPS_PER_SEG["direct7" if ns == 7 else "direct6"]
+        bytes_unit = BYTES_PER_SEG["direct7" if ns == 7 else "direct6"]
+        attempted = None
+    else:
+        nd = 12 if wl == "indirect12" else 14
+        p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05, kernel=kern)
+        dx0 = torch.from_numpy(batch["x0"]).to(dev); dt0 = torch.from_numpy(batch["t0"]).to(dev); dt1 = torch.from_numpy(batch["t1"]).to(dev)
+        d_def = torch.empty((n_seg, nd), dtype=torch.float64, device=dev)
+        d_st = torch.empty(n_seg, dtype=torch.int32, device=dev)
+        d_ns = torch.empty((n_seg, 2), dtype=torch.int32, device=dev)
+        d_phi = torch.empty((n_seg, nd, nd), dtype=torch.float64, device=dev)
+
+        def step_dev():
+            h.indirect_dev(p, n_seg, 0, nd, dx0.data_ptr(), dt0.data_ptr(), dt1.data_ptr(), None, None, None, d_def.data_ptr(),
+                           d_st.data_ptr(), d_ns.data_ptr(), d_phi.data_ptr())
+        pin_in = {k: capi.PinnedBuffer(v.shape) for k, v in batch.items()}
+        for k, v in batch.items():
+            pin_in[k].array[...] = v
+        a_in = {k: b.array for k, b in pin_in.items()}
+
+        def step_e2e():
+            r = h.indirect(a_in["x0"], a_in["t0"], a_in["t1"], params=p, jac=True)
+            return float(r["defect"][0, 0])
+        h2d = sum(v.nbytes for v in batch.values())
+        d2h = n_seg * (nd * 8 + 4 + 8 + nd * nd * 8)
+        flops_unit = None
+        bytes_unit = BYTES_PER_SEG[nd]
+        attempted = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    h.sync()
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    time.sleep(0.3)
+    # ---- device-resident timing: per-iteration event pairs on the launching stream, L2 flushed in between
+    l0 = h.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            evs[i][0].record()
+            step_dev()
+            evs[i][1].record()
+    h.sync()
+    barrier()
+    launches = h.launches - l0
+    times = [a.elapsed_time(b) for a, b in evs]
+    t_total = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_total.item()) / args.steps
+    value = n_seg * world / (ms_per_step * 1e-3)
+    if not direct:
+        nst = d_ns.cpu().numpy()
+        attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
+        flops_unit = FLOPS_PER_STEP_INDIRECT[nd] * attempted
+    # ---- e2e through the host-buffer C ABI
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    chk = 0.0
+    for _ in range(args.steps):
+        chk += step_e2e()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n_seg * world * args.steps / float(t_e2e.item())
+    clocks = sampler.stop()
+    # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
+    peak_burst, _ = h.fp64_peak_probe(2048)
+    peak_sust, ms_p = h.fp64_peak_probe(200000)
+    per_gpu_ms = float(np.mean(times)) / 1.0
+    achieved = flops_unit * n_seg / (per_gpu_ms * 1e-3) / 1e12
+    hbm = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = json.load(f).get("hbm_gbs")
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(wl)
+    except Exception:
+        pass
+    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_sust / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak_sust / 1e12),
+            "traffic": traffic,
+            "peak_source": "DFMA issue-rate probe (lto_fp64_peak_probe) run on this GPU in this process: sustained %.2f TFLOP/s over %.0f ms, "
+                           "burst %.2f; MEASURED_PEAKS.json carries no FP64 figure; spec 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2"
+                           % (peak_sust / 1e12, ms_p, peak_burst / 1e12),
+            "flops_per_unit": flops_unit, "units_per_launch": n_seg, "kernel_ms": per_gpu_ms,
+            "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * n_seg / (per_gpu_ms * 1e-3) / 1e9,
+                    "peak_gbs": hbm, "frac": (bytes_unit * n_seg / (per_gpu_ms * 1e-3) / 1e9 / hbm) if hbm else None}}
+    if attempted is not None:
+        roof["attempted_steps_per_segment"] = attempted
+        roof["accepted_steps_per_segment"] = accepted
+    line = {"metric": "segment-propagations/s (fp64 state+STM)", "value": value, "unit": "segment-propagations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "segment-propagations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "timing": "host wall clock around the blocking lto_*_defect_jac call, pinned host buffers, max over ranks"},
+            "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
+    if rank == 0 and not args.no_cpu_baseline:
+        sample = args.cpu_sample or (8192 if direct else 2048)
+        line["cpu_baseline"] = cpu_baseline(wl, batch, sample)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,340 @@
+// lto_direct_cw.cu -- throughput kernel for the direct method, FIXED grid (K1):
+// defectCalc + jacobianCalc of multiShoot_CRTBP_direct.jl:66-143 for a whole batch in one
+// launch, with the variational equations in place of the reference's 2(n+3) finite-
+// difference re-propagations.
+//
+// Mapping ("column-warp" layout):
+//   CTA  = 32 legs (16 segments: lane 2k = forward leg, lane 2k+1 = backward leg of one segment)
+//   warp = one column of the augmented system:  warp XW carries the state x itself,
+//          every other warp carries one column of S = [Phi | Gamma]  (n + 3 columns)
+//   lane = leg.  Nothing is ever exchanged between lanes except the final defect.
+// The state warp evaluates the nonlinear dynamics once per RK stage and leg and publishes
+// the stage's linearisation (U_xx, k/m, -k u/m^2) through shared memory; the column warps
+// apply it to their column.  The state does not depend on S, so the state warp runs one RK
+// step AHEAD of the column warps (double-buffered step records, one CTA barrier per step).
+// Stage storage: Nystrom form -- only the 3 acceleration components of each stage are
+// kept (registers), positions are rebuilt with G = B*B (lto_tableau.h).  Stage 11 is
+// needed by the error estimate only (ode.jl:892), which the reference takes over the
+// state alone (ode.jl:940-943), so column warps skip it.
+#include "lto_internal.h"
+
+namespace lto {
+
+namespace cw {
+
+constexpr int XW = 3;   // the state warp: SM sub-partition 3 hosts one warp fewer than the others
+
+template <int NS>
+struct Cfg {
+    static constexpr int NCOL = NS + 3;
+    static constexpr int NW = 1 + NCOL;
+    static constexpr int NTHREADS = 32 * NW;
+    static constexpr int SVAL = (NS == 7) ? 10 : 6;          // U[6] (+ k/m, am[3]) per stage and leg
+    static constexpr int STEP_DOUBLES = 13 * SVAL + 1;       // + h
+    static constexpr int TILE_DOUBLES = 4;                   // bm[3] per leg (+ pad)
+    static constexpr size_t SMEM = (size_t)(2 * STEP_DOUBLES + 2 * TILE_DOUBLES) * 32 * sizeof(double);
+};
+
+__device__ __forceinline__ void cta_barrier(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// State warp: one RK step of x = [r v (m)] in Nystrom form; publishes the stage
+// linearisations of this step into `rec` (lane-strided) and accumulates maxErr.
+// ---------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m, const double (&u)[3], double omega,
+                                       double mdot, double h, const EPConst& c, double* __restrict__ rec, double& maxErr) {
+    constexpr int SVAL = Cfg<NS>::SVAL;
+    const double h2 = h * h;
+    double a[13][3];
+    double ev[3] = {0.0, 0.0, 0.0}, ea[3] = {0.0, 0.0, 0.0};
+    rec[13 * SVAL * 32] = h;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+        double R[3], V[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double accv = 0.0, accr = 0.0;
+#pragma unroll
+            for (int l = 0; l < j; ++l) {
+                if (lto_tab::Bf(j, l) != 0.0) accv = fma(lto_tab::Bf(j, l), a[l][q], accv);
+                if (lto_tab::Gf(j, l) != 0.0) accr = fma(lto_tab::Gf(j, l), a[l][q], accr);
+            }
+            V[q] = (j == 0) ? v[q] : fma(h, accv, v[q]);
+            R[q] = (j == 0) ? r[q] : fma(h2, accr, fma(h * lto_tab::Cf(j), v[q], r[q]));
+        }
+        Grav g;
+        grav_eval(R[0], R[1], R[2], c.mu, c.m1, g);
+        double kom, im = 0.0;
+        if (NS == 7) {
+            const double mj = fma(h * lto_tab::Cf(j), mdot, m);
+            im = 1.0 / mj;
+            kom = c.kthr * im;
+        } else {
+            kom = c.kthr / c.default_mass;
+        }
+        double acc[3];
+        grav_accel(g, R[0], V[0], V[1], omega, acc);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) a[j][q] = fma(u[q], kom, acc[q]);
+        if (j != 10) {
+            double* w = rec + j * SVAL * 32;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) w[q * 32] = g.U[q];
+            if (NS == 7) {
+                w[6 * 32] = kom;
+                const double k2 = -kom * im;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[(7 + q) * 32] = k2 * u[q];
+            }
+        }
+        if (lto_tab::PSIf(j) != 0.0) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { ev[q] = fma(lto_tab::PSIf(j), V[q], ev[q]); ea[q] = fma(lto_tab::PSIf(j), a[j][q], ea[q]); }
+        }
+    }
+    double delta = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double sv = 0.0, sr = 0.0;
+#pragma unroll
+        for (int l = 0; l < 13; ++l) {
+            if (lto_tab::CHIf(l) != 0.0) sv = fma(lto_tab::CHIf(l), a[l][q], sv);
+            if (lto_tab::CHIBf(l) != 0.0) sr = fma(lto_tab::CHIBf(l), a[l][q], sr);
+        }
+        r[q] = fma(h2, sr, fma(h, v[q], r[q]));
+        v[q] = fma(h, sv, v[q]);
+        delta = fmax(delta, fmax(fabs(ev[q]), fabs(ea[q])));
+    }
+    if (NS == 7) m = fma(h, mdot, m);
+    delta *= fabs(h * lto_tab::ERRC);                       // ode.jl:940-943 (mass row is identically 0)
+    maxErr = fmax(maxErr, delta);                           // ode.jl:946-948
+}
+
+// ---------------------------------------------------------------------------
+// Column warp: one RK step of one column s = [s_r s_v (s_m)] of S.
+//   KIND 0: Phi column of r or v          (s_m == 0)
+//   KIND 1: Phi column of m (NS == 7)     (s_m == 1)
+//   KIND 2: Gamma column c                (forcing (k/m) e_c on s_v, bm on s_m)
+// ---------------------------------------------------------------------------
+template <int NS, int KIND>
+__device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], double& sm, double bm, const double (&ec)[3],
+                                         double omega, double kom6, const double* __restrict__ rec) {
+    constexpr int SVAL = Cfg<NS>::SVAL;
+    constexpr bool MASS = (NS == 7) && (KIND != 0);
+    const double h = rec[13 * SVAL * 32];
+    const double h2 = h * h;
+    const double w2 = 2.0 * omega;
+    double a[13][3];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+        if (j == 10) continue;
+        double R[3], V[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            double accv = 0.0, accr = 0.0;
+#pragma unroll
+            for (int l = 0; l < j; ++l) {
+                if (lto_tab::Bf(j, l) != 0.0) accv = fma(lto_tab::Bf(j, l), a[l][q], accv);
+                if (lto_tab::Gf(j, l) != 0.0) accr = fma(lto_tab::Gf(j, l), a[l][q], accr);
+            }
+            V[q] = (j == 0) ? sv[q] : fma(h, accv, sv[q]);
+            R[q] = (j == 0) ? sr[q] : fma(h2, accr, fma(h * lto_tab::Cf(j), sv[q], sr[q]));
+        }
+        const double* w = rec + j * SVAL * 32;
+        double U[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) U[q] = w[q * 32];
+        double acc[3];
+        acc[0] = w2 * V[1];
+        acc[1] = -w2 * V[0];
+        acc[2] = 0.0;
+        if (MASS) {
+            const double smj = (KIND == 1) ? 1.0 : fma(h * lto_tab::Cf(j), bm, sm);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[q] = fma(w[(7 + q) * 32], smj, acc[q]);
+        }
+        if (KIND == 2) {
+            const double kom = (NS == 7) ? w[6 * 32] : kom6;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc[q] = fma(ec[q], kom, acc[q]);
+        }
+        sym3_mul_acc(U, R, acc);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) a[j][q] = acc[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double dv = 0.0, dr = 0.0;
+#pragma unroll
+        for (int l = 0; l < 13; ++l) {
+            if (lto_tab::CHIf(l) != 0.0) dv = fma(lto_tab::CHIf(l), a[l][q], dv);
+            if (lto_tab::CHIBf(l) != 0.0) dr = fma(lto_tab::CHIBf(l), a[l][q], dr);
+        }
+        sr[q] = fma(h2, dr, fma(h, sv[q], sr[q]));
+        sv[q] = fma(h, dv, sv[q]);
+    }
+    if (MASS && KIND == 2) sm = fma(h, bm, sm);
+}
+
+template <int NS, int KIND>
+__device__ __forceinline__ void column_warp(const DirectArgs& a, int n_tiles, int col, int lane, double* stepbuf, double* tilebuf) {
+    typedef Cfg<NS> C;
+    constexpr int NV = 2 * (NS + 3);
+    const int nstep = a.cfg.nsteps - 1;
+    const int back = lane & 1;
+    const double omega = back ? -1.0 : 1.0;
+    const double kom6 = a.c.kthr / a.c.default_mass;
+    const int gc = (KIND == 2) ? col - NS : -1;        // control component of a Gamma column
+    double ec[3] = {gc == 0 ? 1.0 : 0.0, gc == 1 ? 1.0 : 0.0, gc == 2 ? 1.0 : 0.0};
+    double sr[3], sv[3], sm = 0.0, bm = 0.0;
+    int buf = 0, tpar = 0;
+    cta_barrier(C::NTHREADS);                           // step 0 of the first tile is ready
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tpar ^= 1) {
+        // ---- initial condition S(0) = [I | 0]
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { sr[q] = (KIND == 0 && col == q) ? 1.0 : 0.0; sv[q] = (KIND == 0 && col == q + 3) ? 1.0 : 0.0; }
+        sm = (KIND == 1) ? 1.0 : 0.0;
+        if (NS == 7 && KIND == 2) bm = tilebuf[(tpar * C::TILE_DOUBLES + gc) * 32 + lane];
+        for (int k = 0; k < nstep; ++k, buf ^= 1) {
+            col_step<NS, KIND>(sr, sv, sm, bm, ec, omega, kom6, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane);
+            if (k == nstep - 1) {
+                // ---- store this column of the segment's Jacobian block, in the defect's frame:
+                //      forward leg  +S        -> columns [X_a | u_a]
+                //      backward leg -(R S R)  -> columns [X_b]      -(R S) -> [u_b]      
+                const long long seg = (long long)tile * 16 + (lane >> 1);
+                if (seg < a.n_seg) {
+                    const int ocol = (KIND == 2) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
+                    double* J = a.jac + seg * (long long)(NS * NV) + (long long)ocol * NS;
+                    const double rj = (KIND == 0 && col >= 3) ? -1.0 : 1.0;
+                    const double sp = back ? -rj : 1.0;       // sign of the r / m rows
+                    const double sq = back ? rj : 1.0;        // sign of the v rows
+                    J[0] = sp * sr[0]; J[1] = sp * sr[1]; J[2] = sp * sr[2];
+                    J[3] = sq * sv[0]; J[4] = sq * sv[1]; J[5] = sq * sv[2];
+                    if (NS == 7) J[6] = sp * sm;
+                }
+            }
+            cta_barrier(C::NTHREADS);
+        }
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void state_warp(const DirectArgs& a, int n_tiles, int lane, double* stepbuf, double* tilebuf) {
+    typedef Cfg<NS> C;
+    const int nsteps = a.cfg.nsteps, nstep = nsteps - 1;
+    const int back = lane & 1;
+    const double omega = back ? -1.0 : 1.0;
+    double r[3], v[3], m = a.c.default_mass, u[3], mdot = 0.0, t0 = 0.0, t1 = 1.0, maxErr = 0.0;
+    long long seg = 0;
+    int buf = 0, tpar = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tpar ^= 1) {
+        // ---- load this tile's legs (multiShoot_CRTBP_direct.jl:82-95)
+        seg = (long long)tile * 16 + (lane >> 1);
+        {
+            const long long sc = seg < a.n_seg ? seg : a.n_seg - 1;     // ragged tail: recompute a valid segment, never store it
+            const long long ia = lto_node_a(sc, a.npt);
+            const double* X = (back ? a.Xb : a.Xa) + ia * NS;
+            const double* U = (back ? a.ub : a.ua) + ia * 3;
+            r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
+            v[0] = X[3]; v[1] = X[4]; v[2] = X[5];
+            if (back) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }     // :92
+            if (NS == 7) m = X[6];
+            u[0] = U[0]; u[1] = U[1]; u[2] = U[2];
+            const double ta = a.ta[ia], tb = a.tb[ia];
+            t0 = ta; t1 = ta + (tb - ta) / 2.0;                         // :70
+            const double un = sqrt(fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2])));
+            mdot = -omega * un * a.c.cmdot;                             // CRTBP_prop_EP_deriv.jl:42
+            if (NS == 7) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const double uh = (un > 0.0) ? u[q] / un : 1.0;     // one-sided slope at |u| = 0
+                    tilebuf[(tpar * C::TILE_DOUBLES + q) * 32 + lane] = -omega * a.c.cmdot * uh;
+                }
+            }
+            maxErr = 0.0;
+        }
+        for (int k = 0; k < nstep; ++k, buf ^= 1) {
+            const double h = linrange_at(t0, t1, nsteps, k + 1) - linrange_at(t0, t1, nsteps, k);   // ode.jl:904
+            x_step<NS>(r, v, m, u, omega, mdot, h, a.c, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane, maxErr);
+            if (k == nstep - 1) {
+                // ---- defect = forward end - R * backward end (:98-101), errors (:104)
+                const unsigned full = 0xffffffffu;
+                double xe[NS];
+                xe[0] = r[0]; xe[1] = r[1]; xe[2] = r[2];
+                xe[3] = back ? -v[0] : v[0]; xe[4] = back ? -v[1] : v[1]; xe[5] = back ? -v[2] : v[2];
+                if (NS == 7) xe[6] = m;
+                bool bad = false;
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    const double other = __shfl_xor_sync(full, xe[q], 1);
+                    const double d = xe[q] - other;
+                    bad |= !(d == d);
+                    if (!back && seg < a.n_seg) a.defect[seg * NS + q] = d;
+                }
+                const double me_o = __shfl_xor_sync(full, maxErr, 1);
+                if (!back && seg < a.n_seg) {
+                    if (a.errors) a.errors[seg] = fmax(maxErr, me_o);
+                    if (a.status) a.status[seg] = bad ? LTO_ST_NAN : LTO_OK;
+                }
+            }
+            if (first) { first = false; cta_barrier(C::NTHREADS); continue; }   // prologue: publish step 0, then run one ahead
+            cta_barrier(C::NTHREADS);
+        }
+    }
+    cta_barrier(C::NTHREADS);                            // pairs with the column warps' final step
+}
+
+template <int NS, int MINB>
+__global__ void __launch_bounds__(Cfg<NS>::NTHREADS, MINB) k_direct_cw(DirectArgs a, int n_tiles) {
+    typedef Cfg<NS> C;
+    extern __shared__ double smem[];
+    double* stepbuf = smem;
+    double* tilebuf = smem + 2 * C::STEP_DOUBLES * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == XW) {
+        state_warp<NS>(a, n_tiles, lane, stepbuf, tilebuf);
+    } else {
+        const int col = warp < XW ? warp : warp - 1;
+        if (col < 6) column_warp<NS, 0>(a, n_tiles, col, lane, stepbuf, tilebuf);
+        else if (NS == 7 && col == 6) column_warp<NS, 1>(a, n_tiles, col, lane, stepbuf, tilebuf);
+        else column_warp<NS, 2>(a, n_tiles, col, lane, stepbuf, tilebuf);
+    }
+}
+
+}  // namespace cw
+
+template <int NS, int MINB>
+static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
+    typedef cw::Cfg<NS> C;
+    static int n_sm = 0;
+    static bool attr = false;
+    if (!attr) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(cw::k_direct_cw<NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const long long n_tiles = (a.n_seg + 15) / 16;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)n_sm * MINB);
+    cw::k_direct_cw<NS, MINB><<<grid, C::NTHREADS, C::SMEM, st>>>(a, (int)n_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
+    *n_launch = 0;
+    if (a.cfg.mode != 0 || a.jac == nullptr || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
+    cudaError_t e;
+    if (nstate == 7) e = launch_cw<7, 2>(a, st);
+    else if (nstate == 6) e = launch_cw<6, 2>(a, st);
+    else return cudaErrorNotSupported;
+    if (e == cudaSuccess) *n_launch = 1;
+    return e;
+}
+
+}  // namespace lto

@@ -49,6 +49,15 @@ struct Grav {
     double U[6];
 };
 
+// 1/sqrt(x): hardware-assisted on the device (<= 1 ulp), IEEE division on the host test build
+LTO_HD double lto_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 LTO_HD void grav_eval(double x, double y, double z, double mu, double m1, Grav& g) {
     g.dx1 = x + mu;
     g.dx2 = g.dx1 - 1.0;
@@ -56,8 +65,8 @@ LTO_HD void grav_eval(double x, double y, double z, double mu, double m1, Grav& 
     const double q = y * y + z * z;
     const double r1s = fma(g.dx1, g.dx1, q);
     const double r2s = fma(g.dx2, g.dx2, q);
-    const double i1 = 1.0 / sqrt(r1s);
-    const double i2 = 1.0 / sqrt(r2s);
+    const double i1 = lto_rsqrt(r1s);
+    const double i2 = lto_rsqrt(r2s);
     const double i1s = i1 * i1, i2s = i2 * i2;
     const double i13 = i1s * i1, i23 = i2s * i2;
     g.a3_1 = m1 * i13;

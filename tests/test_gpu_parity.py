@@ -1,0 +1,225 @@
+"""GPU: parity of liblto_b200.so (through the C ABI) with the CPU oracle, the committed golden
+vectors, and size-independent properties at the benchmark sizes.
+
+Tolerances (BASELINE.json north_star): segment end states / defects 1e-10, Jacobian / STM
+entries 1e-8, both relative to max(1, |value scale|).  FIXED-mode results come from the same
+discrete map as the oracle, so they are held to much tighter bounds below.
+"""
+import numpy as np
+import pytest
+
+from lowthrustopt_b200 import capi, synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE = 1e-10
+TOL_JAC = 1e-8
+
+
+def rel(a, b, scale=None):
+    sc = np.maximum(1.0, np.abs(b) if scale is None else scale)
+    return (np.abs(a - b) / sc).max() if a.size else 0.0
+
+
+# ------------------------------------------------------------------ direct
+@pytest.mark.parametrize("kernel", [capi.LTO_KERNEL_GENERIC, capi.LTO_KERNEL_AUTO])
+@pytest.mark.parametrize("ns", [6, 7])
+def test_direct_fixed_vs_oracle(ns, kernel, lto, oracle):
+    n = 1000 + 37                                      # ragged: not a multiple of any tile size
+    b = S.direct_batch(n, nstate=ns, seed=101)
+    r = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nsteps=10, params=capi.direct_params(kernel=kernel))
+    do, eo, Jo, so = oracle.direct_jac_var(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nthreads=oracle.num_threads())
+    xscale = np.maximum(np.abs(b["Xa"]), np.abs(b["Xb"]))
+    assert rel(r["defect"], do, xscale) < 1e-13
+    assert rel(r["jac"].transpose(0, 2, 1), Jo) < 1e-12
+    assert np.abs(r["errors"] - eo).max() < 2e-14     # rounding-level quantity (mass ~1e3)
+    assert np.all(r["status"] == 0)
+    # defect-only entry point gives the same defect
+    r2 = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nsteps=10, params=capi.direct_params(kernel=kernel), jac=False)
+    assert rel(r2["defect"], r["defect"], xscale) < 1e-14
+
+
+def test_direct_vs_golden(lto, golden):
+    for g in golden["direct"]:
+        r = lto.direct([g["Xa"]], [g["Xb"]], [g["ua"]], [g["ub"]], [g["ta"]], [g["tb"]], nsteps=g["nsteps"],
+                       params=capi.direct_params(Isp=g["Isp"]))
+        sc = np.maximum(1.0, np.abs(np.array(g["Xa"])))
+        assert (np.abs(r["defect"][0] - np.array(g["defect"])) / sc).max() < TOL_STATE
+        J = r["jac"][0].T
+        Jr = np.array(g["jac_richardson"])
+        rows = slice(0, 6) if np.all(np.array(g["ua"]) == 0) else slice(0, g["nstate"])
+        assert rel(J[rows], Jr[rows]) < TOL_JAC * (1 if g["nstate"] == 6 else 10)   # Richardson truth is itself ~1e-8 on mass rows
+        # distance to the reference's own FD Jacobian = the reference's FD noise, reported not gated tightly
+        assert np.abs(J[:6] - np.array(g["jac_fd"])[:6]).max() < 5e-6
+
+
+@pytest.mark.parametrize("ns", [6, 7])
+def test_direct_adaptive_vs_oracle(ns, lto, oracle):
+    n = 257
+    b = S.direct_batch(n, nstate=ns, seed=102)
+    for norm in (capi.LTO_NORM_STATE, capi.LTO_NORM_STATE_SENS):
+        p = capi.direct_params(mode=capi.LTO_ADAPTIVE, tol=1e-12, err_norm=norm)
+        r = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], params=p)
+        do, eo, Jo, so = oracle.direct_jac_var(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], mode=1, tol=1e-12,
+                                              with_partials=bool(norm), nthreads=oracle.num_threads())
+        xscale = np.maximum(np.abs(b["Xa"]), np.abs(b["Xb"]))
+        assert rel(r["defect"], do, xscale) < TOL_STATE
+        assert rel(r["jac"].transpose(0, 2, 1), Jo) < TOL_JAC
+        assert np.all(r["status"] == 0)
+
+
+def test_direct_traj_form_equals_pairs_form(lto):
+    n_traj, n_nodes, ns = 7, 30, 7
+    rng = np.random.default_rng(7)
+    X = np.empty((n_traj, n_nodes, ns)); t = np.empty((n_traj, n_nodes))
+    for j in range(n_traj):
+        tau = rng.uniform() + np.linspace(0, 4.6, n_nodes) / S.PERIODS[0]
+        X[j, :, :6] = S.interp_initial_states(tau, 1) + 1e-3 * rng.standard_normal((n_nodes, 6))
+        X[j, :, 6] = 1000.0 - np.linspace(0, 1, n_nodes)
+        t[j] = np.linspace(0, 4.6, n_nodes) + rng.uniform()
+    U = 0.05 * rng.standard_normal((n_traj, n_nodes, 3))
+    rt = lto.direct_traj(X, U, t)
+    rp = lto.direct(X[:, :-1].reshape(-1, ns), X[:, 1:].reshape(-1, ns), U[:, :-1].reshape(-1, 3), U[:, 1:].reshape(-1, 3),
+                    t[:, :-1].ravel(), t[:, 1:].ravel())
+    assert np.array_equal(rt["defect"], rp["defect"]) and np.array_equal(rt["jac"], rp["jac"])
+
+
+def test_direct_edge_cases(lto, oracle):
+    # empty batch
+    z = np.zeros((0, 7))
+    r = lto.direct(z, z, np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0), np.zeros(0))
+    assert r["defect"].shape == (0, 7) and r["jac"].shape == (0, 20, 7)
+    # |u| = 0 (the demo's first iteration): one-sided mass-flow slope, everything finite
+    b = S.direct_batch(33, nstate=7, seed=5, zero_control=True)
+    r = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"])
+    do, eo, Jo, so = oracle.direct_jac_var(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"])
+    assert np.all(np.isfinite(r["jac"])) and rel(r["jac"].transpose(0, 2, 1), Jo) < 1e-12
+    # bad arguments are errors, not crashes
+    with pytest.raises(capi.LtoError):
+        lto.direct(np.zeros((1, 5)), np.zeros((1, 5)), np.zeros((1, 3)), np.zeros((1, 3)), np.zeros(1), np.ones(1))
+    with pytest.raises(capi.LtoError):
+        lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nsteps=1)
+
+
+def test_direct_full_size_properties(lto):
+    """65,536 segments (BASELINE config 3): properties that need no oracle."""
+    n = 65536
+    b = S.direct_batch(n, nstate=7)
+    r = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"])
+    assert np.all(r["status"] == 0) and np.all(np.isfinite(r["jac"]))
+    # (1) batch-position invariance, bitwise: a permuted batch gives the permuted result
+    perm = np.random.default_rng(1).permutation(n)
+    rp = lto.direct(b["Xa"][perm], b["Xb"][perm], b["ua"][perm], b["ub"][perm], b["ta"][perm], b["tb"][perm])
+    assert np.array_equal(rp["defect"], r["defect"][perm]) and np.array_equal(rp["jac"], r["jac"][perm])
+    # (2) mirror symmetry of the CRTBP, (x,y,z,vx,vy,vz,t) -> (x,-y,z,-vx,vy,-vz,-t) =: M, which the RK map
+    #     inherits: for ballistic segments, swapping the nodes and mirroring them negates the mirrored defect
+    bz = S.direct_batch(4096, nstate=6, seed=9, zero_control=True)
+    r1 = lto.direct(bz["Xa"], bz["Xb"], bz["ua"], bz["ub"], bz["ta"], bz["tb"], jac=False)
+    M = np.array([1, -1, 1, -1, 1, -1.0])
+    r2 = lto.direct(bz["Xb"] * M, bz["Xa"] * M, bz["ub"], bz["ua"], bz["ta"], bz["tb"], jac=False)
+    assert np.abs(r2["defect"] + r1["defect"] * M).max() < 1e-13
+    # (3) Liouville: the (r, v) block of Phi_f has determinant 1 (trace of the 6x6 dynamics matrix is 0)
+    J = rp["jac"][:256].transpose(0, 2, 1)      # (n, 7, 20)
+    Phi_f = J[:, :6, :6]
+    assert np.abs(np.linalg.det(Phi_f) - 1.0).max() < 1e-9
+
+
+# ------------------------------------------------------------------ indirect
+LAWS = [dict(p=1.0, rho=1.0, thrustLimit=0.05), dict(p=2.0, rho=1.0, thrustLimit=10.0), dict(p=1.0, rho=1e-2, thrustLimit=0.05),
+        dict(p=0.0, rho=1.0, thrustLimit=0.05), dict(p=2.0, rho=1.0, thrustLimit=1e-3)]
+
+
+@pytest.mark.parametrize("kernel", [capi.LTO_KERNEL_GENERIC, capi.LTO_KERNEL_AUTO])
+@pytest.mark.parametrize("nd", [12, 14])
+@pytest.mark.parametrize("law", LAWS)
+def test_indirect_vs_oracle(nd, law, kernel, lto, oracle):
+    n = 300 + 11
+    b = S.indirect_batch(n, ndim=nd, seed=202)
+    lv = slice(9, 12) if nd == 12 else slice(10, 13)
+    b["x0"][::3, lv] *= 8.0                      # a third of the batch sits near the |lv| = 1 switch
+    xt = b["x0"] + 0.01
+    p = capi.indirect_params(kernel=kernel, **law)
+    r = lto.indirect(b["x0"], b["t0"], b["t1"], x_target=xt, params=p)
+    ip = oracle.iparams(law["thrustLimit"], p=law["p"], rho=law["rho"])
+    xo, Po, so, nao, nto = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip, nthreads=oracle.num_threads())
+    assert np.all(r["status"] == 0) and np.all(so == 0)
+    assert rel(r["defect"] + xt, xo) < TOL_STATE
+    assert rel(r["phi"].transpose(0, 2, 1), Po, np.abs(Po).max(axis=(1, 2), keepdims=True)) < TOL_JAC
+    assert np.abs(r["nsteps"][:, 0] - nao).max() <= 2
+    # defect-only path (state-only step control, like the reference's plain solve)
+    r0 = lto.indirect(b["x0"], b["t0"], b["t1"], x_target=xt, params=p, jac=False)
+    xo0, so0, _, _ = oracle.indirect_prop(b["x0"], b["t0"], b["t1"], ip, nthreads=oracle.num_threads())
+    assert rel(r0["defect"] + xt, xo0) < TOL_STATE
+
+
+def test_indirect_vs_golden(lto, golden):
+    for g in golden["indirect"]:
+        p = capi.indirect_params(thrustLimit=g["thrustLimit"], mass=g["mass"], time_direction=g["td"], p=g["p"], rho=g["rho"])
+        r = lto.indirect([g["x0"]], [g["t0"]], [g["t1"]], params=p)
+        assert np.abs(r["defect"][0] - np.array(g["xend"])).max() < TOL_STATE
+        if "phi_richardson" in g:
+            assert np.abs(r["phi"][0].T - np.array(g["phi_richardson"])).max() < 5e-8
+
+
+def test_indirect_ode78_controller_and_per_segment_params(lto, oracle):
+    n = 64
+    b = S.indirect_batch(n, ndim=12, seed=203)
+    tl = np.geomspace(10.0, 0.05, n); rho = np.geomspace(1.0, 1e-3, n)
+    p = capi.indirect_params(p=1.0, controller=capi.LTO_CTRL_ODE78)
+    r = lto.indirect(b["x0"], b["t0"], b["t1"], params=p, thrustLimit=tl, rho=rho)
+    ip = oracle.iparams(0.05, p=1.0)
+    xo, Po, so, _, _ = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip, thrustLimit=tl, rho=rho, controller=1)
+    assert rel(r["defect"], xo) < TOL_STATE and rel(r["phi"].transpose(0, 2, 1), Po) < TOL_JAC
+
+
+def test_indirect_traj_form_and_edge_cases(lto):
+    c = S.continuation_batch(n_traj=5, n_seg_per_traj=12, ndim=12)
+    p = capi.indirect_params(p=1.0, rho=1.0)
+    rt = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"])
+    X = c["XC_all"]
+    rp = lto.indirect(X[:, :-1].reshape(-1, 12), c["t_TU"][:, :-1].ravel(), c["t_TU"][:, 1:].ravel(), x_target=X[:, 1:].reshape(-1, 12),
+                      params=p, thrustLimit=np.repeat(c["thrustLimit"], 12))
+    assert np.array_equal(rt["defect"], rp["defect"]) and np.array_equal(rt["phi"], rp["phi"])
+    # empty
+    r = lto.indirect(np.zeros((0, 12)), np.zeros(0), np.zeros(0), params=p)
+    assert r["phi"].shape == (0, 12, 12)
+    # invalid control-law exponent is an error like the reference's error("Invalid value of p!")
+    with pytest.raises(capi.LtoError, match="Invalid value of p"):
+        lto.indirect(np.ones((1, 12)), np.zeros(1), np.ones(1), params=capi.indirect_params(p=0.5))
+    # NaN input -> status 1, not a crash
+    bad = S.indirect_batch(4, ndim=12)
+    bad["x0"][2, 0] = np.nan
+    r = lto.indirect(bad["x0"], bad["t0"], bad["t1"], params=p)
+    assert r["status"][2] == 1 and np.all(r["status"][[0, 1, 3]] == 0)
+
+
+def test_indirect_symplectic_property(lto):
+    """With a smooth control law the 12-dim system is Hamiltonian in (r, v | lr, lv) up to the
+    Coriolis coupling; det(Phi) = 1 (Liouville: trace of A vanishes)."""
+    b = S.indirect_batch(4096, ndim=12, seed=204)
+    r = lto.indirect(b["x0"], b["t0"], b["t1"], params=capi.indirect_params(p=2.0, thrustLimit=10.0))
+    det = np.linalg.det(r["phi"])
+    assert np.abs(det - 1.0).max() < 1e-8
+
+
+# ------------------------------------------------------------------ reference-interface mirror
+def test_reference_closures_mirror(lto, oracle):
+    from lowthrustopt_b200 import direct, indirect
+    direct.set_handle(lto)
+    n_nodes, ns = 30, 6
+    t = np.linspace(0, 20 * 86400 / capi.TU, n_nodes)
+    X = S.interp_initial_states(0.75 + t / S.PERIODS[0], 1).T.copy()          # (6, 30) like the demo's X_all
+    U = np.zeros((3, n_nodes))
+    defect, errors = direct.defectCalc(X, U, t, ns, n_nodes, 10, 2000.0, None)
+    assert defect.shape == (6, 29) and errors.shape == (29,)
+    Jf = direct.jacobianCalc(X, U, t, defect, ns, n_nodes, 10, 2000.0, None, 1e-8)
+    assert Jf.shape == (6 * 29, 30 * 9)
+    do, eo, Jo, _ = oracle.direct_jac_var(X.T[:-1], X.T[1:], U.T[:-1], U.T[1:], t[:-1], t[1:])
+    assert np.abs(defect.T - do).max() < 1e-13
+    assert np.abs(Jf[6:12, 6:18] - Jo[1][:, :12]).max() < 1e-12 and np.abs(Jf[6:12, 180 + 3:180 + 9] - Jo[1][:, 12:]).max() < 1e-12
+    XC = np.vstack([X, 0.1 * np.random.default_rng(0).standard_normal((6, n_nodes))])
+    params = (capi.MU, capi.DU, capi.TU, 10.0, 1000.0, 1.0, 2.0, 1.0)
+    d2, e2 = indirect.defectCalc(XC, t, 6, n_nodes, None, params)
+    J2 = indirect.jacobianCalc(XC, t, 6, n_nodes, None, params)
+    assert d2.shape == (12, 29) and np.all(e2 == 0) and J2.shape == (12 * 29, 12 * 30)
+    assert np.all(J2[:, :6] == 0) and np.array_equal(J2[12:24, 24:36], -np.eye(12))
