@@ -17,6 +17,8 @@
 // needed by the error estimate only (ode.jl:892), which the reference takes over the
 // state alone (ode.jl:940-943), so column warps skip it.
 #include "lto_internal.h"
+#include <cstdlib>
+#include <algorithm>
 
 namespace lto {
 
@@ -330,8 +332,10 @@ cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, i
     *n_launch = 0;
     if (a.cfg.mode != 0 || a.jac == nullptr || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
     cudaError_t e;
-    if (nstate == 7) e = launch_cw<7, 2>(a, st);
-    else if (nstate == 6) e = launch_cw<6, 2>(a, st);
+    static int minb = 0;
+    if (!minb) { const char* v = getenv("LTO_CW_MINB"); minb = (v && v[0] == '1') ? 1 : 2; }
+    if (nstate == 7) e = (minb == 1) ? launch_cw<7, 1>(a, st) : launch_cw<7, 2>(a, st);
+    else if (nstate == 6) e = (minb == 1) ? launch_cw<6, 1>(a, st) : launch_cw<6, 2>(a, st);
     else return cudaErrorNotSupported;
     if (e == cudaSuccess) *n_launch = 1;
     return e;
