@@ -42,6 +42,27 @@ __device__ __forceinline__ void cta_barrier(int nthreads) {
 }
 
 // ---------------------------------------------------------------------------
+// Branch-free 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H /
+// MUFU.RCP64H, ~2^-20) + one cubically convergent correction (error ~2^-60 before
+// rounding).  No slow-path subroutine: keeps the state warp's dependent chain and its
+// instruction footprint short.  r^2 and m are always normal positive numbers here
+// (NaN inputs propagate as NaN and are reported through status[]).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+// ---------------------------------------------------------------------------
 // State warp: one RK step of x = [r v (m)] in Nystrom form; publishes the stage
 // linearisations of this step into `rec` (lane-strided) and accumulates maxErr.
 // ---------------------------------------------------------------------------
@@ -50,6 +71,8 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
                                        double mdot, double h, const EPConst& c, double* __restrict__ rec, double& maxErr) {
     constexpr int SVAL = Cfg<NS>::SVAL;
     const double h2 = h * h;
+    const double w2 = 2.0 * omega;
+    const double kom6 = c.kthr / c.default_mass;
     double a[13][3];
     double ev[3] = {0.0, 0.0, 0.0}, ea[3] = {0.0, 0.0, 0.0};
     rec[13 * SVAL * 32] = h;
@@ -67,24 +90,33 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
             V[q] = (j == 0) ? v[q] : fma(h, accv, v[q]);
             R[q] = (j == 0) ? r[q] : fma(h2, accr, fma(h * lto_tab::Cf(j), v[q], r[q]));
         }
-        Grav g;
-        grav_eval(R[0], R[1], R[2], c.mu, c.m1, g);
-        double kom, im = 0.0;
-        if (NS == 7) {
-            const double mj = fma(h * lto_tab::Cf(j), mdot, m);
-            im = 1.0 / mj;
-            kom = c.kthr * im;
-        } else {
-            kom = c.kthr / c.default_mass;
-        }
-        double acc[3];
-        grav_accel(g, R[0], V[0], V[1], omega, acc);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) a[j][q] = fma(u[q], kom, acc[q]);
+        // ---- gravity: 1/r_b^3 (CRTBP_prop_EP_deriv.jl:24-29) and the gradient U_xx
+        const double dx1 = R[0] + c.mu, dx2 = dx1 - 1.0;
+        const double yz = fma(R[1], R[1], R[2] * R[2]);
+        const double i1 = fast_rsqrt(fma(dx1, dx1, yz));
+        const double i2 = fast_rsqrt(fma(dx2, dx2, yz));
+        const double i1s = i1 * i1, i2s = i2 * i2;
+        const double a31 = c.m1 * i1s * i1, a32 = c.mu * i2s * i2;
+        const double gg1 = 1.0 - (a31 + a32);                       // 1 + g
+        double kom = kom6, im = 0.0;
+        if (NS == 7) { im = fast_rcp(fma(h * lto_tab::Cf(j), mdot, m)); kom = c.kthr * im; }
+        // ---- acceleration (CRTBP_prop_EP_deriv.jl:48-50), thrust u*k/m (:32-38)
+        a[j][0] = fma(u[0], kom, fma(-a31, dx1, fma(-a32, dx2, fma(w2, V[1], R[0]))));
+        a[j][1] = fma(u[1], kom, fma(gg1, R[1], -w2 * V[0]));
+        a[j][2] = fma(u[2], kom, (gg1 - 1.0) * R[2]);
         if (j != 10) {
+            const double a51 = 3.0 * i1s * a31, a52 = 3.0 * i2s * a32;
+            const double s5 = a51 + a52;
+            const double p1 = a51 * dx1, p2 = a52 * dx2;
+            const double t = p1 + p2;
+            const double s5y = s5 * R[1];
             double* w = rec + j * SVAL * 32;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) w[q * 32] = g.U[q];
+            w[0 * 32] = fma(p1, dx1, fma(p2, dx2, gg1));
+            w[1 * 32] = fma(s5y, R[1], gg1);
+            w[2 * 32] = fma(s5 * R[2], R[2], gg1 - 1.0);
+            w[3 * 32] = t * R[1];
+            w[4 * 32] = t * R[2];
+            w[5 * 32] = s5y * R[2];
             if (NS == 7) {
                 w[6 * 32] = kom;
                 const double k2 = -kom * im;
@@ -116,16 +148,19 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
 }
 
 // ---------------------------------------------------------------------------
-// Column warp: one RK step of one column s = [s_r s_v (s_m)] of S.
-//   KIND 0: Phi column of r or v          (s_m == 0)
-//   KIND 1: Phi column of m (NS == 7)     (s_m == 1)
-//   KIND 2: Gamma column c                (forcing (k/m) e_c on s_v, bm on s_m)
+// Column warp: one RK step of one column s = [s_r s_v (s_m)] of S = [Phi | Gamma].
+// ONE instruction stream serves every column (the instruction cache is shared by the
+// whole SM): what distinguishes the columns is data --
+//   Phi column of r or v : s_m == 0,            no forcing      (bm = 0, ec = 0)
+//   Phi column of m      : s_m == 1,            no forcing      (bm = 0, ec = 0, sm = 1)
+//   Gamma column c       : s_m = bm*(t - t0),   forcing (k/m) e_c on s_v, bm on s_m
+// MASS = (NS == 7): rows/columns of the mass exist.
 // ---------------------------------------------------------------------------
-template <int NS, int KIND>
+template <int NS>
 __device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], double& sm, double bm, const double (&ec)[3],
                                          double omega, double kom6, const double* __restrict__ rec) {
     constexpr int SVAL = Cfg<NS>::SVAL;
-    constexpr bool MASS = (NS == 7) && (KIND != 0);
+    constexpr bool MASS = (NS == 7);
     const double h = rec[13 * SVAL * 32];
     const double h2 = h * h;
     const double w2 = 2.0 * omega;
@@ -149,19 +184,15 @@ __device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], doubl
         double U[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) U[q] = w[q * 32];
+        const double kom = MASS ? w[6 * 32] : kom6;
         double acc[3];
-        acc[0] = w2 * V[1];
-        acc[1] = -w2 * V[0];
-        acc[2] = 0.0;
+        acc[0] = fma(ec[0], kom, w2 * V[1]);
+        acc[1] = fma(ec[1], kom, -w2 * V[0]);
+        acc[2] = ec[2] * kom;
         if (MASS) {
-            const double smj = (KIND == 1) ? 1.0 : fma(h * lto_tab::Cf(j), bm, sm);
+            const double smj = fma(h * lto_tab::Cf(j), bm, sm);
 #pragma unroll
             for (int q = 0; q < 3; ++q) acc[q] = fma(w[(7 + q) * 32], smj, acc[q]);
-        }
-        if (KIND == 2) {
-            const double kom = (NS == 7) ? w[6 * 32] : kom6;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) acc[q] = fma(ec[q], kom, acc[q]);
         }
         sym3_mul_acc(U, R, acc);
 #pragma unroll
@@ -178,10 +209,10 @@ __device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], doubl
         sr[q] = fma(h2, dr, fma(h, sv[q], sr[q]));
         sv[q] = fma(h, dv, sv[q]);
     }
-    if (MASS && KIND == 2) sm = fma(h, bm, sm);
+    if (MASS) sm = fma(h, bm, sm);
 }
 
-template <int NS, int KIND>
+template <int NS>
 __device__ __forceinline__ void column_warp(const DirectArgs& a, int n_tiles, int col, int lane, double* stepbuf, double* tilebuf) {
     typedef Cfg<NS> C;
     constexpr int NV = 2 * (NS + 3);
@@ -189,7 +220,7 @@ __device__ __forceinline__ void column_warp(const DirectArgs& a, int n_tiles, in
     const int back = lane & 1;
     const double omega = back ? -1.0 : 1.0;
     const double kom6 = a.c.kthr / a.c.default_mass;
-    const int gc = (KIND == 2) ? col - NS : -1;        // control component of a Gamma column
+    const int gc = col - NS;                             // >= 0: control component of a Gamma column
     double ec[3] = {gc == 0 ? 1.0 : 0.0, gc == 1 ? 1.0 : 0.0, gc == 2 ? 1.0 : 0.0};
     double sr[3], sv[3], sm = 0.0, bm = 0.0;
     int buf = 0, tpar = 0;
@@ -197,20 +228,20 @@ __device__ __forceinline__ void column_warp(const DirectArgs& a, int n_tiles, in
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tpar ^= 1) {
         // ---- initial condition S(0) = [I | 0]
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { sr[q] = (KIND == 0 && col == q) ? 1.0 : 0.0; sv[q] = (KIND == 0 && col == q + 3) ? 1.0 : 0.0; }
-        sm = (KIND == 1) ? 1.0 : 0.0;
-        if (NS == 7 && KIND == 2) bm = tilebuf[(tpar * C::TILE_DOUBLES + gc) * 32 + lane];
+        for (int q = 0; q < 3; ++q) { sr[q] = (col == q) ? 1.0 : 0.0; sv[q] = (col == q + 3) ? 1.0 : 0.0; }
+        sm = (NS == 7 && col == 6) ? 1.0 : 0.0;
+        bm = (NS == 7 && gc >= 0) ? tilebuf[(tpar * C::TILE_DOUBLES + gc) * 32 + lane] : 0.0;
         for (int k = 0; k < nstep; ++k, buf ^= 1) {
-            col_step<NS, KIND>(sr, sv, sm, bm, ec, omega, kom6, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane);
+            col_step<NS>(sr, sv, sm, bm, ec, omega, kom6, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane);
             if (k == nstep - 1) {
                 // ---- store this column of the segment's Jacobian block, in the defect's frame:
                 //      forward leg  +S        -> columns [X_a | u_a]
                 //      backward leg -(R S R)  -> columns [X_b]      -(R S) -> [u_b]      
                 const long long seg = (long long)tile * 16 + (lane >> 1);
                 if (seg < a.n_seg) {
-                    const int ocol = (KIND == 2) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
+                    const int ocol = (gc >= 0) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
                     double* J = a.jac + seg * (long long)(NS * NV) + (long long)ocol * NS;
-                    const double rj = (KIND == 0 && col >= 3) ? -1.0 : 1.0;
+                    const double rj = (col >= 3 && col < 6) ? -1.0 : 1.0;
                     const double sp = back ? -rj : 1.0;       // sign of the r / m rows
                     const double sq = back ? rj : 1.0;        // sign of the v rows
                     J[0] = sp * sr[0]; J[1] = sp * sr[1]; J[2] = sp * sr[2];
@@ -301,9 +332,7 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, MINB) k_direct_cw(DirectArg
         state_warp<NS>(a, n_tiles, lane, stepbuf, tilebuf);
     } else {
         const int col = warp < XW ? warp : warp - 1;
-        if (col < 6) column_warp<NS, 0>(a, n_tiles, col, lane, stepbuf, tilebuf);
-        else if (NS == 7 && col == 6) column_warp<NS, 1>(a, n_tiles, col, lane, stepbuf, tilebuf);
-        else column_warp<NS, 2>(a, n_tiles, col, lane, stepbuf, tilebuf);
+        column_warp<NS>(a, n_tiles, col, lane, stepbuf, tilebuf);
     }
 }
 
@@ -333,7 +362,7 @@ cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, i
     if (a.cfg.mode != 0 || a.jac == nullptr || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
     cudaError_t e;
     static int minb = 0;
-    if (!minb) { const char* v = getenv("LTO_CW_MINB"); minb = (v && v[0] == '1') ? 1 : 2; }
+    if (!minb) { const char* v = getenv("LTO_CW_MINB"); minb = (v && v[0] == '2') ? 2 : 1; }
     if (nstate == 7) e = (minb == 1) ? launch_cw<7, 1>(a, st) : launch_cw<7, 2>(a, st);
     else if (nstate == 6) e = (minb == 1) ? launch_cw<6, 1>(a, st) : launch_cw<6, 2>(a, st);
     else return cudaErrorNotSupported;
