@@ -8,37 +8,63 @@
 //   warp = one column of the augmented system:  warp XW carries the state x itself,
 //          every other warp carries one column of S = [Phi | Gamma]  (n + 3 columns)
 //   lane = leg.  Nothing is ever exchanged between lanes except the final defect.
-// The state warp evaluates the nonlinear dynamics once per RK stage and leg and publishes
+// A state warp evaluates the nonlinear dynamics once per RK stage and leg and publishes
 // the stage's linearisation (U_xx, k/m, -k u/m^2) through shared memory; the column warps
-// apply it to their column.  The state does not depend on S, so the state warp runs one RK
-// step AHEAD of the column warps (double-buffered step records, one CTA barrier per step).
+// apply it to their column.  The state does not depend on S, so a state warp runs AHEAD of
+// the column warps through a 2-slot ring of step records guarded by mbarriers (full: the
+// state warp's 32 lanes arrive; empty: every column thread arrives) -- no CTA-wide barrier.
+// One RK step of the state is a long dependent chain (ncu, profiles/: ~4 cycles/instruction,
+// never waiting), so a CTA keeps TWO tiles in flight, each with its own state warp; the
+// column warps alternate between them step by step, which hides the state chain behind
+// two column phases and fills the FP64 pipe.
 // Stage storage: Nystrom form -- only the 3 acceleration components of each stage are
 // kept (registers), positions are rebuilt with G = B*B (lto_tableau.h).  Stage 11 is
 // needed by the error estimate only (ode.jl:892), which the reference takes over the
 // state alone (ode.jl:940-943), so column warps skip it.
 #include "lto_internal.h"
-#include <cstdlib>
 #include <algorithm>
 
 namespace lto {
 
 namespace cw {
 
-constexpr int XW = 3;   // the state warp: SM sub-partition 3 hosts one warp fewer than the others
+constexpr int NTILE = 2;   // tiles in flight per CTA (one state warp each)
+constexpr int NSLOT = 2;   // ring depth of step records per tile
+// warps 2 and 3 are the state warps: with warp w on SM sub-partition w % 4 the FP64 load is
+// [3 col | 3 col | state + 2 col | state + 2 col] (nstate 7), i.e. balanced
+constexpr int XW0 = 2;
 
 template <int NS>
 struct Cfg {
     static constexpr int NCOL = NS + 3;
-    static constexpr int NW = 1 + NCOL;
+    static constexpr int NW = NTILE + NCOL;
     static constexpr int NTHREADS = 32 * NW;
     static constexpr int SVAL = (NS == 7) ? 10 : 6;          // U[6] (+ k/m, am[3]) per stage and leg
-    static constexpr int STEP_DOUBLES = 13 * SVAL + 1;       // + h
-    static constexpr int TILE_DOUBLES = 4;                   // bm[3] per leg (+ pad)
-    static constexpr size_t SMEM = (size_t)(2 * STEP_DOUBLES + 2 * TILE_DOUBLES) * 32 * sizeof(double);
+    static constexpr int OFF_H = 13 * SVAL;                  // h
+    static constexpr int OFF_BM = OFF_H + 1;                 // bm[3] (nstate 7)
+    static constexpr int STEP_DOUBLES = OFF_BM + ((NS == 7) ? 3 : 0);
+    static constexpr size_t REC_BYTES = (size_t)NTILE * NSLOT * STEP_DOUBLES * 32 * sizeof(double);
+    static constexpr size_t SMEM = REC_BYTES + (size_t)NTILE * NSLOT * 2 * sizeof(unsigned long long);
 };
 
-__device__ __forceinline__ void cta_barrier(int nthreads) {
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+// ---- mbarrier (shared::cta) -------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -75,7 +101,7 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
     const double kom6 = c.kthr / c.default_mass;
     double a[13][3];
     double ev[3] = {0.0, 0.0, 0.0}, ea[3] = {0.0, 0.0, 0.0};
-    rec[13 * SVAL * 32] = h;
+    rec[Cfg<NS>::OFF_H * 32] = h;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
         double R[3], V[3];
@@ -161,7 +187,7 @@ __device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], doubl
                                          double omega, double kom6, const double* __restrict__ rec) {
     constexpr int SVAL = Cfg<NS>::SVAL;
     constexpr bool MASS = (NS == 7);
-    const double h = rec[13 * SVAL * 32];
+    const double h = rec[Cfg<NS>::OFF_H * 32];
     const double h2 = h * h;
     const double w2 = 2.0 * omega;
     double a[13][3];
@@ -212,61 +238,76 @@ __device__ __forceinline__ void col_step(double (&sr)[3], double (&sv)[3], doubl
     if (MASS) sm = fma(h, bm, sm);
 }
 
+// One column thread's state for one tile in flight.
+struct ColState { double sr[3], sv[3], sm, bm; };
+
 template <int NS>
-__device__ __forceinline__ void column_warp(const DirectArgs& a, int n_tiles, int col, int lane, double* stepbuf, double* tilebuf) {
-    typedef Cfg<NS> C;
+__device__ __forceinline__ void col_init(ColState& c, int col) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { c.sr[q] = (col == q) ? 1.0 : 0.0; c.sv[q] = (col == q + 3) ? 1.0 : 0.0; }
+    c.sm = (NS == 7 && col == 6) ? 1.0 : 0.0;                // S(0) = [I | 0]
+    c.bm = 0.0;
+}
+
+// Store this column of the segment's Jacobian block, in the defect's frame:
+//   forward leg  +S        -> columns [X_a | u_a]
+//   backward leg -(R S R)  -> columns [X_b]      -(R S) -> [u_b]      
+template <int NS>
+__device__ __forceinline__ void col_store(const DirectArgs& a, const ColState& c, long long tile, int col, int lane) {
     constexpr int NV = 2 * (NS + 3);
+    const int back = lane & 1, gc = col - NS;
+    const long long seg = tile * 16 + (lane >> 1);
+    if (seg >= a.n_seg) return;
+    const int ocol = (gc >= 0) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
+    double* J = a.jac + seg * (long long)(NS * NV) + (long long)ocol * NS;
+    const double rj = (col >= 3 && col < 6) ? -1.0 : 1.0;
+    const double sp = back ? -rj : 1.0;       // sign of the r / m rows
+    const double sq = back ? rj : 1.0;        // sign of the v rows
+    J[0] = sp * c.sr[0]; J[1] = sp * c.sr[1]; J[2] = sp * c.sr[2];
+    J[3] = sq * c.sv[0]; J[4] = sq * c.sv[1]; J[5] = sq * c.sv[2];
+    if (NS == 7) J[6] = sp * c.sm;
+}
+
+template <int NS>
+__device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_tiles, int col, int lane, double* recs, unsigned bars) {
+    typedef Cfg<NS> C;
     const int nstep = a.cfg.nsteps - 1;
-    const int back = lane & 1;
-    const double omega = back ? -1.0 : 1.0;
+    const double omega = (lane & 1) ? -1.0 : 1.0;
     const double kom6 = a.c.kthr / a.c.default_mass;
     const int gc = col - NS;                             // >= 0: control component of a Gamma column
-    double ec[3] = {gc == 0 ? 1.0 : 0.0, gc == 1 ? 1.0 : 0.0, gc == 2 ? 1.0 : 0.0};
-    double sr[3], sv[3], sm = 0.0, bm = 0.0;
-    int buf = 0, tpar = 0;
-    cta_barrier(C::NTHREADS);                           // step 0 of the first tile is ready
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tpar ^= 1) {
-        // ---- initial condition S(0) = [I | 0]
+    const double ec[3] = {gc == 0 ? 1.0 : 0.0, gc == 1 ? 1.0 : 0.0, gc == 2 ? 1.0 : 0.0};
+    ColState cs[NTILE];
+    unsigned g = 0;                                      // step counter of each tile stream (same for both)
+    for (long long pair = blockIdx.x; pair * NTILE < n_tiles; pair += gridDim.x) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { sr[q] = (col == q) ? 1.0 : 0.0; sv[q] = (col == q + 3) ? 1.0 : 0.0; }
-        sm = (NS == 7 && col == 6) ? 1.0 : 0.0;
-        bm = (NS == 7 && gc >= 0) ? tilebuf[(tpar * C::TILE_DOUBLES + gc) * 32 + lane] : 0.0;
-        for (int k = 0; k < nstep; ++k, buf ^= 1) {
-            col_step<NS>(sr, sv, sm, bm, ec, omega, kom6, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane);
-            if (k == nstep - 1) {
-                // ---- store this column of the segment's Jacobian block, in the defect's frame:
-                //      forward leg  +S        -> columns [X_a | u_a]
-                //      backward leg -(R S R)  -> columns [X_b]      -(R S) -> [u_b]      
-                const long long seg = (long long)tile * 16 + (lane >> 1);
-                if (seg < a.n_seg) {
-                    const int ocol = (gc >= 0) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
-                    double* J = a.jac + seg * (long long)(NS * NV) + (long long)ocol * NS;
-                    const double rj = (col >= 3 && col < 6) ? -1.0 : 1.0;
-                    const double sp = back ? -rj : 1.0;       // sign of the r / m rows
-                    const double sq = back ? rj : 1.0;        // sign of the v rows
-                    J[0] = sp * sr[0]; J[1] = sp * sr[1]; J[2] = sp * sr[2];
-                    J[3] = sq * sv[0]; J[4] = sq * sv[1]; J[5] = sq * sv[2];
-                    if (NS == 7) J[6] = sp * sm;
-                }
+        for (int t = 0; t < NTILE; ++t) col_init<NS>(cs[t], col);
+        for (int k = 0; k < nstep; ++k, ++g) {
+            const unsigned slot = g & (NSLOT - 1), par = (g / NSLOT) & 1;
+#pragma unroll
+            for (int t = 0; t < NTILE; ++t) {
+                const double* rec = recs + (size_t)(t * NSLOT + slot) * C::STEP_DOUBLES * 32 + lane;
+                const unsigned full = bars + (unsigned)((t * NSLOT + slot) * 16), empty = full + 8;
+                mbar_wait(full, par);
+                if (NS == 7 && k == 0 && gc >= 0) cs[t].bm = rec[(C::OFF_BM + gc) * 32];
+                col_step<NS>(cs[t].sr, cs[t].sv, cs[t].sm, cs[t].bm, ec, omega, kom6, rec);
+                mbar_arrive(empty);
+                if (k == nstep - 1) col_store<NS>(a, cs[t], pair * NTILE + t, col, lane);
             }
-            cta_barrier(C::NTHREADS);
         }
     }
 }
 
 template <int NS>
-__device__ __forceinline__ void state_warp(const DirectArgs& a, int n_tiles, int lane, double* stepbuf, double* tilebuf) {
+__device__ __forceinline__ void state_warp(const DirectArgs& a, long long n_tiles, int t, int lane, double* recs, unsigned bars) {
     typedef Cfg<NS> C;
     const int nsteps = a.cfg.nsteps, nstep = nsteps - 1;
     const int back = lane & 1;
     const double omega = back ? -1.0 : 1.0;
-    double r[3], v[3], m = a.c.default_mass, u[3], mdot = 0.0, t0 = 0.0, t1 = 1.0, maxErr = 0.0;
-    long long seg = 0;
-    int buf = 0, tpar = 0;
-    bool first = true;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tpar ^= 1) {
+    double r[3], v[3], m = a.c.default_mass, u[3], bm[3] = {0.0, 0.0, 0.0}, mdot = 0.0, t0 = 0.0, t1 = 1.0, maxErr = 0.0;
+    unsigned g = 0;
+    for (long long pair = blockIdx.x; pair * NTILE < n_tiles; pair += gridDim.x) {
         // ---- load this tile's legs (multiShoot_CRTBP_direct.jl:82-95)
-        seg = (long long)tile * 16 + (lane >> 1);
+        const long long seg = (pair * NTILE + t) * 16 + (lane >> 1);
         {
             const long long sc = seg < a.n_seg ? seg : a.n_seg - 1;     // ragged tail: recompute a valid segment, never store it
             const long long ia = lto_node_a(sc, a.npt);
@@ -285,60 +326,72 @@ __device__ __forceinline__ void state_warp(const DirectArgs& a, int n_tiles, int
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const double uh = (un > 0.0) ? u[q] / un : 1.0;     // one-sided slope at |u| = 0
-                    tilebuf[(tpar * C::TILE_DOUBLES + q) * 32 + lane] = -omega * a.c.cmdot * uh;
+                    bm[q] = -omega * a.c.cmdot * uh;
                 }
             }
             maxErr = 0.0;
         }
-        for (int k = 0; k < nstep; ++k, buf ^= 1) {
+        for (int k = 0; k < nstep; ++k, ++g) {
+            const unsigned slot = g & (NSLOT - 1), use = g / NSLOT;
+            double* rec = recs + (size_t)(t * NSLOT + slot) * C::STEP_DOUBLES * 32 + lane;
+            const unsigned full = bars + (unsigned)((t * NSLOT + slot) * 16), empty = full + 8;
+            if (use > 0) mbar_wait(empty, (use - 1) & 1);               // every column thread is done with this slot
             const double h = linrange_at(t0, t1, nsteps, k + 1) - linrange_at(t0, t1, nsteps, k);   // ode.jl:904
-            x_step<NS>(r, v, m, u, omega, mdot, h, a.c, stepbuf + (size_t)buf * C::STEP_DOUBLES * 32 + lane, maxErr);
-            if (k == nstep - 1) {
-                // ---- defect = forward end - R * backward end (:98-101), errors (:104)
-                const unsigned full = 0xffffffffu;
-                double xe[NS];
-                xe[0] = r[0]; xe[1] = r[1]; xe[2] = r[2];
-                xe[3] = back ? -v[0] : v[0]; xe[4] = back ? -v[1] : v[1]; xe[5] = back ? -v[2] : v[2];
-                if (NS == 7) xe[6] = m;
-                bool bad = false;
+            if (NS == 7) {
 #pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    const double other = __shfl_xor_sync(full, xe[q], 1);
-                    const double d = xe[q] - other;
-                    bad |= !(d == d);
-                    if (!back && seg < a.n_seg) a.defect[seg * NS + q] = d;
-                }
-                const double me_o = __shfl_xor_sync(full, maxErr, 1);
-                if (!back && seg < a.n_seg) {
-                    if (a.errors) a.errors[seg] = fmax(maxErr, me_o);
-                    if (a.status) a.status[seg] = bad ? LTO_ST_NAN : LTO_OK;
-                }
+                for (int q = 0; q < 3; ++q) rec[(C::OFF_BM + q) * 32] = bm[q];
             }
-            if (first) { first = false; cta_barrier(C::NTHREADS); continue; }   // prologue: publish step 0, then run one ahead
-            cta_barrier(C::NTHREADS);
+            x_step<NS>(r, v, m, u, omega, mdot, h, a.c, rec, maxErr);
+            mbar_arrive(full);
+        }
+        // ---- defect = forward end - R * backward end (:98-101), errors (:104)
+        const unsigned fullmask = 0xffffffffu;
+        double xe[NS];
+        xe[0] = r[0]; xe[1] = r[1]; xe[2] = r[2];
+        xe[3] = back ? -v[0] : v[0]; xe[4] = back ? -v[1] : v[1]; xe[5] = back ? -v[2] : v[2];
+        if (NS == 7) xe[6] = m;
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const double other = __shfl_xor_sync(fullmask, xe[q], 1);
+            const double d = xe[q] - other;
+            bad |= !(d == d);
+            if (!back && seg < a.n_seg) a.defect[seg * NS + q] = d;
+        }
+        const double me_o = __shfl_xor_sync(fullmask, maxErr, 1);
+        if (!back && seg < a.n_seg) {
+            if (a.errors) a.errors[seg] = fmax(maxErr, me_o);
+            if (a.status) a.status[seg] = bad ? LTO_ST_NAN : LTO_OK;
         }
     }
-    cta_barrier(C::NTHREADS);                            // pairs with the column warps' final step
 }
 
-template <int NS, int MINB>
-__global__ void __launch_bounds__(Cfg<NS>::NTHREADS, MINB) k_direct_cw(DirectArgs a, int n_tiles) {
+template <int NS>
+__global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a, long long n_tiles) {
     typedef Cfg<NS> C;
-    extern __shared__ double smem[];
-    double* stepbuf = smem;
-    double* tilebuf = smem + 2 * C::STEP_DOUBLES * 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* recs = reinterpret_cast<double*>(smem_raw);
+    const unsigned bars = smem_u32(smem_raw + C::REC_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == XW) {
-        state_warp<NS>(a, n_tiles, lane, stepbuf, tilebuf);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NTILE * NSLOT; ++i) {
+            mbar_init(bars + i * 16, 32);                    // full : the state warp's lanes
+            mbar_init(bars + i * 16 + 8, 32 * C::NCOL);      // empty: every column thread
+        }
+    }
+    __syncthreads();
+    if (warp >= XW0 && warp < XW0 + NTILE) {
+        state_warp<NS>(a, n_tiles, warp - XW0, lane, recs, bars);
     } else {
-        const int col = warp < XW ? warp : warp - 1;
-        column_warp<NS>(a, n_tiles, col, lane, stepbuf, tilebuf);
+        const int col = warp < XW0 ? warp : warp - NTILE;
+        column_warp<NS>(a, n_tiles, col, lane, recs, bars);
     }
 }
 
 }  // namespace cw
 
-template <int NS, int MINB>
+template <int NS>
 static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
     typedef cw::Cfg<NS> C;
     static int n_sm = 0;
@@ -347,13 +400,14 @@ static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(cw::k_direct_cw<NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(cw::k_direct_cw<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     const long long n_tiles = (a.n_seg + 15) / 16;
-    const int grid = (int)std::min<long long>(n_tiles, (long long)n_sm * MINB);
-    cw::k_direct_cw<NS, MINB><<<grid, C::NTHREADS, C::SMEM, st>>>(a, (int)n_tiles);
+    const long long n_pairs = (n_tiles + cw::NTILE - 1) / cw::NTILE;
+    const int grid = (int)std::min<long long>(n_pairs, (long long)n_sm);
+    cw::k_direct_cw<NS><<<grid, C::NTHREADS, C::SMEM, st>>>(a, n_tiles);
     return cudaGetLastError();
 }
 
@@ -361,10 +415,8 @@ cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, i
     *n_launch = 0;
     if (a.cfg.mode != 0 || a.jac == nullptr || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
     cudaError_t e;
-    static int minb = 0;
-    if (!minb) { const char* v = getenv("LTO_CW_MINB"); minb = (v && v[0] == '2') ? 2 : 1; }
-    if (nstate == 7) e = (minb == 1) ? launch_cw<7, 1>(a, st) : launch_cw<7, 2>(a, st);
-    else if (nstate == 6) e = (minb == 1) ? launch_cw<6, 1>(a, st) : launch_cw<6, 2>(a, st);
+    if (nstate == 7) e = launch_cw<7>(a, st);
+    else if (nstate == 6) e = launch_cw<6>(a, st);
     else return cudaErrorNotSupported;
     if (e == cudaSuccess) *n_launch = 1;
     return e;
