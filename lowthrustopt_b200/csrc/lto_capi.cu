@@ -20,6 +20,7 @@ struct lto_handle {
     cudaEvent_t ev_chunk[8];
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
+    unsigned long long* d_ctr;
     int64_t launches;
     double last_ms;
     char err[512];
@@ -101,6 +102,7 @@ int lto_init(int device, lto_handle** out) {
     CK(h, cudaEventCreate(&h->ev_t0));
     CK(h, cudaEventCreate(&h->ev_t1));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    CK(h, cudaMalloc((void**)&h->d_ctr, 256));
     *out = h;
     return LTO_SUCCESS;
 }
@@ -111,6 +113,7 @@ void lto_destroy(lto_handle* h) {
     cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
+    if (h->d_ctr) cudaFree(h->d_ctr);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
@@ -325,7 +328,7 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
         a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
         a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
         a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
-        a.n_seg = ns; a.npt = npt;
+        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr;
         rc = dispatch_indirect(h, a, ndim, p->kernel); if (rc) return rc;
         cudaEvent_t ev = h->ev_chunk[ci & 7];
         CK(h, cudaEventRecord(ev, h->s_compute));
@@ -424,7 +427,7 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
     a.x0 = x0; a.t0 = t0;
     if (n_nodes > 0) { a.t1 = t0 + 1; a.x_target = x0 + ndim; } else { a.t1 = t1; a.x_target = x_target; }
     a.thrustLimit_arr = thrustLimit_arr; a.rho_arr = rho_arr;
-    a.defect = defect; a.status = status; a.nsteps_out = nsteps_out; a.phi = phi; a.n_seg = n_seg; a.npt = n_nodes;
+    a.defect = defect; a.status = status; a.nsteps_out = nsteps_out; a.phi = phi; a.n_seg = n_seg; a.npt = n_nodes; a.counter = h->d_ctr;
     return dispatch_indirect(h, a, ndim, p->kernel);
 }
 

@@ -1,0 +1,50 @@
+// lto_cw_common.cuh -- pieces shared by the column-warp throughput kernels
+// (lto_direct_cw.cu, lto_indirect_cw.cu): shared-memory mbarriers and branch-free
+// reciprocal / reciprocal square root.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace lto {
+namespace cwc {
+
+// ---- mbarrier (shared::cta): producer/consumer hand-off between a state warp and the
+// column warps without a CTA-wide barrier.  arrive has release, try_wait acquire semantics.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// ---- Branch-free 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H /
+// MUFU.RCP64H, ~2^-20) + one cubically convergent correction (error ~2^-60 before
+// rounding).  No slow-path subroutine: keeps a state warp's dependent chain and its
+// instruction footprint short.  NaN inputs propagate as NaN (reported through status[]).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y * e, p, y);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
+}
+
+}  // namespace cwc
+}  // namespace lto

@@ -25,6 +25,7 @@ struct IndirectArgs {
     const double *thrustLimit_arr, *rho_arr;   // per segment (pairs) or per trajectory (npt > 0), or NULL
     double *defect, *phi;
     int32_t *status, *nsteps_out;
+    unsigned long long* counter;               // device work-queue counter (throughput kernel)
     long long n_seg;
     int npt;
     IndirectCfg cfg;

@@ -4,14 +4,14 @@
 namespace lto {
 
 cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch);
+cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch);
 
 cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
     return launch_direct_cw(a, nstate, st, n_launch);
 }
 
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
-    *n_launch = 0;
-    return cudaErrorNotSupported;
+    return launch_indirect_cw(a, ndim, st, n_launch);
 }
 
 }  // namespace lto
