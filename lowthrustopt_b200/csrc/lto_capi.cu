@@ -21,6 +21,7 @@ struct lto_handle {
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
     unsigned long long* d_ctr;
+    void* d_scr; size_t d_scr_cap;
     int64_t launches;
     double last_ms;
     char err[512];
@@ -114,6 +115,7 @@ void lto_destroy(lto_handle* h) {
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ctr) cudaFree(h->d_ctr);
+    if (h->d_scr) cudaFree(h->d_scr);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
@@ -308,6 +310,7 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     char* dq = (char*)h->d_out;
     double* dD = (double*)dq; dq += bD; int32_t* dS = (int32_t*)dq; dq += bS; int32_t* dN = (int32_t*)dq; dq += bN;
     double* dJ = want_jac ? (double*)dq : nullptr;
+    if (want_jac) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, indirect_cw_scratch_bytes(h->n_sm)); if (rc) return rc; }
     CK(h, cudaMemcpyAsync(dX, x0, rows * ND * 8, cudaMemcpyHostToDevice, h->s_copy));
     CK(h, cudaMemcpyAsync(dT0, t0, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
     if (npt == 0) CK(h, cudaMemcpyAsync(dT1, t1, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
@@ -328,7 +331,7 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
         a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
         a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
         a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
-        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr;
+        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr; a.scratch = (double*)h->d_scr;
         rc = dispatch_indirect(h, a, ndim, p->kernel); if (rc) return rc;
         cudaEvent_t ev = h->ev_chunk[ci & 7];
         CK(h, cudaEventRecord(ev, h->s_compute));
@@ -427,7 +430,9 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
     a.x0 = x0; a.t0 = t0;
     if (n_nodes > 0) { a.t1 = t0 + 1; a.x_target = x0 + ndim; } else { a.t1 = t1; a.x_target = x_target; }
     a.thrustLimit_arr = thrustLimit_arr; a.rho_arr = rho_arr;
+    if (phi) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, indirect_cw_scratch_bytes(h->n_sm)); if (rc) return rc; }
     a.defect = defect; a.status = status; a.nsteps_out = nsteps_out; a.phi = phi; a.n_seg = n_seg; a.npt = n_nodes; a.counter = h->d_ctr;
+    a.scratch = (double*)h->d_scr;
     return dispatch_indirect(h, a, ndim, p->kernel);
 }
 

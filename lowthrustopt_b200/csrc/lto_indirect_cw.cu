@@ -5,32 +5,35 @@
 // (drive_rk8); Phi replaces ForwardDiff.jacobian(f, x0) (:121).
 //
 // Mapping:
-//   tile        = 16 segment SLOTS; a CTA keeps NTILE tiles in flight
-//   state warp  = one per tile; lane & 15 = slot.  Runs the nonlinear 12-dim system, the
-//                 step-size controller and the per-slot work queue (a slot that finishes
-//                 its segment pulls the next one from a global counter, so slots advance
-//                 independently and no lane waits for the slowest segment of a batch).
-//                 Publishes, per attempted step, the 13 stage linearisations U, W, G
-//                 (18 doubles per stage and slot) + h + control flags in shared memory.
-//   column warp = 6 per CTA, shared by all tiles; warp w carries STM columns 2w (lanes
-//                 0-15) and 2w+1 (lanes 16-31) of the 16 slots, so the two half-warps read
-//                 the same stage record (one shared-memory wavefront per 128-bit load).
+//   tile        = 32 segment SLOTS owned by one state warp (lane = slot); a CTA keeps
+//                 NTILE = 2 tiles in flight.
+//   state warp  = runs the nonlinear 12-dim system, the step-size controller and the
+//                 per-slot work queue (a slot that finishes its segment pulls the next one
+//                 from a global counter, so slots advance independently and no lane waits
+//                 for the slowest segment of the batch).  Publishes, per attempted step,
+//                 the 13 stage linearisations U, W, G (18 doubles per stage and slot) + h +
+//                 control flags in shared memory.
+//   column warp = 6 per CTA, shared by the tiles.  Warp w carries STM columns 2w (lanes
+//                 0-15) and 2w+1 (lanes 16-31) of 16 slots at a time, so the two half-warps
+//                 read the same stage record (a 128-bit load costs the minimum two
+//                 shared-memory wavefronts); a tile is processed as two half-phases.
 //                 A thread owns one whole column (12 components): every RK combination
-//                 and the structured product A*phi stay in its registers.
+//                 and the structured product A*phi stay in its ~240 registers, which is
+//                 what limits the CTA to 8 warps (2 per SM sub-partition).
 //   hand-off    = two mbarriers per tile (record full / columns done); the column warps
-//                 cycle over the tiles, so a state warp's dependent chain for one tile is
-//                 hidden behind the column work of the others.
+//                 alternate between the tiles, so one state warp's dependent chain is
+//                 hidden behind the column work of the other tile.
 // Step control uses the joint norm over x and Phi (LTO_NORM_STATE_SENS, the ForwardDiff
 // semantics) or x alone: each column thread returns its partial sum of squared scaled
-// errors and the state warp decides.  Between visits a column's current and candidate
-// values live in a shared-memory stash, so rejecting a step costs nothing extra.
+// errors and the state warp decides.  Between visits a column's current value lives in a
+// shared-memory stash and its candidate in an L2-resident scratch, so rejecting a step
+// costs nothing extra.
 // The initial step is Hairer's estimate over the state components (the generic kernel
 // and the oracle take it over x and Phi): the two paths may choose different step
 // sequences and agree to the integration tolerance, not to rounding.
 #include "lto_internal.h"
 #include "lto_cw_common.cuh"
 #include <algorithm>
-#include <cstdlib>
 
 namespace lto {
 namespace icw {
@@ -38,41 +41,42 @@ namespace icw {
 using namespace cwc;
 
 constexpr int ND = 12;
-constexpr int TS = 16;            // segment slots per tile
+constexpr int NTILE = 2;          // state warps = tiles in flight
+constexpr int TS = 32;            // segment slots per tile
+constexpr int HS = 16;            // slots per column half-phase
 constexpr int NCW = 6;            // column warps
 constexpr int NCT = 32 * NCW;     // column threads
 constexpr int NC2 = 9;            // double2 per stage record: U[6] W[6] G[6]
+constexpr int NW = NTILE + NCW;
+constexpr int NTHREADS = 32 * NW;
 
 enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };
 
-template <int NTILE>
-struct Cfg {
-    static constexpr int NW = NTILE + NCW;
-    static constexpr int NTHREADS = 32 * NW;
-    static constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);      // stage records
-    static constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
-    static constexpr size_t STASH_BYTES = (size_t)2 * ND * NCT * sizeof(double);      // current / candidate columns
-    static constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
-    static constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + STASH_BYTES + ERR_BYTES;
-    static constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * 32;                   // + {full, done, tile_done} per tile
-};
+// ---- shared-memory plan ------------------------------------------------------
+constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);      // stage records of one tile
+constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
+constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);        // current columns, both halves
+constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
+constexpr size_t XN_BYTES = (size_t)ND * TS * sizeof(double);              // the state's candidate
+constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
+constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * 32;                   // + {full, done, tile_done} per tile
+constexpr size_t SCRATCH_BYTES_PER_CTA = (size_t)NTILE * 2 * ND * NCT * sizeof(double);   // candidate columns (global)
 
 struct TileSmem {
-    double2* rec; double* hval; int2* hctl; double* stash; double* errp;
+    double2* rec; double* hval; int2* hctl; double* cur; double* errp; double* xn;
     unsigned bar_full, bar_done; volatile int* tile_done;
 };
 
-template <int NTILE>
 __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
-    typedef Cfg<NTILE> C;
-    unsigned char* p = base + (size_t)t * C::TILE_BYTES;
+    unsigned char* p = base + (size_t)t * TILE_BYTES;
     TileSmem s;
-    s.rec = reinterpret_cast<double2*>(p); p += C::REC_BYTES;
+    s.rec = reinterpret_cast<double2*>(p); p += REC_BYTES;
     s.hval = reinterpret_cast<double*>(p); p += TS * sizeof(double);
     s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
-    s.stash = reinterpret_cast<double*>(p); p += C::STASH_BYTES;
-    s.errp = reinterpret_cast<double*>(p);
-    unsigned char* b = base + (size_t)NTILE * C::TILE_BYTES + (size_t)t * 32;
+    s.cur = reinterpret_cast<double*>(p); p += CUR_BYTES;
+    s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
+    s.xn = reinterpret_cast<double*>(p);
+    unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * 32;
     s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 8);
     s.tile_done = reinterpret_cast<volatile int*>(b + 16);
     return s;
@@ -108,8 +112,9 @@ __device__ __forceinline__ void stage_input(const KStore& K, const double (&y)[N
     }
 }
 
-// 8th-order update (ode.jl:937) and the scaled squared error of the embedded estimate
-// (ode.jl:940 with the controller's scaling atol + rtol*max(|y|, |ynew|)).
+// 8th-order update (ode.jl:937) and, if ERR, the scaled squared error of the embedded
+// estimate (ode.jl:940 with the controller's scaling atol + rtol*max(|y|, |ynew|)).
+template <bool ERR>
 __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)[ND], double h, double h2, double atol, double rtol,
                                               double (&yn)[ND]) {
     double esum = 0.0;
@@ -130,16 +135,18 @@ __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)
         yn[3 + q] = fma(h, sv, y[3 + q]);
         yn[6 + q] = fma(h, sl, y[6 + q]);
         yn[9 + q] = fma(h, sm, y[9 + q]);
-        double e[4];
-        e[0] = ce2 * (K.kv[0][q] - K.kv[11][q]);                                              // psi^T B = e_1 - e_12
-        e[1] = ce * ((K.kv[0][q] + K.kv[10][q]) - (K.kv[11][q] + K.kv[12][q]));
-        e[2] = ce * ((K.kl[0][q] + K.kl[10][q]) - (K.kl[11][q] + K.kl[12][q]));
-        e[3] = ce * ((K.km[0][q] + K.km[10][q]) - (K.km[11][q] + K.km[12][q]));
+        if (ERR) {
+            double e[4];
+            e[0] = ce2 * (K.kv[0][q] - K.kv[11][q]);                                          // psi^T B = e_1 - e_12
+            e[1] = ce * ((K.kv[0][q] + K.kv[10][q]) - (K.kv[11][q] + K.kv[12][q]));
+            e[2] = ce * ((K.kl[0][q] + K.kl[10][q]) - (K.kl[11][q] + K.kl[12][q]));
+            e[3] = ce * ((K.km[0][q] + K.km[10][q]) - (K.km[11][q] + K.km[12][q]));
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const double sc = fma(rtol, fmax(fabs(y[3 * b + q]), fabs(yn[3 * b + q])), atol);
-            const double r = e[b] * fast_rcp(sc);
-            esum = fma(r, r, esum);
+            for (int b = 0; b < 4; ++b) {
+                const double sc = fma(rtol, fmax(fabs(y[3 * b + q]), fabs(yn[3 * b + q])), atol);
+                const double r = e[b] * fast_rcp(sc);
+                esum = fma(r, r, esum);
+            }
         }
     }
     return esum;
@@ -148,6 +155,8 @@ __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)
 // ---------------------------------------------------------------------------
 // Column thread: one attempted RK step of one STM column phi = [pr pv plr plv].
 //   kv = U pr + C pv + G plv;  kl = -(W pr + U plv);  km = -plr - C^T plv   (lto_math.cuh sc_col)
+// Stage 11 (index 10) enters only the error estimate: skipped when the columns are not
+// part of the step-control norm.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void sym3_mul_nacc(const double M[6], const double v[3], double out[3]) {
     out[0] = fma(-M[0], v[0], fma(-M[3], v[1], fma(-M[4], v[2], out[0])));
@@ -177,6 +186,7 @@ __device__ __forceinline__ void col_stage(KStore& K, const double (&p)[ND], doub
     K.km[J][2] = -L[2];
 }
 
+template <bool ERR>
 __device__ __forceinline__ double col_attempt(const double (&p)[ND], double h, double w2, const double2* __restrict__ rec,
                                               double atol, double rtol, double (&pn)[ND]) {
     const double h2 = h * h;
@@ -184,106 +194,185 @@ __device__ __forceinline__ double col_attempt(const double (&p)[ND], double h, d
     col_stage<0>(K, p, h, h2, w2, rec);  col_stage<1>(K, p, h, h2, w2, rec);  col_stage<2>(K, p, h, h2, w2, rec);
     col_stage<3>(K, p, h, h2, w2, rec);  col_stage<4>(K, p, h, h2, w2, rec);  col_stage<5>(K, p, h, h2, w2, rec);
     col_stage<6>(K, p, h, h2, w2, rec);  col_stage<7>(K, p, h, h2, w2, rec);  col_stage<8>(K, p, h, h2, w2, rec);
-    col_stage<9>(K, p, h, h2, w2, rec);  col_stage<10>(K, p, h, h2, w2, rec); col_stage<11>(K, p, h, h2, w2, rec);
-    col_stage<12>(K, p, h, h2, w2, rec);
-    return step_finish(K, p, h, h2, atol, rtol, pn);
+    col_stage<9>(K, p, h, h2, w2, rec);
+    if (ERR) col_stage<10>(K, p, h, h2, w2, rec);
+    col_stage<11>(K, p, h, h2, w2, rec); col_stage<12>(K, p, h, h2, w2, rec);
+    return step_finish<ERR>(K, p, h, h2, atol, rtol, pn);
 }
 
-template <int NTILE>
+template <bool JOINT>
 __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int lane, unsigned char* smem) {
-    const int slot = lane & (TS - 1);
     const int col = 2 * cw + (lane >> 4);
     const int ct = cw * 32 + lane;
     const double w2 = 2.0 * a.c.omega;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
-    unsigned alive = (1u << NTILE) - 1u, cur = 0u;        // cur bit t: which stash buffer holds the current column of tile t
+    double* cand_base = a.scratch + (size_t)blockIdx.x * (SCRATCH_BYTES_PER_CTA / sizeof(double)) + ct;
+    unsigned alive = (1u << NTILE) - 1u;
     unsigned visit = 0;
     while (alive) {
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < NTILE; ++t) {
             if (!(alive & (1u << t))) continue;
-            const TileSmem S = tile_smem<NTILE>(smem, t);
+            const TileSmem S = tile_smem(smem, t);
             mbar_wait(S.bar_full, visit & 1);
-            const int2 hc = S.hctl[slot];
-            const double h = S.hval[slot];
-            if (hc.x & F_ACCEPT) cur ^= (1u << t);
-            const unsigned cb = (cur >> t) & 1u;
-            double* sc = S.stash + (size_t)cb * ND * NCT + ct;
-            double* sn = S.stash + (size_t)(cb ^ 1u) * ND * NCT + ct;
-            double p[ND];
+            const bool done = *S.tile_done != 0;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                const int slot = hf * HS + (lane & (HS - 1));
+                const int2 hc = S.hctl[slot];
+                const double h = S.hval[slot];
+                double* sc = S.cur + (size_t)hf * ND * NCT + ct;
+                double* sn = cand_base + (size_t)(t * 2 + hf) * ND * NCT;
+                double p[ND];
+                if (hc.x & F_ACCEPT) {
 #pragma unroll
-            for (int i = 0; i < ND; ++i) p[i] = sc[i * NCT];
-            if (hc.x & F_STORE) {                                      // column `col` of ForwardDiff.jacobian(f, x0) (:121)
-                double* out = a.phi + (long long)hc.y * (ND * ND) + col * ND;
+                    for (int i = 0; i < ND; ++i) { p[i] = __ldcg(sn + i * NCT); sc[i * NCT] = p[i]; }
+                } else {
 #pragma unroll
-                for (int i = 0; i < ND; ++i) out[i] = p[i];
+                    for (int i = 0; i < ND; ++i) p[i] = sc[i * NCT];
+                }
+                if (hc.x & F_STORE) {                                  // column `col` of ForwardDiff.jacobian(f, x0) (:121)
+                    double* out = a.phi + (long long)hc.y * (ND * ND) + col * ND;
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) out[i] = p[i];
+                }
+                if (hc.x & F_RESET) {
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; sc[i * NCT] = p[i]; }
+                }
+                if (done) continue;
+                double pn[ND];
+                const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, atol, rtol, pn);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) __stcg(sn + i * NCT, pn[i]);
+                if (JOINT) S.errp[col * TS + slot] = es;
             }
-            if (hc.x & F_RESET) {
-#pragma unroll
-                for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; sc[i * NCT] = p[i]; }
-            }
-            if (*S.tile_done) { alive &= ~(1u << t); continue; }
-            double pn[ND];
-            const double es = col_attempt(p, h, w2, S.rec + slot, atol, rtol, pn);
-#pragma unroll
-            for (int i = 0; i < ND; ++i) sn[i * NCT] = pn[i];
-            S.errp[col * TS + slot] = es;
-            mbar_arrive(S.bar_done);
+            if (done) alive &= ~(1u << t);
+            else mbar_arrive(S.bar_done);
         }
         ++visit;
     }
 }
 
 // ---------------------------------------------------------------------------
-// State warp.
+// State warp: right-hand side CRTBP_stateCostate_deriv! (src/CRTBP_stateCostate_deriv.jl:9-90)
+// and its linearisation (lto_math.cuh sc_stage gives the reference formulation; this is the
+// same arithmetic arranged for a short dependent chain: no divisions, no library calls
+// except exp / pow).
 // ---------------------------------------------------------------------------
-template <int J, bool REC>
-__device__ __forceinline__ int state_stage(KStore& K, const double (&x)[ND], double h, double h2, const SCConst& c, double tl, double rho,
-                                           double2* __restrict__ rec, bool writer) {
-    double s[ND], f[ND];
-    {
-        double R[3], V[3], L[3], M[3];
-        stage_input<J>(K, x, h, h2, R, V, L, M);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { s[q] = R[q]; s[3 + q] = V[q]; s[6 + q] = L[q]; s[9 + q] = M[q]; }
+struct LawConst { double aL, rho_inv, rho_inv_quarter_aL; };   // per slot: aL = thrustLimit*k/mass, 1/rho, aL/(4 rho)
+
+template <bool LIN>
+__device__ __forceinline__ void sc_eval(const double (&R)[3], const double (&V)[3], const double (&L)[3], const double (&M)[3],
+                                        const SCConst& c, const LawConst& lw, double (&kv)[3], double (&kl)[3], double (&km)[3],
+                                        double2* __restrict__ w) {
+    const double w2 = 2.0 * c.omega;
+    // ---- gravity (:69-70, :78-81) and its gradient
+    const double dx1 = R[0] + c.mu, dx2 = dx1 - 1.0;
+    const double yz = fma(R[1], R[1], R[2] * R[2]);
+    const double i1 = fast_rsqrt(fma(dx1, dx1, yz)), i2 = fast_rsqrt(fma(dx2, dx2, yz));
+    const double i1s = i1 * i1, i2s = i2 * i2;
+    const double a31 = c.m1 * i1s * i1, a32 = c.mu * i2s * i2;
+    const double a51 = 3.0 * a31 * i1s, a52 = 3.0 * a32 * i2s;
+    const double gg = -(a31 + a32), s5 = a51 + a52;
+    const double p1 = a51 * dx1, p2 = a52 * dx2, t = p1 + p2;
+    double U[6];
+    U[0] = fma(p1, dx1, fma(p2, dx2, 1.0 + gg));
+    U[1] = fma(s5 * R[1], R[1], 1.0 + gg);
+    U[2] = fma(s5 * R[2], R[2], gg);
+    U[3] = t * R[1]; U[4] = t * R[2]; U[5] = s5 * R[1] * R[2];
+    // ---- control law (:36-64): u_acc = -umag * lv/|lv| = -uon * lv
+    const double n2 = fma(M[0], M[0], fma(M[1], M[1], M[2] * M[2]));
+    const bool dead = !(n2 > 0.0);                                     // :59-64 NaN guard -> zero control
+    const double in = dead ? 0.0 : fast_rsqrt(n2);
+    const double n = n2 * in;
+    double umag, dn = 0.0;
+    if (c.p == 1.0) {                                                  // :41-43  0.5 (1 + tanh((n-1)/(2 rho))) aL
+        const double y = fmin(fmax((n - 1.0) * lw.rho_inv, -700.0), 700.0);
+        const double ey = exp(y);                                      // tanh(y/2) = 1 - 2/(e^y + 1)
+        const double th = fma(-2.0, fast_rcp(ey + 1.0), 1.0);
+        umag = fma(0.5 * lw.aL, th, 0.5 * lw.aL);
+        dn = lw.rho_inv_quarter_aL * fma(-th, th, 1.0);
+    } else if (c.p == 0.0) {                                           // :36-39
+        umag = lw.aL;
+    } else {                                                           // :45-50
+        const double e = 1.0 / (c.p - 1.0);
+        const double wv = (c.p == 2.0) ? 0.5 * n : pow(n / c.p, e);
+        if (wv > lw.aL) umag = lw.aL;
+        else { umag = wv; dn = dead ? 0.0 : e * wv * in; }
     }
-    SCStage st;
-    const int bad = sc_stage<ND>(s, c, tl, rho, f, st);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { K.kv[J][q] = f[3 + q]; K.kl[J][q] = f[6 + q]; K.km[J][q] = f[9 + q]; }
-    if (REC && writer) {
-        double2* w = rec + J * NC2 * TS;
-        w[0 * TS] = make_double2(st.U[0], st.U[1]); w[1 * TS] = make_double2(st.U[2], st.U[3]); w[2 * TS] = make_double2(st.U[4], st.U[5]);
-        w[3 * TS] = make_double2(st.W[0], st.W[1]); w[4 * TS] = make_double2(st.W[2], st.W[3]); w[5 * TS] = make_double2(st.W[4], st.W[5]);
-        w[6 * TS] = make_double2(st.G[0], st.G[1]); w[7 * TS] = make_double2(st.G[2], st.G[3]); w[8 * TS] = make_double2(st.G[4], st.G[5]);
+    if (dead) { umag = 0.0; dn = 0.0; }
+    if (!(n2 == n2)) umag = n2;                                        // a NaN costate stays NaN (reported through status[])
+    const double uon = umag * in;
+    // ---- derivatives (:78-88)
+    kv[0] = fma(-uon, M[0], fma(-a31, dx1, fma(-a32, dx2, fma(w2, V[1], R[0]))));
+    kv[1] = fma(-uon, M[1], fma(gg, R[1], fma(-w2, V[0], R[1])));
+    kv[2] = fma(-uon, M[2], gg * R[2]);
+    kl[0] = -fma(U[0], M[0], fma(U[3], M[1], U[4] * M[2]));
+    kl[1] = -fma(U[3], M[0], fma(U[1], M[1], U[5] * M[2]));
+    kl[2] = -fma(U[4], M[0], fma(U[5], M[1], U[2] * M[2]));
+    km[0] = fma(w2, M[1], -L[0]);
+    km[1] = fma(-w2, M[0], -L[1]);
+    km[2] = -L[2];
+    if (LIN) {
+        // G = -uon I + (uon - dn) lh lh^T,  lh = lv/|lv|
+        const double cd = uon - dn;
+        const double l0 = M[0] * in, l1 = M[1] * in, l2 = M[2] * in;
+        const double c0 = cd * l0, c1 = cd * l1;
+        // W = d(U lv)/dr = sum_b [ h_b d_b d_b^T + a5_b (d_b lv^T + lv d_b^T) ] + (e1 + e2) I,  d_b = (dx_b, y, z)
+        const double ylz = fma(R[1], M[1], R[2] * M[2]);
+        const double e1 = a51 * fma(dx1, M[0], ylz), e2 = a52 * fma(dx2, M[0], ylz);
+        const double h1 = -5.0 * e1 * i1s, h2 = -5.0 * e2 * i2s;
+        const double ee = e1 + e2, hs = h1 + h2;
+        const double hx = fma(h1, dx1, h2 * dx2);
+        const double sM0 = s5 * M[0];
+        w[0 * TS] = make_double2(U[0], U[1]);
+        w[1 * TS] = make_double2(U[2], U[3]);
+        w[2 * TS] = make_double2(U[4], U[5]);
+        w[3 * TS] = make_double2(fma(h1 * dx1, dx1, fma(h2 * dx2, dx2, fma(2.0 * t, M[0], ee))),        // W_xx
+                                 fma(hs * R[1], R[1], fma(2.0 * s5 * R[1], M[1], ee)));                 // W_yy
+        w[4 * TS] = make_double2(fma(hs * R[2], R[2], fma(2.0 * s5 * R[2], M[2], ee)),                  // W_zz
+                                 fma(hx, R[1], fma(t, M[1], sM0 * R[1])));                              // W_xy
+        w[5 * TS] = make_double2(fma(hx, R[2], fma(t, M[2], sM0 * R[2])),                               // W_xz
+                                 fma(hs * R[1], R[2], s5 * fma(R[1], M[2], M[1] * R[2])));              // W_yz
+        w[6 * TS] = make_double2(fma(c0, l0, -uon), fma(c1, l1, -uon));
+        w[7 * TS] = make_double2(fma(cd * l2, l2, -uon), c0 * l1);
+        w[8 * TS] = make_double2(c0 * l2, c1 * l2);
     }
-    return bad;
+}
+
+template <int J>
+__device__ __forceinline__ void state_stage(KStore& K, const double (&x)[ND], double h, double h2, const SCConst& c, const LawConst& lw,
+                                            double2* __restrict__ rec) {
+    double R[3], V[3], L[3], M[3];
+    stage_input<J>(K, x, h, h2, R, V, L, M);
+    sc_eval<true>(R, V, L, M, c, lw, K.kv[J], K.kl[J], K.km[J], rec + J * NC2 * TS);
 }
 
 __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) { const double q = e[i] / fma(rtol, fabs(y[i]), atol); s = fma(q, q, s); }
-    return sqrt(s / (double)ND);
+    for (int i = 0; i < ND; ++i) { const double q = e[i] * fast_rcp(fma(rtol, fabs(y[i]), atol)); s = fma(q, q, s); }
+    return sqrt(s * (1.0 / (double)ND));
 }
 
-template <int NTILE>
+template <bool JOINT>
 __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
-    const TileSmem S = tile_smem<NTILE>(smem, t);
-    const int slot = lane & (TS - 1);
-    const bool writer = lane < TS;                 // lanes 16-31 mirror lanes 0-15 (same values, no stores)
+    const TileSmem S = tile_smem(smem, t);
+    const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
-    const bool joint = (a.phi != nullptr) && (a.cfg.err_norm != 0);
-    const double inv_ne = joint ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
-    double x[ND], xn[ND];
+    const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
+    double x[ND];
 #pragma unroll
-    for (int i = 0; i < ND; ++i) { x[i] = 0.0; xn[i] = 0.0; }
-    double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, tl = a.c.thrustLimit, rho = a.c.rho, esum = 0.0;
+    for (int i = 0; i < ND; ++i) x[i] = 0.0;
+    double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
+    LawConst lw; lw.aL = 0.0; lw.rho_inv = 1.0; lw.rho_inv_quarter_aL = 0.0;
     long long seg = -1, ia = 0;
     int na = 0, nt = 0, status = 0;
     bool active = false, lastrej = false, last = false, have = false, exhausted = false;
     unsigned visit = 0;
+    double2* rec = S.rec + slot;
     while (true) {
         int flags = 0, store_seg = 0;
         bool finished = false;
@@ -291,7 +380,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             mbar_wait(S.bar_done, (visit - 1) & 1);
             if (active) {
                 double s2 = esum;
-                if (joint) {
+                if (JOINT) {
 #pragma unroll
                     for (int c = 0; c < ND; ++c) s2 += S.errp[c * TS + slot];
                 }
@@ -303,7 +392,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                     if (eest <= 1.0) {
                         ++na; flags |= F_ACCEPT;
 #pragma unroll
-                        for (int i = 0; i < ND; ++i) x[i] = xn[i];
+                        for (int i = 0; i < ND; ++i) x[i] = S.xn[i * TS + slot];
                         if (last) { tcur = tf; finished = true; }
                         else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
                     } else {
@@ -323,52 +412,47 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
 #pragma unroll
             for (int i = 0; i < ND; ++i) nan |= !(x[i] == x[i]);
             if (nan && status == 0) status = LTO_ST_NAN;
-            if (writer) {
 #pragma unroll
-                for (int i = 0; i < ND; ++i) a.defect[seg * ND + i] = a.x_target ? x[i] - a.x_target[ia * ND + i] : x[i];
-                if (a.status) a.status[seg] = status;
-                if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
-            }
+            for (int i = 0; i < ND; ++i) a.defect[seg * ND + i] = a.x_target ? x[i] - a.x_target[ia * ND + i] : x[i];
+            if (a.status) a.status[seg] = status;
+            if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
             flags |= F_STORE; store_seg = (int)seg;
             active = false;
         }
         bool fresh = false;
-        {
-            const bool want = !active && !exhausted;
-            long long idx = -1;
-            if (writer && want) idx = (long long)atomicAdd(a.counter, 1ull);
-            idx = __shfl_sync(fullmask, idx, slot);
-            if (want) {
-                if (idx < a.n_seg) {
-                    seg = idx; ia = lto_node_a(seg, a.npt);
-                    const long long it = lto_traj_of(seg, a.npt);
+        if (!active && !exhausted) {
+            const long long idx = (long long)atomicAdd(a.counter, 1ull);
+            if (idx < a.n_seg) {
+                seg = idx; ia = lto_node_a(seg, a.npt);
+                const long long it = lto_traj_of(seg, a.npt);
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) x[i] = a.x0[ia * ND + i];
-                    tcur = a.t0[ia]; tf = a.t1[ia];
-                    if (!(tcur < tf)) tf = tcur;                          // empty span: one zero-length step, Phi = I
-                    span = tf - tcur;
-                    tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
-                    rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
-                    na = 0; nt = 0; status = 0; lastrej = false;
-                    active = true; fresh = true; flags |= F_RESET;
-                } else {
-                    exhausted = true;
-                }
+                for (int i = 0; i < ND; ++i) x[i] = a.x0[ia * ND + i];
+                tcur = a.t0[ia]; tf = a.t1[ia];
+                if (!(tcur < tf)) tf = tcur;                              // empty span: one zero-length step, Phi = I
+                span = tf - tcur;
+                const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
+                const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
+                lw.aL = tl * a.c.kthr / a.c.mass;                         // :33
+                lw.rho_inv = 1.0 / rho;
+                lw.rho_inv_quarter_aL = lw.aL / (4.0 * rho);
+                na = 0; nt = 0; status = 0; lastrej = false;
+                active = true; fresh = true; flags |= F_RESET;
+            } else {
+                exhausted = true;
             }
         }
-        const bool any_active = __any_sync(fullmask, active);
-        if (!any_active) {
-            if (writer) { S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg); }
+        if (!__any_sync(fullmask, active)) {
+            S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg);
             if (lane == 0) *S.tile_done = 1;
             mbar_arrive(S.bar_full);
             break;
         }
         // ---- one attempted step (13 stages); a fresh slot first picks its initial step
         KStore K;
-        int bad = state_stage<0, true>(K, x, 0.0, 0.0, a.c, tl, rho, S.rec + slot, writer);
+        state_stage<0>(K, x, 0.0, 0.0, a.c, lw, rec);
         if (__any_sync(fullmask, fresh)) {
             // Hairer-Norsett-Wanner initial step over the state components (drive_rk8 in lto_prop_generic.cuh)
-            double f0[ND], f1[ND], y1[ND];
+            double f0[ND], y1[ND];
 #pragma unroll
             for (int q = 0; q < 3; ++q) { f0[q] = x[3 + q]; f0[3 + q] = K.kv[0][q]; f0[6 + q] = K.kl[0][q]; f0[9 + q] = K.km[0][q]; }
             const double d0 = rms12(x, x, atol, rtol), d1 = rms12(f0, x, atol, rtol);
@@ -376,11 +460,14 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             h0 = fmin(h0, span);
 #pragma unroll
             for (int i = 0; i < ND; ++i) y1[i] = fma(h0, f0[i], x[i]);
-            SCStage st1;
-            bad |= sc_stage<ND>(y1, a.c, tl, rho, f1, st1);
+            {
+                const double R1[3] = {y1[0], y1[1], y1[2]}, V1[3] = {y1[3], y1[4], y1[5]}, L1[3] = {y1[6], y1[7], y1[8]}, M1[3] = {y1[9], y1[10], y1[11]};
+                double kv1[3], kl1[3], km1[3];
+                sc_eval<false>(R1, V1, L1, M1, a.c, lw, kv1, kl1, km1, nullptr);
 #pragma unroll
-            for (int i = 0; i < ND; ++i) f1[i] -= f0[i];
-            const double d2 = rms12(f1, x, atol, rtol) / h0;
+                for (int q = 0; q < 3; ++q) { y1[q] = V1[q] - f0[q]; y1[3 + q] = kv1[q] - f0[3 + q]; y1[6 + q] = kl1[q] - f0[6 + q]; y1[9 + q] = km1[q] - f0[9 + q]; }
+            }
+            const double d2 = rms12(y1, x, atol, rtol) / h0;
             const double dm = fmax(d1, d2);
             const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_eighth_root(dm / 0.01);
             if (fresh) h = fmin(fmin(100.0 * h0, h1), span);
@@ -389,72 +476,68 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         if (tcur + h >= tf) { h = tf - tcur; last = true; }
         if (active) ++nt;
         const double h2 = h * h;
-        bad |= state_stage<1, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<2, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<3, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<4, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<5, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<6, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<7, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<8, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<9, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<10, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<11, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        bad |= state_stage<12, true>(K, x, h, h2, a.c, tl, rho, S.rec + slot, writer);
-        esum = step_finish(K, x, h, h2, atol, rtol, xn);
-        if (active && bad) status = LTO_ST_BADP;
-        if (writer) { S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg); }
+        state_stage<1>(K, x, h, h2, a.c, lw, rec);  state_stage<2>(K, x, h, h2, a.c, lw, rec);  state_stage<3>(K, x, h, h2, a.c, lw, rec);
+        state_stage<4>(K, x, h, h2, a.c, lw, rec);  state_stage<5>(K, x, h, h2, a.c, lw, rec);  state_stage<6>(K, x, h, h2, a.c, lw, rec);
+        state_stage<7>(K, x, h, h2, a.c, lw, rec);  state_stage<8>(K, x, h, h2, a.c, lw, rec);  state_stage<9>(K, x, h, h2, a.c, lw, rec);
+        state_stage<10>(K, x, h, h2, a.c, lw, rec); state_stage<11>(K, x, h, h2, a.c, lw, rec); state_stage<12>(K, x, h, h2, a.c, lw, rec);
+        {
+            double xn[ND];
+            esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) S.xn[i * TS + slot] = xn[i];
+        }
+        S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg);
         mbar_arrive(S.bar_full);
         have = true; ++visit;
     }
 }
 
-template <int NTILE>
-__global__ void __launch_bounds__(Cfg<NTILE>::NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
-    typedef Cfg<NTILE> C;
+template <bool JOINT>
+__global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < NTILE) {
-        const TileSmem S = tile_smem<NTILE>(smem_raw, threadIdx.x);
+        const TileSmem S = tile_smem(smem_raw, threadIdx.x);
         mbar_init(S.bar_full, 32);
         mbar_init(S.bar_done, NCT);
         *S.tile_done = 0;
     }
     __syncthreads();
-    if (warp < NTILE) state_warp<NTILE>(a, warp, lane, smem_raw);
-    else column_warp<NTILE>(a, warp - NTILE, lane, smem_raw);
+    // warps 2 and 3 are the state warps: each shares its SM sub-partition with one column warp
+    if (warp == 2 || warp == 3) state_warp<JOINT>(a, warp - 2, lane, smem_raw);
+    else column_warp<JOINT>(a, warp < 2 ? warp : warp - 2, lane, smem_raw);
 }
 
 }  // namespace icw
 
-template <int NTILE>
+size_t indirect_cw_scratch_bytes(int n_sm) { return (size_t)n_sm * icw::SCRATCH_BYTES_PER_CTA; }
+
+template <bool JOINT>
 static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
-    typedef icw::Cfg<NTILE> C;
     static int n_sm = 0;
     static bool attr = false;
     if (!attr) {
         int dev = 0;
         cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(icw::k_indirect_cw<NTILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(icw::k_indirect_cw<JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw::SMEM);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    const long long per_cta = (long long)NTILE * icw::TS;
+    const long long per_cta = (long long)icw::NTILE * icw::TS;
     const int grid = (int)std::min<long long>((a.n_seg + per_cta - 1) / per_cta, (long long)n_sm);
-    icw::k_indirect_cw<NTILE><<<grid, C::NTHREADS, C::SMEM, st>>>(a);
+    icw::k_indirect_cw<JOINT><<<grid, icw::NTHREADS, icw::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
-    if (ndim != 12 || a.phi == nullptr || a.counter == nullptr || a.cfg.controller != 0 || a.n_seg <= 0 || a.n_seg > 0x7fffffffll)
+    if (ndim != 12 || a.phi == nullptr || a.counter == nullptr || a.scratch == nullptr || a.cfg.controller != 0 || a.n_seg <= 0 ||
+        a.n_seg > 0x7fffffffll)
         return cudaErrorNotSupported;
-    static int ntile = 0;
-    if (!ntile) { const char* v = getenv("LTO_ICW_NTILE"); ntile = (v && v[0] == '3') ? 3 : 2; }
-    cudaError_t e = (ntile == 2) ? launch_icw<2>(a, st) : launch_icw<3>(a, st);
+    cudaError_t e = (a.cfg.err_norm != 0) ? launch_icw<true>(a, st) : launch_icw<false>(a, st);
     if (e == cudaSuccess) *n_launch = 1;
     return e;
 }

@@ -26,6 +26,7 @@ struct IndirectArgs {
     double *defect, *phi;
     int32_t *status, *nsteps_out;
     unsigned long long* counter;               // device work-queue counter (throughput kernel)
+    double* scratch;                           // indirect_cw_scratch_bytes(n_sm) of device memory (throughput kernel)
     long long n_seg;
     int npt;
     IndirectCfg cfg;
@@ -41,6 +42,7 @@ cudaError_t launch_indirect_generic(const IndirectArgs& a, int ndim, cudaStream_
 // throughput kernels; return cudaErrorNotSupported when the configuration is not covered
 cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch);
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch);
+size_t indirect_cw_scratch_bytes(int n_sm);
 cudaError_t launch_fp64_probe(int iters, double* d_sink, int n_sm, cudaStream_t st, long long* n_threads, int* chains);
 
 }  // namespace lto
