@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--workload", default="direct7_fixed", choices=WORKLOADS)
     ap.add_argument("--n-seg", type=int, default=0, help="segments per GPU (default: 65536 direct / 131072 indirect)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fast"])
+    ap.add_argument("--err-norm", default="joint", choices=["joint", "state"], help="indirect step-control norm: x+Phi (ForwardDiff semantics) or x only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
     return ap.parse_args()
@@ -219,7 +220,8 @@ def run_ours(args):
         attempted = None
     else:
         nd = 12 if wl == "indirect12" else 14
-        p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05, kernel=kern)
+        p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05, kernel=kern,
+                                 err_norm=capi.LTO_NORM_STATE_SENS if args.err_norm == "joint" else capi.LTO_NORM_STATE)
         dx0 = torch.from_numpy(batch["x0"]).to(dev); dt0 = torch.from_numpy(batch["t0"]).to(dev); dt1 = torch.from_numpy(batch["t1"]).to(dev)
         d_def = torch.empty((n_seg, nd), dtype=torch.float64, device=dev)
         d_st = torch.empty(n_seg, dtype=torch.int32, device=dev)

@@ -172,6 +172,10 @@ int lto_sync(lto_handle* h);   /* cudaStreamSynchronize(lto_stream(h)) */
  * register-resident DFMA loop on every SM and returns achieved FLOP/s (FMA = 2). */
 int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms);
 
+/* Diagnostics: with LTO_ICW_PROF=1 in the environment at lto_init, the indirect throughput kernel
+ * records per-warp cycle counters ([CTA][warp][work, wait, count, alive]); this copies them out. */
+int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words);
+
 #ifdef __cplusplus
 }
 #endif

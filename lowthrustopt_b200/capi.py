@@ -28,7 +28,7 @@ EXPORTS = [
     "lto_direct_params_default", "lto_indirect_params_default",
     "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
-    "lto_direct_dev", "lto_indirect_dev", "lto_fp64_peak_probe",
+    "lto_direct_dev", "lto_indirect_dev", "lto_fp64_peak_probe", "lto_debug_profile",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
         L.lto_direct_dev.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 6 + [vp] * 4
         L.lto_indirect_dev.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
         L.lto_fp64_peak_probe.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lto_debug_profile.argtypes = [vp, vp, ci]
         _lib = L
     return _lib
 
@@ -193,6 +194,11 @@ class Handle:
         f = C.c_double(); ms = C.c_double()
         self._ck(lib().lto_fp64_peak_probe(self._h, int(iters), C.byref(f), C.byref(ms)))
         return f.value, ms.value
+
+    def debug_profile(self, n_words=8192):
+        out = np.zeros(n_words, dtype=np.uint64)
+        self._ck(lib().lto_debug_profile(self._h, _ptr(out), n_words))
+        return out
 
     # ---- direct ---------------------------------------------------------
     def direct(self, Xa, Xb, ua, ub, ta, tb, nsteps=10, params=None, jac=True, out=None):

@@ -7,10 +7,12 @@
 #include <cstring>
 #include <cstdarg>
 #include <algorithm>
+#include <cstdlib>
 
 using namespace lto;
 
 static char g_err[512] = "";
+static const size_t LTO_PROF_WORDS = 8192;
 
 struct lto_handle {
     int device;
@@ -22,6 +24,7 @@ struct lto_handle {
     void* d_out; size_t d_out_cap;
     unsigned long long* d_ctr;
     void* d_scr; size_t d_scr_cap;
+    unsigned long long* d_prof;                 // LTO_ICW_PROF=1: per-warp cycle counters of the last indirect throughput launch
     int64_t launches;
     double last_ms;
     char err[512];
@@ -104,6 +107,7 @@ int lto_init(int device, lto_handle** out) {
     CK(h, cudaEventCreate(&h->ev_t1));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     CK(h, cudaMalloc((void**)&h->d_ctr, 256));
+    if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
     *out = h;
     return LTO_SUCCESS;
 }
@@ -116,6 +120,7 @@ void lto_destroy(lto_handle* h) {
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->d_scr) cudaFree(h->d_scr);
+    if (h->d_prof) cudaFree(h->d_prof);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
@@ -331,7 +336,7 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
         a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
         a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
         a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
-        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr; a.scratch = (double*)h->d_scr;
+        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr; a.scratch = (double*)h->d_scr; a.prof = h->d_prof;
         rc = dispatch_indirect(h, a, ndim, p->kernel); if (rc) return rc;
         cudaEvent_t ev = h->ev_chunk[ci & 7];
         CK(h, cudaEventRecord(ev, h->s_compute));
@@ -432,8 +437,17 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
     a.thrustLimit_arr = thrustLimit_arr; a.rho_arr = rho_arr;
     if (phi) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, indirect_cw_scratch_bytes(h->n_sm)); if (rc) return rc; }
     a.defect = defect; a.status = status; a.nsteps_out = nsteps_out; a.phi = phi; a.n_seg = n_seg; a.npt = n_nodes; a.counter = h->d_ctr;
-    a.scratch = (double*)h->d_scr;
+    a.scratch = (double*)h->d_scr; a.prof = h->d_prof;
     return dispatch_indirect(h, a, ndim, p->kernel);
+}
+
+int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (!h->d_prof) return fail(h, LTO_ERR_ARG, "profiling counters are off (set LTO_ICW_PROF=1 before lto_init)");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    CK(h, cudaMemcpy(out, h->d_prof, std::min<size_t>((size_t)n_words, LTO_PROF_WORDS) * 8, cudaMemcpyDeviceToHost));
+    return LTO_SUCCESS;
 }
 
 int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms_out) {

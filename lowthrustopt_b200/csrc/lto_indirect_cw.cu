@@ -59,7 +59,13 @@ constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);        // cu
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
 constexpr size_t XN_BYTES = (size_t)ND * TS * sizeof(double);              // the state's candidate
 constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
-constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * 32;                   // + {full, done, tile_done} per tile
+constexpr size_t BAR_BYTES = 128;                                          // 13 stage barriers, done, tile_done
+constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
+// Stage-level hand-off (columns start a tile while its state warp is still producing the later
+// stages; one mbarrier per stage) was measured and is NOT faster: the 13 release-arrivals lengthen
+// the state warp's chain and both warp kinds compete for the same issue slots.  Kept switchable.
+constexpr bool STAGE_PIPE = false;
+constexpr int START_STAGE = 4;
 constexpr size_t SCRATCH_BYTES_PER_CTA = (size_t)NTILE * 2 * ND * NCT * sizeof(double);   // candidate columns (global)
 
 struct TileSmem {
@@ -76,9 +82,9 @@ __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
     s.cur = reinterpret_cast<double*>(p); p += CUR_BYTES;
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
     s.xn = reinterpret_cast<double*>(p);
-    unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * 32;
-    s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 8);
-    s.tile_done = reinterpret_cast<volatile int*>(b + 16);
+    unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * BAR_BYTES;
+    s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 13 * 8);         // bar_full + 8 j: stage j's record is published
+    s.tile_done = reinterpret_cast<volatile int*>(b + 14 * 8);
     return s;
 }
 
@@ -165,9 +171,11 @@ __device__ __forceinline__ void sym3_mul_nacc(const double M[6], const double v[
 }
 
 template <int J>
-__device__ __forceinline__ void col_stage(KStore& K, const double (&p)[ND], double h, double h2, double w2, const double2* __restrict__ rec) {
+__device__ __forceinline__ void col_stage(KStore& K, const double (&p)[ND], double h, double h2, double w2, const double2* __restrict__ rec,
+                                          unsigned bar, unsigned par) {
     double R[3], V[3], L[3], M[3];
     stage_input<J>(K, p, h, h2, R, V, L, M);
+    if (STAGE_PIPE && J > START_STAGE) mbar_wait(bar + 8 * J, par);   // the state warp may still be producing the later stages
     const double2* w = rec + J * NC2 * TS;
     double U[6], W[6], G[6];
     { const double2 a = w[0 * TS], b = w[1 * TS], c = w[2 * TS]; U[0] = a.x; U[1] = a.y; U[2] = b.x; U[3] = b.y; U[4] = c.x; U[5] = c.y; }
@@ -186,17 +194,35 @@ __device__ __forceinline__ void col_stage(KStore& K, const double (&p)[ND], doub
     K.km[J][2] = -L[2];
 }
 
+// The column warps run the same ~30 KB straight-line body; re-converging them a few times per
+// attempt keeps their instruction-fetch windows together (one miss stream instead of six).
+#ifndef LTO_ICW_NOLOCKSTEP
+#define LTO_ICW_LOCKSTEP() asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory")
+#else
+#define LTO_ICW_LOCKSTEP()
+#endif
+
 template <bool ERR>
 __device__ __forceinline__ double col_attempt(const double (&p)[ND], double h, double w2, const double2* __restrict__ rec,
-                                              double atol, double rtol, double (&pn)[ND]) {
+                                              unsigned bar, unsigned par, double atol, double rtol, double (&pn)[ND]) {
     const double h2 = h * h;
     KStore K;
-    col_stage<0>(K, p, h, h2, w2, rec);  col_stage<1>(K, p, h, h2, w2, rec);  col_stage<2>(K, p, h, h2, w2, rec);
-    col_stage<3>(K, p, h, h2, w2, rec);  col_stage<4>(K, p, h, h2, w2, rec);  col_stage<5>(K, p, h, h2, w2, rec);
-    col_stage<6>(K, p, h, h2, w2, rec);  col_stage<7>(K, p, h, h2, w2, rec);  col_stage<8>(K, p, h, h2, w2, rec);
-    col_stage<9>(K, p, h, h2, w2, rec);
-    if (ERR) col_stage<10>(K, p, h, h2, w2, rec);
-    col_stage<11>(K, p, h, h2, w2, rec); col_stage<12>(K, p, h, h2, w2, rec);
+    col_stage<0>(K, p, h, h2, w2, rec, bar, par);  col_stage<1>(K, p, h, h2, w2, rec, bar, par);  col_stage<2>(K, p, h, h2, w2, rec, bar, par);
+    col_stage<3>(K, p, h, h2, w2, rec, bar, par);  col_stage<4>(K, p, h, h2, w2, rec, bar, par);  col_stage<5>(K, p, h, h2, w2, rec, bar, par);
+    LTO_ICW_LOCKSTEP();
+#ifdef LTO_ICW_FAKE   /* timing experiment only: half the stages (wrong results) */
+#pragma unroll
+    for (int j = 6; j < 13; ++j)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { K.kv[j][q] = K.kv[j - 6][q]; K.kl[j][q] = K.kl[j - 6][q]; K.km[j][q] = K.km[j - 6][q]; }
+#else
+    col_stage<6>(K, p, h, h2, w2, rec, bar, par);  col_stage<7>(K, p, h, h2, w2, rec, bar, par);  col_stage<8>(K, p, h, h2, w2, rec, bar, par);
+    LTO_ICW_LOCKSTEP();
+    col_stage<9>(K, p, h, h2, w2, rec, bar, par);
+    if (ERR) col_stage<10>(K, p, h, h2, w2, rec, bar, par);
+    LTO_ICW_LOCKSTEP();
+    col_stage<11>(K, p, h, h2, w2, rec, bar, par); col_stage<12>(K, p, h, h2, w2, rec, bar, par);
+#endif
     return step_finish<ERR>(K, p, h, h2, atol, rtol, pn);
 }
 
@@ -209,12 +235,18 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
     double* cand_base = a.scratch + (size_t)blockIdx.x * (SCRATCH_BYTES_PER_CTA / sizeof(double)) + ct;
     unsigned alive = (1u << NTILE) - 1u;
     unsigned visit = 0;
+    long long c_wait = 0, c_work = 0, n_work = 0;
+    const long long c_begin = clock64();
     while (alive) {
 #pragma unroll 1
         for (int t = 0; t < NTILE; ++t) {
             if (!(alive & (1u << t))) continue;
             const TileSmem S = tile_smem(smem, t);
-            mbar_wait(S.bar_full, visit & 1);
+            const long long c0 = clock64();
+            mbar_wait(S.bar_full, visit & 1);                           // header + stage 0
+            if (STAGE_PIPE && !*S.tile_done) mbar_wait(S.bar_full + 8 * START_STAGE, visit & 1);
+            const long long c1 = clock64();
+            c_wait += c1 - c0;
             const bool done = *S.tile_done != 0;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
@@ -242,15 +274,19 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 }
                 if (done) continue;
                 double pn[ND];
-                const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, atol, rtol, pn);
+                const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, S.bar_full, visit & 1, atol, rtol, pn);
 #pragma unroll
                 for (int i = 0; i < ND; ++i) __stcg(sn + i * NCT, pn[i]);
                 if (JOINT) S.errp[col * TS + slot] = es;
             }
             if (done) alive &= ~(1u << t);
-            else mbar_arrive(S.bar_done);
+            else { mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += 2; }
         }
         ++visit;
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + NTILE + cw) * 4;
+        o[0] = c_work; o[1] = c_wait; o[2] = n_work; o[3] = clock64() - c_begin;
     }
 }
 
@@ -341,12 +377,31 @@ __device__ __forceinline__ void sc_eval(const double (&R)[3], const double (&V)[
     }
 }
 
+// One out-of-line copy of the right-hand side serves all 13 stages: the state warp's code
+// must stay small, or its instruction stream evicts the column warps' loop body from the
+// instruction cache (ncu: stall_no_inst was the top stall of BOTH warp kinds).
+__device__ __noinline__ void sc_eval_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
+                                          double m0, double m1, double m2, const SCConst* c, double aL, double rho_inv, double rq,
+                                          double2* w, double* out) {
+    const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, v2}, L[3] = {l0, l1, l2}, M[3] = {m0, m1, m2};
+    LawConst lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rho_inv_quarter_aL = rq;
+    double kv[3], kl[3], km[3];
+    sc_eval<true>(R, V, L, M, *c, lw, kv, kl, km, w);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { out[q] = kv[q]; out[3 + q] = kl[q]; out[6 + q] = km[q]; }
+}
+
 template <int J>
 __device__ __forceinline__ void state_stage(KStore& K, const double (&x)[ND], double h, double h2, const SCConst& c, const LawConst& lw,
-                                            double2* __restrict__ rec) {
+                                            double2* __restrict__ rec, unsigned bar) {
     double R[3], V[3], L[3], M[3];
     stage_input<J>(K, x, h, h2, R, V, L, M);
-    sc_eval<true>(R, V, L, M, c, lw, K.kv[J], K.kl[J], K.km[J], rec + J * NC2 * TS);
+    double out[9];
+    sc_eval_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], &c, lw.aL, lw.rho_inv, lw.rho_inv_quarter_aL,
+                 rec + J * NC2 * TS, out);
+    if (STAGE_PIPE && J > 0) mbar_arrive(bar + 8 * J);     // stage J's record is published (stage 0 goes out with the header)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { K.kv[J][q] = out[q]; K.kl[J][q] = out[3 + q]; K.km[J][q] = out[6 + q]; }
 }
 
 __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
@@ -373,11 +428,17 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     bool active = false, lastrej = false, last = false, have = false, exhausted = false;
     unsigned visit = 0;
     double2* rec = S.rec + slot;
+    long long c_wait = 0, c_work = 0, c_pre = 0;
+    const long long c_begin = clock64();
     while (true) {
         int flags = 0, store_seg = 0;
         bool finished = false;
+        const long long c0 = clock64();
+        long long c1 = c0;
         if (have) {
             mbar_wait(S.bar_done, (visit - 1) & 1);
+            c1 = clock64();
+            c_wait += c1 - c0;
             if (active) {
                 double s2 = esum;
                 if (JOINT) {
@@ -448,8 +509,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             break;
         }
         // ---- one attempted step (13 stages); a fresh slot first picks its initial step
+        const long long c2 = clock64();
+        c_pre += c2 - c1;
         KStore K;
-        state_stage<0>(K, x, 0.0, 0.0, a.c, lw, rec);
+        state_stage<0>(K, x, 0.0, 0.0, a.c, lw, rec, S.bar_full);
         if (__any_sync(fullmask, fresh)) {
             // Hairer-Norsett-Wanner initial step over the state components (drive_rk8 in lto_prop_generic.cuh)
             double f0[ND], y1[ND];
@@ -475,20 +538,27 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         last = false;
         if (tcur + h >= tf) { h = tf - tcur; last = true; }
         if (active) ++nt;
+        S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg);
+        if (STAGE_PIPE) mbar_arrive(S.bar_full);                         // header + stage 0
         const double h2 = h * h;
-        state_stage<1>(K, x, h, h2, a.c, lw, rec);  state_stage<2>(K, x, h, h2, a.c, lw, rec);  state_stage<3>(K, x, h, h2, a.c, lw, rec);
-        state_stage<4>(K, x, h, h2, a.c, lw, rec);  state_stage<5>(K, x, h, h2, a.c, lw, rec);  state_stage<6>(K, x, h, h2, a.c, lw, rec);
-        state_stage<7>(K, x, h, h2, a.c, lw, rec);  state_stage<8>(K, x, h, h2, a.c, lw, rec);  state_stage<9>(K, x, h, h2, a.c, lw, rec);
-        state_stage<10>(K, x, h, h2, a.c, lw, rec); state_stage<11>(K, x, h, h2, a.c, lw, rec); state_stage<12>(K, x, h, h2, a.c, lw, rec);
+        state_stage<1>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<2>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<3>(K, x, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage<4>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<5>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<6>(K, x, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage<7>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<8>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<9>(K, x, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage<10>(K, x, h, h2, a.c, lw, rec, S.bar_full); state_stage<11>(K, x, h, h2, a.c, lw, rec, S.bar_full); state_stage<12>(K, x, h, h2, a.c, lw, rec, S.bar_full);
         {
             double xn[ND];
             esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
 #pragma unroll
             for (int i = 0; i < ND; ++i) S.xn[i * TS + slot] = xn[i];
         }
-        S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg);
-        mbar_arrive(S.bar_full);
+        if (!STAGE_PIPE) mbar_arrive(S.bar_full);                        // the whole attempt's record
+        c_work += clock64() - c2;
         have = true; ++visit;
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + t) * 4;
+        o[0] = c_work; o[1] = c_wait; o[2] = visit; o[3] = clock64() - c_begin;
+        a.prof[(size_t)gridDim.x * NW * 4 + (size_t)blockIdx.x * NTILE + t] = c_pre;
     }
 }
 
@@ -498,14 +568,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < NTILE) {
         const TileSmem S = tile_smem(smem_raw, threadIdx.x);
-        mbar_init(S.bar_full, 32);
+        for (int j = 0; j < 13; ++j) mbar_init(S.bar_full + 8 * j, 32);
         mbar_init(S.bar_done, NCT);
         *S.tile_done = 0;
     }
     __syncthreads();
-    // warps 2 and 3 are the state warps: each shares its SM sub-partition with one column warp
-    if (warp == 2 || warp == 3) state_warp<JOINT>(a, warp - 2, lane, smem_raw);
-    else column_warp<JOINT>(a, warp < 2 ? warp : warp - 2, lane, smem_raw);
+    // warps 3 and 7 (both on SM sub-partition 3) are the state warps; the other three sub-partitions
+    // each host two column warps that run the same instruction stream side by side
+    if ((warp & 3) == 3) state_warp<JOINT>(a, warp >> 2, lane, smem_raw);
+    else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
 }
 
 }  // namespace icw

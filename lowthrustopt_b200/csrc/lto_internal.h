@@ -27,6 +27,7 @@ struct IndirectArgs {
     int32_t *status, *nsteps_out;
     unsigned long long* counter;               // device work-queue counter (throughput kernel)
     double* scratch;                           // indirect_cw_scratch_bytes(n_sm) of device memory (throughput kernel)
+    unsigned long long* prof;                  // optional per-warp cycle counters [grid][8 warps][4] (diagnostics), or NULL
     long long n_seg;
     int npt;
     IndirectCfg cfg;
