@@ -29,7 +29,7 @@
 // shared-memory stash and its candidate in an L2-resident scratch, so rejecting a step
 // costs nothing extra.
 // The initial step is Hairer's estimate over the state components (the generic kernel
-// and the oracle take it over x and Phi): the two paths may choose different step
+// and the CPU checker take it over x and Phi): the two paths may choose different step
 // sequences and agree to the integration tolerance, not to rounding.
 #include "lto_internal.h"
 #include "lto_cw_common.cuh"
