@@ -1,0 +1,400 @@
+"""Host-side mirror of the reference's two outer solvers, for running BASELINE configs 1-2
+(the demo scripts) end to end without Julia / Ipopt / SuiteSparse.
+
+    multiShoot_CRTBP_direct      src/multiShoot_CRTBP_direct.jl:58-594
+    multiShoot_CRTBP_indirect    src/multiShoot_CRTBP_indirect.jl:58-345
+    reduceFuel_indirect          src/HelperFunctions.jl:105-193
+    trajectory_stack_guess       CRTBP_Multishoot_direct_demo.jl:117-157
+
+Same names, argument order and return values.  Arrays use the reference's shapes
+(nstate x n_nodes etc.).  What stays on the host is only the small dense linear algebra of
+the update step; EVERY propagation goes through a `backend` -- by default `GpuBackend`
+(liblto_b200.so on the B200; there is no CPU propagation in this package).  The line
+searches and the two t_f-perturbed defect evaluations are issued as ONE batched call
+each (n_traj = 20 / 10 / 2) instead of the reference's sequential loops.
+
+Deliberate, documented substitutions for third-party solvers that are not part of the hot path:
+  * direct QP (JuMP + Ipopt, :264-386): with flagEnd = false (what the demo runs) every bound
+    collapses to an equality, the problem is an equality-constrained convex QP and is solved
+    exactly through its KKT system.  flagEnd = true needs bound constraints -> NotImplementedError.
+  * indirect step (`-sparse(J) \\ defect`, SuiteSparseQR, :181-182): dense least squares; the
+    system has full column rank once the structurally empty columns are dropped.
+"""
+import numpy as np
+
+from . import capi
+from .capi import DAY
+from .synthetic import interp_initial_states, load_orbit
+
+
+# --------------------------------------------------------------------------- backends
+class GpuBackend:
+    """All propagation on the GPU through the C ABI (lowthrustopt_b200.capi.Handle)."""
+
+    def __init__(self, handle=None, device=0):
+        self.h = handle or capi.Handle(device)
+        self.calls = 0
+
+    # direct: X (B, N, n), U (B, N, 3), t (B, N)
+    def direct_defect(self, X, U, t, nsteps, Isp, MU, DU, TU):
+        self.calls += 1
+        r = self.h.direct_traj(X, U, t, nsteps=nsteps, params=capi.direct_params(Isp=Isp, MU_=MU, DU_=DU, TU_=TU), jac=False)
+        B, N, n = X.shape
+        return r["defect"].reshape(B, N - 1, n), r["errors"].reshape(B, N - 1)
+
+    def direct_blocks(self, X, U, t, nsteps, Isp, MU, DU, TU):
+        self.calls += 1
+        r = self.h.direct_traj(X, U, t, nsteps=nsteps, params=capi.direct_params(Isp=Isp, MU_=MU, DU_=DU, TU_=TU), jac=True)
+        B, N, n = X.shape
+        return r["defect"].reshape(B, N - 1, n), r["errors"].reshape(B, N - 1), r["jac"].reshape(B, N - 1, 2 * (n + 3), n).transpose(0, 1, 3, 2)
+
+    # indirect: XC (B, N, m), t (B, N); params = the reference's tuple
+    def _ip(self, params, **kw):
+        MU, DU, TU, thrustLimit, mass, td, p, rho = params
+        if not (p == 0 or p >= 1):
+            raise ValueError("Invalid value of p!")                       # CRTBP_stateCostate_deriv.jl:52
+        return capi.indirect_params(thrustLimit=thrustLimit, mass=mass, time_direction=td, p=p, rho=rho, MU_=MU, DU_=DU, TU_=TU, **kw)
+
+    def indirect_defect(self, XC, t, params):
+        self.calls += 1
+        r = self.h.indirect_traj(XC, t, params=self._ip(params), jac=False)
+        B, N, m = XC.shape
+        return r["defect"].reshape(B, N - 1, m)
+
+    def indirect_blocks(self, XC, t, params):
+        self.calls += 1
+        r = self.h.indirect_traj(XC, t, params=self._ip(params), jac=True)
+        B, N, m = XC.shape
+        return r["defect"].reshape(B, N - 1, m), r["phi"].reshape(B, N - 1, m, m).transpose(0, 1, 3, 2)
+
+    def propagate(self, x0, t0, t1, params):
+        """x(t1) for independent rows x0 (B, m): solve(ODEProblem(odefun, x0, (t0, t1), params), Vern8(), 1e-13)[:, end]."""
+        self.calls += 1
+        return self.h.indirect(x0, t0, t1, params=self._ip(params), jac=False)["defect"]
+
+
+_default_backend = None
+
+
+def default_backend():
+    global _default_backend
+    if _default_backend is None:
+        _default_backend = GpuBackend()
+    return _default_backend
+
+
+# --------------------------------------------------------------------------- endpoint helpers
+def _orbit_states(X_states):
+    """Accept the reference's 6 x 100 table (X0_states) and return a tau -> state(6) function:
+    interpolating natural cubic spline on LinRange(0, 1, 100), tau wrapped to [0, 1]
+    (HelperFunctions.jl:18-35, multiShoot_CRTBP_direct.jl:434-461)."""
+    from scipy.interpolate import CubicSpline
+    X_states = np.asarray(X_states, dtype=np.float64)
+    sp = CubicSpline(np.linspace(0.0, 1.0, X_states.shape[1]), X_states.T, bc_type="natural")
+
+    def wrap(tau):
+        tau = float(tau)
+        while tau > 1:
+            tau -= 1
+        while tau < 0:
+            tau += 1
+        return tau
+    return lambda tau: sp(wrap(tau))
+
+
+def interpInitialStates(p1, X0_times, X0_states, MU=None):
+    return _orbit_states(X0_states)(p1)
+
+
+def interpEndStates(tau1, tau2, X0_times, X0_states, Xf_times, Xf_states, MU=None):
+    return _orbit_states(X0_states)(tau1), _orbit_states(Xf_states)(tau2)
+
+
+def find_tau(X_times, X_states, state, MU=None):
+    """find_τ (HelperFunctions.jl:38-48): the first of 1001 uniform tau with the smallest distance."""
+    f = _orbit_states(X_states)
+    tau_trial = np.linspace(0.0, 1.0, 1001)
+    d = np.array([np.linalg.norm(f(tt) - state) for tt in tau_trial])
+    return float(tau_trial[np.argmin(d)])
+
+
+def controlLaw_cart(lambda_v, thrustLimit, p, rho, mass, DU=capi.DU, TU=capi.TU):
+    """Control [N] from the primer vector (multiShoot_CRTBP_indirect.jl:389-440); post-processing only."""
+    n = np.linalg.norm(lambda_v)
+    aL = thrustLimit / mass / 1e3 * TU ** 2 / DU
+    if p == 0:
+        umag = aL
+    elif p == 1:
+        umag = 0.5 * (1 + np.tanh((n - 1) / (2 * rho))) * aL
+    elif p > 1:
+        umag = min((n / p) ** (1 / (p - 1)), aL)
+    else:
+        raise ValueError("Invalid value of p!")
+    if not n > 0 or np.isnan(umag):
+        return np.zeros(3)
+    return -umag * np.asarray(lambda_v) / n * mass * DU * 1e3 / TU ** 2
+
+
+def trajectory_stack_guess(X0_states, Xf_states, MU=capi.MU, DU=capi.DU, TU=capi.TU, n_nodes=30, tof1_days=10.0, tof2_days=10.0,
+                           tau1=0.75, backend=None):
+    """The demos' trajectory-stacking initial guess (CRTBP_Multishoot_direct_demo.jl:117-157): two ballistic
+    arcs (thrustLimit = 0), the second starting at the point of the final orbit closest to the end of the
+    first.  The reference samples two dense-output solutions; here every node is its own propagation
+    from the arc's start (one batched call per arc), which agrees to the integration tolerance.
+    Returns (XC_trajectoryStack 12 x n_nodes, t_TU, tau1, tau2, state_0, state_f)."""
+    be = backend or default_backend()
+    tof1 = tof1_days * DAY / TU; tof2 = tof2_days * DAY / TU; tof = tof1 + tof2
+    t_TU = np.linspace(0.0, tof, n_nodes)
+    t1 = t_TU[t_TU < tof1]; t2 = t_TU[t_TU >= tof1]
+    params = (MU, DU, TU, 0.0, 1e3, 1.0, 1.0, 1.0)
+    state_0 = np.concatenate([_orbit_states(X0_states)(tau1), np.zeros(6)])
+    ends = np.concatenate([t1, [tof1]])
+    arc1 = be.propagate(np.tile(state_0, (ends.size, 1)), np.zeros(ends.size), ends, params)
+    tau2_0 = find_tau(None, Xf_states, arc1[-1, :6])
+    state_f0 = np.concatenate([_orbit_states(Xf_states)(tau2_0), np.zeros(6)])
+    ends2 = np.concatenate([t2, [tof1 + tof2]])
+    arc2 = be.propagate(np.tile(state_f0, (ends2.size, 1)), np.full(ends2.size, tof1), ends2, params)
+    tau2 = find_tau(None, Xf_states, arc2[-1, :6])
+    state_f = np.concatenate([_orbit_states(Xf_states)(tau2), np.zeros(6)])
+    XC = np.vstack([arc1[:-1], arc2[:-1]]).T.copy()
+    XC[:, 0] = state_0
+    XC[:, -1] = state_f
+    return XC, t_TU, tau1, tau2, state_0, state_f
+
+
+# --------------------------------------------------------------------------- direct method
+def _band_direct(blocks, n, N):
+    """Scatter of jacobianCalc (multiShoot_CRTBP_direct.jl:146-162): blocks (N-1, n, 2(n+3)) -> Jac_full."""
+    J = np.zeros((n * (N - 1), N * (n + 3)))
+    for i in range(N - 1):
+        rows = slice(i * n, (i + 1) * n)
+        J[rows, i * n:(i + 2) * n] = blocks[i][:, :2 * n]
+        c0 = n * N + 3 * i
+        J[rows, c0:c0 + 6] = blocks[i][:, 2 * n:]
+    return J
+
+
+def _qp_direct(X_all, u_all, dV1, dV2, defect, Jac_full, n, N, state_0, state_f, mass, tau, t0_TU, tf_TU, DU, TU, allowImpulsive):
+    """optimizeTraj (:248-403) for flagEnd = false: variables [X_jump | u_jump | dV1_jump | dV2_jump]
+    (tf_jump, p1_jump, p2_jump are pinned to 0 by their bounds, :288-293)."""
+    nX, nU = n * N, 3 * N
+    nz = nX + nU + 6
+    t_fixed = t0_TU + (tau + 1) / 2 * (tf_TU - t0_TU)
+    dt = np.diff(t_fixed)
+    dt_temp = np.concatenate([dt / 2, [dt[-1] / 2]]) + np.concatenate([[0.0], dt[:-1] / 2, [0.0]])      # :323-325
+    w = np.repeat(dt_temp, 3)
+    s = (DU / TU) ** 2
+    H = np.zeros(nz); g = np.zeros(nz)
+    H[nX:nX + nU] = 2 * w; g[nX:nX + nU] = 2 * w * u_all.T.ravel()
+    H[nX + nU:] = 2 * s; g[nX + nU:] = 2 * s * np.concatenate([dV1, dV2])
+    rows = []; rhs = []
+    A_dyn = np.zeros((Jac_full.shape[0], nz)); A_dyn[:, :nX + nU] = -Jac_full[:, :nX + nU]                 # :337
+    rows.append(A_dyn); rhs.append(defect.T.ravel())
+    E = np.zeros((12, nz))
+    for k in range(6):
+        E[k, k] = 1.0; E[6 + k, (N - 1) * n + k] = 1.0
+    for k in range(3):
+        E[3 + k, nX + nU + k] = 1.0; E[9 + k, nX + nU + 3 + k] = 1.0
+    b0 = state_0 - X_all[:6, 0] - np.concatenate([np.zeros(3), dV1])                                       # :374-375
+    bf = state_f - X_all[:6, -1] - np.concatenate([np.zeros(3), dV2])
+    rows.append(E); rhs.append(np.concatenate([b0, bf]))
+    if n == 7:
+        M = np.zeros((1, nz)); M[0, 6] = 1.0
+        rows.append(M); rhs.append(np.array([mass - X_all[6, 0]]))                                        # :270
+    if not allowImpulsive:
+        Z = np.zeros((6, nz)); Z[np.arange(6), nX + nU + np.arange(6)] = 1.0
+        rows.append(Z); rhs.append(np.zeros(6))                                                           # :301-302
+    A = np.vstack(rows); b = np.concatenate(rhs)
+    nc = A.shape[0]
+    K = np.zeros((nz + nc, nz + nc))
+    K[np.arange(nz), np.arange(nz)] = H
+    K[:nz, nz:] = A.T; K[nz:, :nz] = A
+    r = np.concatenate([-g, b])
+    try:
+        sol = np.linalg.solve(K, r)
+        if not np.all(np.isfinite(sol)):
+            raise np.linalg.LinAlgError
+    except np.linalg.LinAlgError:
+        sol = np.linalg.lstsq(K, r, rcond=None)[0]
+    z = sol[:nz]
+    x_update = z[:nX].reshape(N, n).T
+    u_update = z[nX:nX + nU].reshape(N, 3).T
+    dV1_update = z[nX + nU:nX + nU + 3]; dV2_update = z[nX + nU + 3:]
+    cost = float(np.sum((u_all.T.ravel() + z[nX:nX + nU]) ** 2 * w) + s * np.sum((dV1 + dV1_update) ** 2) + s * np.sum((dV2 + dV2_update) ** 2))
+    return x_update, u_update, dV1_update, dV2_update, cost
+
+
+def multiShoot_CRTBP_direct(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, MU, DU, TU, n_nodes, nsteps, mass, Isp, X0_times, X0_states,
+                            Xf_times, Xf_states, plot_yn=False, flagEnd=False, beta=0.0, allowImpulsive=False, maxIter=100,
+                            backend=None, log=None):
+    """(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, defect) = multiShoot_CRTBP_direct(...)   (:58-60, :593).
+    `log`, if a list, receives one dict per SQP iteration (iter, er, cost, alpha)."""
+    if flagEnd:
+        raise NotImplementedError("flagEnd = true makes the subproblem a bound-constrained NLP (Ipopt, :286-298); only the "
+                                  "demo's flagEnd = false equality-constrained QP is mirrored")
+    be = backend or default_backend()
+    X_all = np.array(X_all, dtype=np.float64); u_all = np.array(u_all, dtype=np.float64); t_TU = np.array(t_TU, dtype=np.float64)
+    dV1 = np.array(dV1, dtype=np.float64); dV2 = np.array(dV2, dtype=np.float64)
+    n = X_all.shape[0]; N = n_nodes
+    t0_TU = t_TU[0]; tf_TU = t_TU[-1]
+    tau = (t_TU - t0_TU) / (tf_TU - t0_TU) * 2 - 1                                                        # :481
+
+    def defectCalc(X, U, t):
+        d, e = be.direct_defect(X.T[None], U.T[None], t[None], nsteps, Isp, MU, DU, TU)
+        return d[0].T.copy(), e[0]
+
+    defect, errors = defectCalc(X_all, u_all, t_TU)                                                       # :486
+    iterCount = 0; er = 1.0
+    while er > 1e-6:                                                                                      # :491
+        iterCount += 1
+        if iterCount > maxIter:
+            break
+        _, _, blocks = be.direct_blocks(X_all.T[None], u_all.T[None], t_TU[None], nsteps, Isp, MU, DU, TU)   # :500
+        Jac_full = _band_direct(blocks[0], n, N)
+        pert_tf = 1e-3                                                                                    # :504
+        t0_TU = t_TU[0]; tf_TU = t_TU[-1]
+        t_mod = np.stack([t0_TU + (tau + 1) / 2 * (tf_TU + pert_tf - t0_TU), t0_TU + (tau + 1) / 2 * (tf_TU - pert_tf - t0_TU)])
+        dm, _ = be.direct_defect(np.stack([X_all.T] * 2), np.stack([u_all.T] * 2), t_mod, nsteps, Isp, MU, DU, TU)   # :511-512 (one batch)
+        ddefect_dt = (dm[0] - dm[1]) / (2 * pert_tf)
+        Jac_full = np.hstack([Jac_full, ddefect_dt.ravel()[:, None]])                                     # :516
+        state_0, state_f = interpEndStates(tau1, tau2, X0_times, X0_states, Xf_times, Xf_states, MU)
+        x_update, u_update, dV1_update, dV2_update, cost = _qp_direct(X_all, u_all, dV1, dV2, defect, Jac_full, n, N, state_0, state_f,
+                                                                      mass, tau, t0_TU, tf_TU, DU, TU, allowImpulsive)
+        alpha = 1.0
+        if iterCount > 10:                                                                                # :559-561, lineSearch :405-430
+            alpha_all = np.linspace(0.1, 1.0, 10)
+            Xt = np.stack([(X_all + x_update * a).T for a in alpha_all]); Ut = np.stack([(u_all + u_update * a).T for a in alpha_all])
+            dd, _ = be.direct_defect(Xt, Ut, np.stack([t_TU] * 10), nsteps, Isp, MU, DU, TU)
+            ers = np.sum(dd.reshape(10, -1) ** 2, axis=1)
+            alpha = float(alpha_all[np.argmin(ers)])
+        X_all = X_all + x_update * alpha; u_all = u_all + u_update * alpha                                # :563-569
+        dV1 = dV1 + dV1_update * alpha; dV2 = dV2 + dV2_update * alpha
+        t_TU = t0_TU + (tau + 1) / 2 * (tf_TU - t0_TU)                                                    # :582
+        defect, errors = defectCalc(X_all, u_all, t_TU)                                                   # :585
+        er = float(np.max(np.abs(defect)))
+        if log is not None:
+            log.append(dict(iter=iterCount, er=er, cost=cost, alpha=alpha))
+    return X_all, u_all, tau1, tau2, t_TU, dV1, dV2, defect
+
+
+# --------------------------------------------------------------------------- indirect method
+def _band_indirect(phi, nstate, N):
+    """Band assembly of jacobianCalc (multiShoot_CRTBP_indirect.jl:127-142): phi (N-1, m, m) -> Jac_full."""
+    m = 2 * nstate
+    J = np.zeros((m * (N - 1), N * m))
+    eye = np.eye(m)
+    for i in range(N - 1):
+        J[i * m:(i + 1) * m, i * m:(i + 1) * m] = phi[i]
+        J[i * m:(i + 1) * m, (i + 1) * m:(i + 2) * m] = -eye
+    J[:, :nstate] = 0.0                                                                                   # :141
+    J[:, -2 * nstate:-nstate] = 0.0                                                                       # :142
+    return J
+
+
+def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLimit, plot_yn=False, flag_adjointsOnly=False,
+                              maxIter=50, p=1.0, rho=1.0, backend=None, log=None):
+    """(XC_all, defect, status_flag) = multiShoot_CRTBP_indirect(...)   (:58-59, :344)."""
+    be = backend or default_backend()
+    XC_all = np.array(XC_all, dtype=np.float64); t_TU = np.asarray(t_TU, dtype=np.float64)
+    nstate = XC_all.shape[0] // 2; m = 2 * nstate; N = n_nodes
+    if nstate != 6:
+        raise NotImplementedError("the reference's indirect solver hard-codes the 12-dim RHS (:258) and 6-element end pins (:324-325)")
+    params = (MU, DU, TU, thrustLimit, mass0, 1.0, p, rho)                                                # :260
+    status_flag = 0
+    state_0 = XC_all[:nstate, 0].copy(); state_f = XC_all[:nstate, -1].copy()
+
+    def defectCalc(XC):
+        return be.indirect_defect(XC.T[None], t_TU[None], params)[0].T.copy()
+
+    keep = np.ones(N * m, dtype=bool)
+    if flag_adjointsOnly:                                                                                 # :169-178
+        for ind in range(N - 1):
+            keep[ind * m:ind * m + nstate] = False
+
+    def solve(J, dvec):
+        """-sparse(J) \\ d (:181-182): least squares over the structurally non-empty columns, 0 elsewhere."""
+        Jk = J[:, keep]
+        live = np.any(Jk != 0.0, axis=0)
+        sol = np.zeros(Jk.shape[1])
+        sol[live] = -np.linalg.lstsq(Jk[:, live], dvec, rcond=None)[0]
+        full = np.zeros(N * m)
+        full[keep] = sol
+        return full.reshape(N, m).T
+
+    defect = defectCalc(XC_all)                                                                           # :274
+    iterCount = 0; er = 1.0
+    while er > 1e-10:                                                                                     # :280
+        iterCount += 1
+        if iterCount > maxIter:
+            status_flag = 1
+            break
+        _, phi = be.indirect_blocks(XC_all.T[None], t_TU[None], params)                                   # :290
+        Jac_full = _band_indirect(phi[0], nstate, N)
+        xc_update = solve(Jac_full, defect.T.ravel())
+        if np.max(np.abs(xc_update)) < 1e-1:                                                              # SOC :190-214
+            d_soc = defectCalc(XC_all + xc_update)
+            xc_update = xc_update + solve(Jac_full, d_soc.T.ravel())
+        alpha = 1.0
+        if iterCount > 3:                                                                                 # :300-302, lineSearch :221-246
+            alpha_all = np.linspace(0.1, 1.0, 20)
+            trial = np.stack([(XC_all + xc_update * a).T for a in alpha_all])
+            dd = be.indirect_defect(trial, np.stack([t_TU] * 20), params)
+            ers = np.sum(dd.reshape(20, -1) ** 2, axis=1)
+            alpha = float(alpha_all[np.argmin(ers)])
+        XC_all = XC_all + xc_update * alpha                                                               # :304
+        XC_all[:6, 0] = state_0; XC_all[:6, -1] = state_f                                                 # :324-325
+        defect = defectCalc(XC_all)                                                                       # :328
+        er = float(np.max(np.abs(defect)))
+        if log is not None:
+            log.append(dict(iter=iterCount, er=er, alpha=alpha))
+        if not er <= 1e3:                                                                                 # :333-336 (also catches NaN)
+            iterCount += 100
+            if np.isnan(er):
+                break
+    if np.isnan(XC_all[0, 0]):                                                                            # :339-341
+        status_flag = 2
+    return XC_all, defect, status_flag
+
+
+def reduceFuel_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rho_current, rho_target, backend=None, rng=None,
+                        log=None):
+    """rho-continuation driver (HelperFunctions.jl:105-193).  `rng` supplies the rand() of the back-off (:182)."""
+    rng = rng or np.random.default_rng(0)
+    if rho_target > rho_current:
+        rho_target = rho_current
+    p = 1.0; rho_temp = rho_current; maxIter = 10
+
+    def run(XC, rho):
+        out = multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, False, False, maxIter, p, rho, backend=backend)
+        if log is not None:
+            log.append(dict(rho=rho, status=out[2], er=float(np.max(np.abs(out[1])))))
+        return out
+
+    XC_new, defect, status = run(XC_all, rho_temp)
+    if status == 0 and rho_current == rho_target:
+        return XC_new, defect, status
+    while status != 0 and rho_temp < 1:                                                                   # :131-141
+        rho_temp = min(rho_temp * 5, 1.0)
+        XC_new, defect, status = run(XC_all, rho_temp)
+    if rho_temp == 1 and status != 0:
+        return XC_new, defect, status
+    if status == 0:
+        XC_all = XC_new.copy()
+    count = 0
+    while rho_temp > rho_target or status != 0:                                                           # :155-187
+        count += 1
+        if count > 100:
+            return XC_new, defect, 3
+        if status == 0:
+            XC_all = XC_new.copy()
+            rho_temp = max(rho_temp / 2, rho_target)
+        else:
+            rho_temp *= 3 * (1 + rng.random())
+        XC_new, defect, status = run(XC_all, rho_temp)
+    return XC_new, defect, status
+
+
+def demo_fixtures():
+    """(X0_times, X0_states, Xf_times, Xf_states) as the demos load them (CRTBP_Multishoot_direct_demo.jl:68-71)."""
+    X0 = load_orbit(1); Xf = load_orbit(2)
+    return np.linspace(0, 1, X0.shape[1]), X0, np.linspace(0, 1, Xf.shape[1]), Xf

@@ -1,0 +1,60 @@
+"""TEST INFRASTRUCTURE: a `backend` for lowthrustopt_b200.solvers that routes every propagation
+through the CPU oracle instead of the GPU, so the host loops can be (a) exercised on a CPU-only
+machine and (b) run twice -- oracle-backed and GPU-backed -- to compare converged trajectories."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+class OracleBackend:
+    def __init__(self, jac="var"):
+        O.build()
+        self.nt = O.num_threads()
+        self.jac = jac          # "var": variational / dual numbers; "fd": the reference's forward differences (direct only)
+        self.calls = 0
+
+    @staticmethod
+    def _pairs(X, U, t):
+        B, N, n = X.shape
+        return (X[:, :-1].reshape(-1, n), X[:, 1:].reshape(-1, n), U[:, :-1].reshape(-1, 3), U[:, 1:].reshape(-1, 3),
+                t[:, :-1].ravel(), t[:, 1:].ravel())
+
+    def direct_defect(self, X, U, t, nsteps, Isp, MU, DU, TU):
+        self.calls += 1
+        B, N, n = X.shape
+        d, e, st, _ = O.direct_defect(*self._pairs(X, U, t), nsteps=nsteps, dp=O.dparams(MU, DU, TU, Isp), nthreads=self.nt)
+        return d.reshape(B, N - 1, n), e.reshape(B, N - 1)
+
+    def direct_blocks(self, X, U, t, nsteps, Isp, MU, DU, TU):
+        self.calls += 1
+        B, N, n = X.shape
+        pr = self._pairs(X, U, t)
+        dp = O.dparams(MU, DU, TU, Isp)
+        if self.jac == "fd":
+            d, e, st, _ = O.direct_defect(*pr, nsteps=nsteps, dp=dp, nthreads=self.nt)
+            J = O.direct_jac_fd(*pr, d, nsteps=nsteps, dp=dp, nthreads=self.nt)
+        else:
+            d, e, J, st = O.direct_jac_var(*pr, nsteps=nsteps, dp=dp, nthreads=self.nt)
+        return d.reshape(B, N - 1, n), e.reshape(B, N - 1), J.reshape(B, N - 1, n, 2 * (n + 3))
+
+    @staticmethod
+    def _ip(params):
+        MU, DU, TU, thrustLimit, mass, td, p, rho = params
+        return O.iparams(thrustLimit, mass=mass, td=td, p=p, rho=rho, MU_=MU, DU_=DU, TU_=TU)
+
+    def indirect_defect(self, XC, t, params):
+        self.calls += 1
+        B, N, m = XC.shape
+        xe, st, _, _ = O.indirect_prop(XC[:, :-1].reshape(-1, m), t[:, :-1].ravel(), t[:, 1:].ravel(), self._ip(params), nthreads=self.nt)
+        return (xe - XC[:, 1:].reshape(-1, m)).reshape(B, N - 1, m)
+
+    def indirect_blocks(self, XC, t, params):
+        self.calls += 1
+        B, N, m = XC.shape
+        xe, phi, st, _, _ = O.indirect_prop_jac(XC[:, :-1].reshape(-1, m), t[:, :-1].ravel(), t[:, 1:].ravel(), self._ip(params),
+                                                nthreads=self.nt)
+        return (xe - XC[:, 1:].reshape(-1, m)).reshape(B, N - 1, m), phi.reshape(B, N - 1, m, m)
+
+    def propagate(self, x0, t0, t1, params):
+        self.calls += 1
+        return O.indirect_prop(x0, t0, t1, self._ip(params), nthreads=self.nt)[0]

@@ -1,0 +1,90 @@
+"""GPU: BASELINE configs 1-2 (the two demo scripts) end to end.  The same host loops
+(lowthrustopt_b200/solvers.py) are run twice -- every propagation on the GPU through the C ABI, and every
+propagation through the CPU oracle -- and the converged trajectories are compared.
+
+Tolerances (BASELINE.json north_star): converged trajectories 1e-8, final mass 1e-9 (relative)."""
+import numpy as np
+import pytest
+
+from lowthrustopt_b200 import capi, solvers as S
+from oracle_backend import OracleBackend
+
+pytestmark = pytest.mark.gpu
+MU, DU, TU = capi.MU, capi.DU, capi.TU
+TOL_TRAJ = 1e-8
+TOL_MASS = 1e-9
+
+
+@pytest.fixture(scope="module")
+def backends(lto):
+    return S.GpuBackend(handle=lto), OracleBackend()
+
+
+def _direct(be, fx, guess, nstate):
+    X0t, X0, Xft, Xf = fx
+    XC, t_TU, tau1, tau2, s0, sf = guess
+    X_all = XC[:6].copy()
+    if nstate == 7:
+        X_all = np.vstack([X_all, 1000.0 * np.ones((1, 30))])
+    log = []
+    out = S.multiShoot_CRTBP_direct(X_all, np.zeros((3, 30)), tau1, tau2, t_TU, np.zeros(3), np.zeros(3), MU, DU, TU, 30, 10, 1e3, 2000.0,
+                                    X0t, X0, Xft, Xf, backend=be, log=log)
+    return out, log
+
+
+def test_demo_guess_and_direct_solve_gpu_vs_oracle(backends):
+    gpu, cpu = backends
+    fx = S.demo_fixtures()
+    g_gpu = S.trajectory_stack_guess(fx[1], fx[3], backend=gpu)
+    g_cpu = S.trajectory_stack_guess(fx[1], fx[3], backend=cpu)
+    assert g_gpu[3] == g_cpu[3] == 0.274                                        # tau2 (find_tau)
+    assert np.abs(g_gpu[0] - g_cpu[0]).max() < 1e-10                            # ballistic arcs: segment end states
+    for ns in (6, 7):
+        (Xg, ug, *_r, dg), lg = _direct(gpu, fx, g_cpu, ns)
+        (Xc, uc, *_r, dc), lc = _direct(cpu, fx, g_cpu, ns)
+        assert len(lg) == len(lc) and lg[-1]["er"] < 1e-6                       # same SQP iteration count, converged (:491)
+        assert np.abs(Xg[:6] - Xc[:6]).max() < TOL_TRAJ and np.abs(ug - uc).max() < TOL_TRAJ
+        if ns == 7:
+            assert np.abs(Xg[6] / Xc[6] - 1.0).max() < TOL_MASS                 # mass history incl. final mass
+            assert abs(Xg[6, -1] / Xc[6, -1] - 1.0) < TOL_MASS
+
+
+def test_indirect_demo_gpu_vs_oracle(backends):
+    gpu, cpu = backends
+    fx = S.demo_fixtures()
+    guess = S.trajectory_stack_guess(fx[1], fx[3], backend=gpu)
+    (X_all, *_), _ = _direct(gpu, fx, guess, 6)
+    t_TU, s0, sf = guess[1], guess[4], guess[5]
+    rng = np.random.default_rng(42)
+    XC0 = np.vstack([X_all, 0.1 * rng.standard_normal((6, 30))])                # CRTBP_Multishoot_indirect_demo.jl:166-176
+    XC0[:6, 0] = s0[:6]; XC0[:6, -1] = sf[:6]
+    XC0[:, 1:-1] += 1e-10 * rng.standard_normal((12, 28))
+    res = {}
+    for name, be in (("gpu", gpu), ("cpu", cpu)):
+        XC = XC0.copy()
+        hist = []
+        XC, d, st = S.multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 10.0, False, True, 10, 2.0, 1.0, backend=be)
+        hist.append(st)
+        XC, d, st = S.multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 10.0, False, False, 50, 2.0, 1.0, backend=be)
+        hist.append(st); Xp2 = XC.copy()
+        XC, d, st = S.multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 0.05, False, False, 30, 1.0, 1.0, backend=be)
+        hist.append(st); Xp1 = XC.copy()
+        XC, d, st = S.reduceFuel_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 0.05, 1.0, 1e-2, backend=be)
+        hist.append(st)
+        res[name] = (hist, Xp2, Xp1, XC, np.abs(d).max())
+    assert res["gpu"][0] == res["cpu"][0] == [1, 0, 0, 0]
+    assert np.abs(res["gpu"][1] - res["cpu"][1]).max() < TOL_TRAJ               # p = 2 solution
+    assert np.abs(res["gpu"][2] - res["cpu"][2]).max() < TOL_TRAJ               # p = 1, rho = 1
+    assert np.abs(res["gpu"][3] - res["cpu"][3]).max() < TOL_TRAJ               # rho-continuation to 1e-2
+    assert res["gpu"][4] < 1e-10                                                # converged to the reference's threshold (:280)
+
+
+def test_line_search_batch_equals_sequential(backends):
+    """The 20 trial trajectories of lineSearch (:221-246) in one call give the same defects as 20 calls."""
+    gpu, _ = backends
+    c = __import__("lowthrustopt_b200.synthetic", fromlist=["x"]).continuation_batch(n_traj=20, n_seg_per_traj=29, ndim=12)
+    params = (MU, DU, TU, 0.05, 1e3, 1.0, 1.0, 1.0)
+    d_all = gpu.indirect_defect(c["XC_all"], c["t_TU"], params)
+    for j in (0, 7, 19):
+        dj = gpu.indirect_defect(c["XC_all"][j:j + 1], c["t_TU"][j:j + 1], params)
+        assert np.array_equal(dj[0], d_all[j])

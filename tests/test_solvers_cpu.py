@@ -1,0 +1,107 @@
+"""CPU: the host-side mirror of the reference's outer solvers (lowthrustopt_b200/solvers.py), driven through the
+ORACLE backend (tests/oracle_backend.py) because there is no GPU here.  Checks the host logic -- band assembly,
+QP / least-squares update, SOC, line search, end-state pinning -- against the behavioural anchors of
+SURVEY.md Appendix C (BASELINE configs 1-2, the two demo scripts)."""
+import numpy as np
+import pytest
+
+from lowthrustopt_b200 import capi, solvers as S
+from oracle_backend import OracleBackend
+
+MU, DU, TU = capi.MU, capi.DU, capi.TU
+
+
+@pytest.fixture(scope="module")
+def demo():
+    be = OracleBackend()
+    X0t, X0, Xft, Xf = S.demo_fixtures()
+    XC, t_TU, tau1, tau2, s0, sf = S.trajectory_stack_guess(X0, Xf, backend=be)
+    return dict(be=be, fx=(X0t, X0, Xft, Xf), XC=XC, t=t_TU, tau1=tau1, tau2=tau2, s0=s0, sf=sf)
+
+
+def test_trajectory_stack_guess(demo):
+    # CRTBP_Multishoot_direct_demo.jl:117-157; anchors SURVEY App. C
+    assert demo["XC"].shape == (12, 30) and abs(demo["tau2"] - 0.274) < 1e-12
+    d, _ = demo["be"].direct_defect(demo["XC"][:6].T[None], np.zeros((1, 30, 3)), demo["t"][None], 10, 2000.0, MU, DU, TU)
+    assert abs(np.abs(d).max() - 2.6265e-2) < 2e-6                            # initial max defect of the direct demo
+
+
+def run_direct(demo, be, nstate=6):
+    X0t, X0, Xft, Xf = demo["fx"]
+    X_all = demo["XC"][:6].copy()
+    if nstate == 7:
+        X_all = np.vstack([X_all, 1000.0 * np.ones((1, 30))])
+    log = []
+    out = S.multiShoot_CRTBP_direct(X_all, np.zeros((3, 30)), demo["tau1"], demo["tau2"], demo["t"], np.zeros(3), np.zeros(3), MU, DU, TU,
+                                    30, 10, 1e3, 2000.0, X0t, X0, Xft, Xf, False, False, 0.0, False, 100, backend=be, log=log)
+    return out, log
+
+
+def test_direct_demo_converges_like_the_anchors(demo):
+    out, log = run_direct(demo, demo["be"])
+    ers = [l["er"] for l in log]
+    assert len(ers) == 4 and ers[-1] < 1e-6                                   # multiShoot_CRTBP_direct.jl:491
+    for got, want in zip(ers, (2.67e-3, 1.40e-5, 1.71e-6, 2.65e-10)):
+        assert abs(got - want) / want < 0.01
+    assert abs(log[-1]["cost"] - 0.00521) < 1e-5
+    X_all, u_all = out[0], out[1]
+    assert abs(np.linalg.norm(u_all, axis=0).max() - 0.0526) < 1e-4
+    assert np.allclose(X_all[:, 0], demo["s0"][:6]) and np.allclose(X_all[:, -1], demo["sf"][:6])   # hard-fixed endpoints (:374-375)
+
+
+def test_direct_variational_jacobian_is_a_drop_in_for_the_reference_fd(demo):
+    """Same solver, Jacobian from the reference's own forward differences (pert 1e-8): same iteration history."""
+    _, log_var = run_direct(demo, demo["be"])
+    out_fd, log_fd = run_direct(demo, OracleBackend(jac="fd"))
+    assert len(log_fd) == len(log_var)
+    for a, b in zip(log_var[:3], log_fd[:3]):
+        assert abs(a["er"] - b["er"]) / a["er"] < 1e-3
+
+
+def test_direct_nstate7_mass_row(demo):
+    out, log = run_direct(demo, demo["be"], nstate=7)
+    assert log[-1]["er"] < 1e-6 and len(log) <= 6
+    m = out[0][6]
+    assert m[0] == 1000.0 and np.all(np.diff(m) < 0) and 995 < m[-1] < 1000
+
+
+def test_direct_flagEnd_is_refused(demo):
+    X0t, X0, Xft, Xf = demo["fx"]
+    with pytest.raises(NotImplementedError):
+        S.multiShoot_CRTBP_direct(demo["XC"][:6], np.zeros((3, 30)), 0.75, 0.274, demo["t"], np.zeros(3), np.zeros(3), MU, DU, TU, 30, 10,
+                                  1e3, 2000.0, X0t, X0, Xft, Xf, False, True, backend=demo["be"])
+
+
+def test_indirect_demo_sequence(demo):
+    be = demo["be"]
+    (X_all, *_), _ = run_direct(demo, be)
+    rng = np.random.default_rng(42)
+    XC = np.vstack([X_all, 0.1 * rng.standard_normal((6, 30))])                # CRTBP_Multishoot_indirect_demo.jl:166-176
+    XC[:6, 0] = demo["s0"][:6]; XC[:6, -1] = demo["sf"][:6]
+    XC[:, 1:-1] += 1e-10 * rng.standard_normal((12, 28))
+    log = []
+    XC, d, st = S.multiShoot_CRTBP_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 10.0, False, True, 10, 2.0, 1.0, backend=be, log=log)
+    assert st == 1 and abs(log[-1]["er"] - 1.14e-4) < 1e-6                     # adjoints-only stalls: states cannot move
+    log = []
+    XC, d, st = S.multiShoot_CRTBP_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 10.0, False, False, 50, 2.0, 1.0, backend=be, log=log)
+    assert st == 0 and len(log) == 1 and log[0]["er"] < 1e-10
+    peak = max(np.linalg.norm(S.controlLaw_cart(XC[9:12, i], 10.0, 2.0, 1.0, 1e3)) for i in range(30))
+    assert abs(peak - 0.0547) < 2e-4
+    log = []
+    XC, d, st = S.multiShoot_CRTBP_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 0.05, False, False, 30, 1.0, 1.0, backend=be, log=log)
+    assert st == 0 and len(log) == 4 and abs(log[0]["er"] - 6.93e-2) < 1e-4 and log[-1]["er"] < 1e-10
+    assert np.array_equal(XC[:6, 0], demo["s0"][:6]) and np.array_equal(XC[:6, -1], demo["sf"][:6])   # :324-325
+    # rho-continuation (HelperFunctions.jl:105-193), three halvings
+    clog = []
+    XC2, d2, st2 = S.reduceFuel_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 0.05, 1.0, 0.125, backend=be, log=clog)
+    assert st2 == 0 and [c["rho"] for c in clog] == [1.0, 0.5, 0.25, 0.125] and all(c["status"] == 0 for c in clog)
+
+
+def test_invalid_p_and_nan_status():
+    be = OracleBackend()
+    XC = np.zeros((12, 3)); XC[0] = 1.0; XC[9] = 0.1
+    with pytest.raises(ValueError, match="Invalid value of p"):
+        S.GpuBackend._ip(None, (MU, DU, TU, 1.0, 1e3, 1.0, 0.5, 1.0))
+    XC[:, 0] = np.nan
+    out, d, st = S.multiShoot_CRTBP_indirect(XC, np.array([0.0, 0.1, 0.2]), MU, DU, TU, 3, 1e3, 0.05, False, False, 3, 1.0, 1.0, backend=be)
+    assert st == 2                                                              # isnan(XC_all[1]) -> status_flag 2 (:339-341)
