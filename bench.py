@@ -33,7 +33,8 @@ FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 55000.0}
 # Algorithmic HBM bytes per unit
 BYTES_PER_SEG = {"direct7": 1360.0, "direct6": (2 * 6 + 6 + 2 + 6 + 1 + 6 * 18) * 8.0, 12: 1360.0, 14: 1808.0}
 
-WORKLOADS = ["direct7_fixed", "direct6_fixed", "direct7_adaptive", "indirect12", "indirect14"]
+WORKLOADS = ["direct7_fixed", "direct6_fixed", "direct7_adaptive", "indirect12", "indirect14", "indirect12_1m", "continuation"]
+SHARDED = ("indirect12_1m", "continuation")      # strong-scaling workloads: fixed total, sharded + all-gathered (lowthrustopt_b200/sharded.py)
 
 
 def parse():
@@ -48,6 +49,8 @@ def parse():
     ap.add_argument("--err-norm", default="joint", choices=["joint", "state"], help="indirect step-control norm: x+Phi (ForwardDiff semantics) or x only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
+    ap.add_argument("--chunks", type=int, default=4, help="all-gather / compute overlap chunks of the sharded paths")
     return ap.parse_args()
 
 
@@ -111,17 +114,22 @@ def cpu_reference_pass(workload, batch, n, nthreads):
     return time.perf_counter() - t
 
 
-def cpu_baseline(workload, batch, sample):
+def cpu_baseline(workload, batch, sample, seconds=12.0):
+    """The reference ALGORITHM on the host cores for about `seconds` of CPU work: repeated passes over the first
+    `sample` segments of the same batch."""
     from oracle import oracle as O
     O.build()
     nthreads = O.num_threads()
     n = min(sample, len(next(iter(batch.values()))))
     cpu_reference_pass(workload, batch, min(n, 256), nthreads)        # warm the thread pool
-    dt = cpu_reference_pass(workload, batch, n, nthreads)
-    return {"value": n / dt, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
-            "sample": "%d segments of the same batch, reference algorithm (%s) restated in C++ (oracle/), OpenMP over segments, %.1f s"
-                      % (n, "defectCalc + forward-FD jacobianCalc, pert 1e-8" if workload.startswith("direct") else
-                         "dual numbers through the adaptive RK8", dt)}
+    dt, passes = 0.0, 0
+    while dt < seconds and passes < 10000:
+        dt += cpu_reference_pass(workload, batch, n, nthreads); passes += 1
+    return {"value": n * passes / dt, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
+            "sample": "%d passes over the first %d segments of the same batch, reference algorithm (%s) restated in C++ (oracle/), "
+                      "OpenMP over segments on %d threads, %.1f s"
+                      % (passes, n, "defectCalc + forward-FD jacobianCalc, pert 1e-8" if workload.startswith("direct") else
+                         "dual numbers through the adaptive RK8", nthreads, dt)}
 
 
 def run_reference(args):
@@ -153,6 +161,15 @@ def run_reference(args):
 
 
 def workload_config(workload, n_seg, n_gpus):
+    if workload in SHARDED:
+        desc = {"indirect12_1m": "BASELINE configs[3]: 1,048,576 perturbed indirect-shooting guesses (12-dim reference RHS, adaptive RK8 1e-13, "
+                                 "12x12 STM) in TOTAL, sharded across the GPUs, defects + STM blocks all-gathered to every rank",
+                "continuation": "BASELINE configs[4]: 1,024 trajectories x 200 segments (L2_Anderson_2 ballistic stack, thrustLimit ladder 10 -> 0.05 N); "
+                                "one step = one Newton iteration of multiShoot_CRTBP_indirect = 1 STM pass + 22 defect-only passes (SOC + 20 line-search "
+                                "points + check), every pass all-gathered to the solver rank"}[workload]
+        return {"workload": workload, "description": desc, "segments_total": n_seg, "segments_per_gpu": n_seg // n_gpus,
+                "l2": "not flushed: each pass writes more output than the 126 MB L2 holds", "parallelism": "units interleaved across %d GPU(s) "
+                "in chunks; NCCL all-gather of each chunk overlapped with the next chunk's kernel" % n_gpus}
     desc = {
         "direct7_fixed": "BASELINE configs[2]: synthetic batch of 65,536 direct-method segments per GPU, nstate 7 + STM + control "
                          "sensitivities (7x20 Jacobian block), FIXED RKF7(8) grid nsteps=10 both legs (reference ode7_8 path)",
@@ -166,17 +183,214 @@ def workload_config(workload, n_seg, n_gpus):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    return world, rank, local
+
+
+def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl):
+    peak_burst, _ = h.fp64_peak_probe(2048)
+    peak_sust, ms_p = h.fp64_peak_probe(200000)
+    achieved = flops_unit * units_per_launch / (kernel_ms * 1e-3) / 1e12
+    hbm = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = json.load(f).get("hbm_gbs")
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(wl)
+    except Exception:
+        pass
+    gbs = bytes_unit * units_per_launch / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "fp64", "achieved": achieved, "peak": peak_sust / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak_sust / 1e12),
+            "traffic": traffic,
+            "peak_source": "DFMA issue-rate probe (lto_fp64_peak_probe) run on this GPU in this process: sustained %.2f TFLOP/s over %.0f ms, "
+                           "burst %.2f; MEASURED_PEAKS.json carries no FP64 figure; spec 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2"
+                           % (peak_sust / 1e12, ms_p, peak_burst / 1e12),
+            "flops_per_unit": flops_unit, "units_per_launch": units_per_launch, "kernel_ms": kernel_ms,
+            "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": (gbs / hbm) if hbm else None}}
+
+
+def run_sharded(args):
+    """Strong-scaling workloads through lowthrustopt_b200.sharded (units interleaved over the ranks, chunked all-gather)."""
+    import torch
+    import torch.distributed as dist
+    from lowthrustopt_b200 import capi, sharded, synthetic as S
+
+    world, rank, local = dist_setup()
+    dev = torch.device("cuda", local)
+    h = capi.Handle(local)
+    wl = args.workload
+    nd = 12
+    if wl == "indirect12_1m":
+        n_units = args.n_seg or (1 << 20); n_nodes = 2; passes_def = 0
+        b = S.indirect_batch(n_units, ndim=nd, seed=20180002) if rank == 0 else None
+        if rank == 0:
+            XC = np.zeros((n_units, 2, nd)); XC[:, 0] = b["x0"]
+            tt = np.stack([b["t0"], b["t1"]], axis=1)
+            tl = 0.05
+    else:
+        n_units = args.n_seg or 1024; n_nodes = 201; passes_def = 22
+        if rank == 0:
+            c = S.continuation_batch(n_traj=n_units, n_seg_per_traj=n_nodes - 1, ndim=nd)
+            XC, tt, tl = c["XC_all"], c["t_TU"], c["thrustLimit"]
+    spu = n_nodes - 1
+    n_seg = n_units * spu
+    sh = sharded.ShardedIndirect(h, n_units, n_nodes, nd, dev, n_chunks=args.chunks)
+    p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
+    pin_in = pin_out = None
+    if rank == 0:
+        pin_in = {"XC": capi.PinnedBuffer(XC.shape), "t": capi.PinnedBuffer(tt.shape)}
+        pin_in["XC"].array[...] = XC; pin_in["t"].array[...] = tt
+        pin_out = {"defect": torch.empty((n_units, spu, nd), dtype=torch.float64).pin_memory(),
+                   "phi": torch.empty((n_units, spu, nd, nd), dtype=torch.float64).pin_memory(),
+                   "status": torch.empty((n_units, spu), dtype=torch.int32).pin_memory()}
+        sh.load(pin_in["XC"].array, pin_in["t"].array, tl, 1.0)
+    else:
+        sh.load()
+
+    def step():
+        out, plan = sh.run(p, jac=True)
+        for _ in range(passes_def):
+            sh.run(p, jac=False)
+        return out
+
+    def step_e2e():
+        if rank == 0:
+            sh.load(pin_in["XC"].array, pin_in["t"].array, tl, 1.0)
+        else:
+            sh.load()
+        out = step()
+        if rank == 0:
+            for k in pin_out:
+                pin_out[k].copy_(out[k], non_blocking=True)
+            torch.cuda.synchronize()
+            return float(pin_out["defect"][0, 0, 0])
+        return 0.0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
+    l0 = h.launches
+    sh.run_jac.timing = []
+    stream = sh.stream
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = step()
+    e1.record(stream)
+    barrier()
+    launches = h.launches - l0
+    t_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_total.item()) / args.steps
+    kt = [(a.elapsed_time(b), cnt) for a, b, cnt in sh.run_jac.timing]
+    sh.run_jac.timing = None
+    kernel_ms = float(np.mean([x[0] for x in kt])); units_per_launch = int(np.mean([x[1] for x in kt])) * spu
+    nst = out["nsteps"].cpu().numpy().reshape(-1, 2)
+    attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
+    passes = 1 + passes_def
+    value = n_seg * passes / (ms_per_step * 1e-3)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, units_per_launch, kernel_ms, BYTES_PER_SEG[nd], "indirect12")
+    roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
+    roof["kernel"] = "k_indirect_cw (the STM pass); launches of %d segments" % units_per_launch
+    gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + passes_def * n_seg * (nd * 8 + 12)
+    line = {"metric": "segment-propagations/s (fp64 state+STM)", "value": value, "unit": "segment-propagations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world), "clocks": clocks,
+            "passes_per_step": {"stm": 1, "defect_only": passes_def},
+            "collective": {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor)", "chunks": args.chunks,
+                           "bytes_gathered_per_rank_per_step": int(gathered)},
+            "e2e": {"value": n_seg * passes * args.steps / float(t_e2e.item()), "unit": "segment-propagations/s",
+                    "h2d_bytes_per_step": int(n_units * n_nodes * (nd + 1) * 8), "d2h_bytes_per_step": int(n_seg * (nd * 8 + nd * nd * 8 + 4)),
+                    "timing": "host wall clock on the solver rank: pinned host inputs -> H2D -> broadcast -> sharded passes + all-gather -> "
+                              "D2H of defect/STM/status into pinned memory; max over ranks"},
+            "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def allgather_leg(args, h, dev, wl, n_seg, world, rank, batch, p):
+    """The same weak-scaling batch (n_seg segments per GPU) with every rank's defects + Jacobian/STM blocks all-gathered
+    so the solver rank holds the full set (north_star); chunked so the NCCL all-gather overlaps the next chunk's kernel."""
+    import torch
+    import torch.distributed as dist
+    from lowthrustopt_b200 import sharded
+    total = n_seg * world
+    if wl.startswith("direct"):
+        ns = 7 if wl.startswith("direct7") else 6
+        sh = sharded.ShardedDirect(h, total, ns, dev, n_chunks=args.chunks)
+        # every rank contributes its own batch: all-gather the inputs once (untimed set-up), globally ordered like the shard plan
+        for k, dst in sh.inp.items():
+            loc = torch.from_numpy(np.ascontiguousarray(batch[k])).to(dev)
+            dist.all_gather_into_tensor(dst, loc)
+        per_unit = ns * 8 + 8 + 4 + ns * 2 * (ns + 3) * 8
+    else:
+        nd = 12 if wl == "indirect12" else 14
+        sh = sharded.ShardedIndirect(h, total, 2, nd, dev, n_chunks=args.chunks)
+        XC = np.zeros((n_seg, 2, nd)); XC[:, 0] = batch["x0"]
+        dist.all_gather_into_tensor(sh.XC, torch.from_numpy(XC).to(dev))
+        dist.all_gather_into_tensor(sh.t, torch.from_numpy(np.stack([batch["t0"], batch["t1"]], axis=1)).to(dev))
+        sh.tl.fill_(0.05); sh.rho.fill_(1.0)
+        per_unit = nd * 8 + 12 + nd * nd * 8
+    for _ in range(3):
+        sh.run(p, jac=True)
+    torch.cuda.synchronize(); dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(sh.stream)
+    for _ in range(args.steps):
+        sh.run(p, jac=True)
+    e1.record(sh.stream)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.steps
+    return {"value": total / (ms * 1e-3), "unit": "segment-propagations/s", "ms_per_step": ms, "chunks": args.chunks,
+            "bytes_received_per_rank_per_step": int(per_unit * n_seg * (world - 1)),
+            "what": "same batch, outputs of all ranks all-gathered (NCCL over NVLink) into every rank's HBM, max over ranks"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from lowthrustopt_b200 import capi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+    if args.workload in SHARDED:
+        return run_sharded(args)
+
+    world, rank, local = dist_setup()
     dev = torch.device("cuda", local)
     h = capi.Handle(local)
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
@@ -235,9 +449,12 @@ def run_ours(args):
         for k, v in batch.items():
             pin_in[k].array[...] = v
         a_in = {k: b.array for k, b in pin_in.items()}
+        pin_out = {"defect": capi.PinnedBuffer((n_seg, nd)), "status": capi.PinnedBuffer((n_seg,), np.int32),
+                   "nsteps": capi.PinnedBuffer((n_seg, 2), np.int32), "phi": capi.PinnedBuffer((n_seg, nd, nd))}
+        out_arrays = {k: b.array for k, b in pin_out.items()}
 
         def step_e2e():
-            r = h.indirect(a_in["x0"], a_in["t0"], a_in["t1"], params=p, jac=True)
+            r = h.indirect(a_in["x0"], a_in["t0"], a_in["t1"], params=p, jac=True, out=out_arrays)
             return float(r["defect"][0, 0])
         h2d = sum(v.nbytes for v in batch.values())
         d2h = n_seg * (nd * 8 + 4 + 8 + nd * nd * 8)
@@ -295,30 +512,8 @@ def run_ours(args):
     e2e_value = n_seg * world * args.steps / float(t_e2e.item())
     clocks = sampler.stop()
     # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
-    peak_burst, _ = h.fp64_peak_probe(2048)
-    peak_sust, ms_p = h.fp64_peak_probe(200000)
-    per_gpu_ms = float(np.mean(times)) / 1.0
-    achieved = flops_unit * n_seg / (per_gpu_ms * 1e-3) / 1e12
-    hbm = None
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            hbm = json.load(f).get("hbm_gbs")
-    except Exception:
-        pass
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(wl)
-    except Exception:
-        pass
-    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_sust / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak_sust / 1e12),
-            "traffic": traffic,
-            "peak_source": "DFMA issue-rate probe (lto_fp64_peak_probe) run on this GPU in this process: sustained %.2f TFLOP/s over %.0f ms, "
-                           "burst %.2f; MEASURED_PEAKS.json carries no FP64 figure; spec 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2"
-                           % (peak_sust / 1e12, ms_p, peak_burst / 1e12),
-            "flops_per_unit": flops_unit, "units_per_launch": n_seg, "kernel_ms": per_gpu_ms,
-            "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": bytes_unit * n_seg / (per_gpu_ms * 1e-3) / 1e9,
-                    "peak_gbs": hbm, "frac": (bytes_unit * n_seg / (per_gpu_ms * 1e-3) / 1e9 / hbm) if hbm else None}}
+    per_gpu_ms = float(np.mean(times))
+    roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl)
     if attempted is not None:
         roof["attempted_steps_per_segment"] = attempted
         roof["accepted_steps_per_segment"] = accepted
@@ -329,9 +524,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "segment-propagations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "host wall clock around the blocking lto_*_defect_jac call, pinned host buffers, max over ranks"},
             "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
+    if world > 1:
+        line["allgather"] = allgather_leg(args, h, dev, wl, n_seg, world, rank, batch, p)
     if rank == 0 and not args.no_cpu_baseline:
         sample = args.cpu_sample or (8192 if direct else 2048)
-        line["cpu_baseline"] = cpu_baseline(wl, batch, sample)
+        line["cpu_baseline"] = cpu_baseline(wl, batch, sample, args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line), flush=True)
     h.close()

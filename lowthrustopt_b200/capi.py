@@ -241,8 +241,9 @@ class Handle:
         return dict(defect=defect, errors=errors, status=status)
 
     # ---- indirect -------------------------------------------------------
-    def indirect(self, x0, t0, t1, x_target=None, params=None, thrustLimit=None, rho=None, jac=True):
-        """pairs form.  x0: (n_seg, ndim).  Returns dict(defect, status, nsteps (n_seg,2), phi (n_seg, ndim, ndim) column-major)."""
+    def indirect(self, x0, t0, t1, x_target=None, params=None, thrustLimit=None, rho=None, jac=True, out=None):
+        """pairs form.  x0: (n_seg, ndim).  Returns dict(defect, status, nsteps (n_seg,2), phi (n_seg, ndim, ndim) column-major).
+        `out` may supply preallocated (e.g. pinned) arrays under the same keys."""
         p = params or indirect_params()
         x0, t0, t1 = map(_f64, (x0, t0, t1))
         if x0.ndim != 2:
@@ -251,9 +252,11 @@ class Handle:
         xt = None if x_target is None else _f64(x_target)
         tl = None if thrustLimit is None else _f64(thrustLimit)
         rh = None if rho is None else _f64(rho)
-        defect = np.empty((n_seg, nd)); status = np.empty(n_seg, dtype=np.int32); nst = np.empty((n_seg, 2), dtype=np.int32)
+        o = out or {}
+        defect = o.get("defect", np.empty((n_seg, nd))); status = o.get("status", np.empty(n_seg, dtype=np.int32))
+        nst = o.get("nsteps", np.empty((n_seg, 2), dtype=np.int32))
         if jac:
-            phi = np.empty((n_seg, nd, nd))
+            phi = o.get("phi", np.empty((n_seg, nd, nd)))
             self._ck(lib().lto_indirect_defect_jac(self._h, C.addressof(p), n_seg, nd, _ptr(x0), _ptr(t0), _ptr(t1), _ptr(xt),
                                                    _ptr(tl), _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst), _ptr(phi)))
             return dict(defect=defect, status=status, nsteps=nst, phi=phi)

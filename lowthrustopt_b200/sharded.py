@@ -1,0 +1,220 @@
+"""Multi-GPU form of the hot path: one process per GPU (torch.distributed), independent units
+(segments, or whole trajectories) sharded across the ranks, and ONE kind of collective --
+an all-gather of each rank's output slab (defects, Jacobian / STM blocks, status words) so that
+the rank running the host-side Newton step holds the full set (BASELINE.json north_star;
+SURVEY.md 8(e)).  There is no halo and no reduction: segment i depends only on its own node data
+(multiShoot_CRTBP_direct.jl:82-101, multiShoot_CRTBP_indirect.jl:75-82).
+
+Work assignment.  The unit range is cut into `n_chunks` chunks of world*cs units; inside chunk c
+rank r owns units [(c*world + r)*cs, (c*world + r + 1)*cs).  Consequences:
+  * the all-gather of chunk c lands directly in the final, globally ordered arrays
+    (no re-ordering pass, no second copy);
+  * chunk c's all-gather (NCCL stream) overlaps chunk c+1's propagation kernel (library stream);
+  * every rank takes an interleaved sample of the batch, which evens out the spread of adaptive
+    step counts along a trajectory (4..67 accepted steps per segment).
+The tail is padded up to a whole chunk; padded rows are never computed and are sliced off.
+
+torch is plumbing here (device buffers, streams, the process group); the propagation itself is
+liblto_b200's kernels enqueued through lto_*_dev.  On CPU (gloo) the same machinery runs with a
+caller-supplied `compute` -- that is how tests/ cover the N > 1 logic without GPUs.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import capi
+
+
+class ShardPlan:
+    def __init__(self, n_units, world, n_chunks=2):
+        if n_units < 0 or world < 1 or n_chunks < 1:
+            raise ValueError("bad shard plan")
+        self.n_units, self.world = int(n_units), int(world)
+        n_chunks = max(1, min(int(n_chunks), -(-self.n_units // self.world) or 1))
+        self.cs = max(1, -(-self.n_units // (self.world * n_chunks)))                   # units per rank per chunk
+        self.n_chunks = max(1, -(-self.n_units // (self.world * self.cs)))
+        self.padded = self.n_chunks * self.world * self.cs
+
+    def local(self, rank, c):
+        """(first unit, number of real units) of rank `rank` in chunk c."""
+        u0 = (c * self.world + rank) * self.cs
+        return u0, max(0, min(self.cs, self.n_units - u0))
+
+    def owner(self, unit):
+        c, rem = divmod(int(unit), self.world * self.cs)
+        return c, rem // self.cs
+
+
+class ShardedRunner:
+    """spec: name -> (per-unit shape tuple, torch dtype).  run() returns {name: tensor (n_units, *shape)} on every rank."""
+
+    def __init__(self, spec, device, group=None, n_chunks=2):
+        self.spec, self.device, self.group = dict(spec), torch.device(device), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_chunks = n_chunks
+        self.cuda = self.device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self._bufs = {}
+        self.timing = None          # set to a list to collect (start, end) CUDA event pairs around every compute call
+
+    def _buffers(self, plan):
+        key = (plan.padded, plan.cs)
+        if self._bufs.get("key") != key:
+            full = {k: torch.zeros((plan.padded,) + tuple(s), dtype=dt, device=self.device) for k, (s, dt) in self.spec.items()}
+            loc = {k: [torch.zeros((plan.cs,) + tuple(s), dtype=dt, device=self.device) for _ in range(plan.n_chunks)]
+                   for k, (s, dt) in self.spec.items()}
+            self._bufs = {"key": key, "full": full, "loc": loc}
+        return self._bufs["full"], self._bufs["loc"]
+
+    def run(self, n_units, compute, compute_stream=None):
+        """compute(unit0, count, outs) fills outs[name][:count] for units [unit0, unit0+count) -- on `compute_stream`
+        (a torch.cuda stream object wrapping the library's stream) when on CUDA, synchronously on CPU."""
+        plan = ShardPlan(n_units, self.world, self.n_chunks)
+        full, loc = self._buffers(plan)
+        works = []
+        for c in range(plan.n_chunks):
+            u0, cnt = plan.local(self.rank, c)
+            outs = {k: loc[k][c] for k in self.spec}
+            if cnt > 0:
+                if self.cuda and self.timing is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(compute_stream); compute(u0, cnt, outs); e1.record(compute_stream)
+                    self.timing.append((e0, e1, cnt))
+                else:
+                    compute(u0, cnt, outs)
+            if self.world == 1:
+                for k in self.spec:
+                    if self.cuda:
+                        with torch.cuda.stream(compute_stream):
+                            full[k][c * plan.cs:(c + 1) * plan.cs].copy_(outs[k], non_blocking=True)
+                    else:
+                        full[k][c * plan.cs:(c + 1) * plan.cs].copy_(outs[k])
+                continue
+            g0 = c * self.world * plan.cs
+            if self.cuda:
+                ev = torch.cuda.Event()
+                ev.record(compute_stream)
+                self.comm_stream.wait_event(ev)
+                with torch.cuda.stream(self.comm_stream):
+                    for k in self.spec:
+                        works.append(dist.all_gather_into_tensor(full[k][g0:g0 + self.world * plan.cs], outs[k], group=self.group, async_op=True))
+            else:
+                for k in self.spec:
+                    dist.all_gather_into_tensor(full[k][g0:g0 + self.world * plan.cs], outs[k], group=self.group)
+        if self.cuda:
+            with torch.cuda.stream(self.comm_stream):
+                for w in works:
+                    w.wait()
+            self.comm_stream.synchronize()
+            if compute_stream is not None:
+                compute_stream.synchronize()
+        return {k: v[:n_units] for k, v in full.items()}, plan
+
+
+def _bcast(t, src, group):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
+class ShardedIndirect:
+    """Indirect method, trajectory form, across the ranks of `group`: the multi-GPU counterpart of
+    lto_indirect_defect[_jac]_traj.  Unit = one trajectory (its n_nodes-1 segments), so each rank's slab is a
+    contiguous block of whole trajectories of the solver's arrays."""
+
+    def __init__(self, handle, n_traj, n_nodes, ndim, device, group=None, n_chunks=2, compute=None):
+        self.h, self.n_traj, self.n_nodes, self.nd = handle, int(n_traj), int(n_nodes), int(ndim)
+        self.device, self.group = torch.device(device), group
+        spu = n_nodes - 1
+        f64, i32 = torch.float64, torch.int32
+        self.spec_def = {"defect": ((spu, ndim), f64), "status": ((spu,), i32), "nsteps": ((spu, 2), i32)}
+        self.spec_jac = dict(self.spec_def, phi=((spu, ndim, ndim), f64))
+        self.run_def = ShardedRunner(self.spec_def, device, group, n_chunks)
+        self.run_jac = ShardedRunner(self.spec_jac, device, group, n_chunks)
+        self._compute = compute
+        self.XC = torch.empty((n_traj, n_nodes, ndim), dtype=f64, device=self.device)
+        self.t = torch.empty((n_traj, n_nodes), dtype=f64, device=self.device)
+        self.tl = torch.empty(n_traj, dtype=f64, device=self.device)
+        self.rho = torch.empty(n_traj, dtype=f64, device=self.device)
+        self.stream = None
+        if self.device.type == "cuda" and handle is not None:
+            self.stream = torch.cuda.ExternalStream(handle.stream, device=self.device)
+
+    def load(self, XC_all=None, t_TU=None, thrustLimit=None, rho=None, src=0):
+        """The solver rank (`src`) supplies host arrays; every rank ends up with the inputs on its device."""
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        for dst, a in ((self.XC, XC_all), (self.t, t_TU), (self.tl, thrustLimit), (self.rho, rho)):
+            if rank == src:
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), tuple(dst.shape)))   # scalars allowed for tl / rho
+                dst.copy_(torch.from_numpy(a), non_blocking=True)
+            _bcast(dst, src, self.group)
+
+    def _gpu_compute(self, params, jac):
+        h, nn, nd = self.h, self.n_nodes, self.nd
+
+        def compute(u0, cnt, outs):
+            h.indirect_dev(params, cnt * (nn - 1), nn, nd, self.XC[u0].data_ptr(), self.t[u0].data_ptr(), None, None,
+                           self.tl[u0:].data_ptr(), self.rho[u0:].data_ptr(), outs["defect"].data_ptr(), outs["status"].data_ptr(),
+                           outs["nsteps"].data_ptr(), outs["phi"].data_ptr() if jac else None)
+        return compute
+
+    def run(self, params, jac=True):
+        """One pass over all trajectories.  Returns {defect, status, nsteps[, phi]} as full, globally ordered tensors
+        (n_traj, n_nodes-1, ...) on every rank's device."""
+        runner = self.run_jac if jac else self.run_def
+        if self._compute is not None:
+            compute = lambda u0, cnt, outs: self._compute(self, params, jac, u0, cnt, outs)   # noqa: E731
+        else:
+            if self.h is None:
+                raise capi.LtoError("ShardedIndirect needs a liblto_b200 handle: there is no CPU propagation path")
+            compute = self._gpu_compute(params, jac)
+            if self.stream is not None:                       # inputs were produced on torch's current stream
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        out, plan = runner.run(self.n_traj, compute, self.stream)
+        return out, plan
+
+
+class ShardedDirect:
+    """Direct method, pairs form (BASELINE config 3 shape) across ranks: unit = one segment."""
+
+    def __init__(self, handle, n_seg, nstate, device, group=None, n_chunks=2, nsteps=10, compute=None):
+        self.h, self.n_seg, self.ns, self.nsteps = handle, int(n_seg), int(nstate), int(nsteps)
+        self.device, self.group = torch.device(device), group
+        f64, i32 = torch.float64, torch.int32
+        nv = 2 * (nstate + 3)
+        self.spec_def = {"defect": ((nstate,), f64), "errors": ((), f64), "status": ((), i32)}
+        self.spec_jac = dict(self.spec_def, jac=((nv, nstate), f64))
+        self.run_def = ShardedRunner(self.spec_def, device, group, n_chunks)
+        self.run_jac = ShardedRunner(self.spec_jac, device, group, n_chunks)
+        self._compute = compute
+        self.inp = {k: torch.empty((n_seg,) + s, dtype=f64, device=self.device)
+                    for k, s in (("Xa", (nstate,)), ("Xb", (nstate,)), ("ua", (3,)), ("ub", (3,)), ("ta", ()), ("tb", ()))}
+        self.stream = None
+        if self.device.type == "cuda" and handle is not None:
+            self.stream = torch.cuda.ExternalStream(handle.stream, device=self.device)
+
+    def load(self, batch=None, src=0):
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        for k, dst in self.inp.items():
+            if rank == src:
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(batch[k], dtype=np.float64)).reshape(dst.shape), non_blocking=True)
+            _bcast(dst, src, self.group)
+
+    def run(self, params, jac=True):
+        runner = self.run_jac if jac else self.run_def
+        if self._compute is not None:
+            compute = lambda u0, cnt, outs: self._compute(self, params, jac, u0, cnt, outs)   # noqa: E731
+        else:
+            if self.h is None:
+                raise capi.LtoError("ShardedDirect needs a liblto_b200 handle: there is no CPU propagation path")
+            h, ns, i = self.h, self.ns, self.inp
+
+            def compute(u0, cnt, outs):
+                h.direct_dev(params, cnt, 0, ns, self.nsteps, i["Xa"][u0:].data_ptr(), i["Xb"][u0:].data_ptr(), i["ua"][u0:].data_ptr(),
+                             i["ub"][u0:].data_ptr(), i["ta"][u0:].data_ptr(), i["tb"][u0:].data_ptr(), outs["defect"].data_ptr(),
+                             outs["errors"].data_ptr(), outs["status"].data_ptr(), outs["jac"].data_ptr() if jac else None)
+            if self.stream is not None:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        out, plan = runner.run(self.n_seg, compute, self.stream)
+        return out, plan
