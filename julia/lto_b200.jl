@@ -1,0 +1,83 @@
+# UNEXECUTED in this repository's environment (no Julia in the image); kept in sync with INTEGRATION.md section 2.
+using LinearAlgebra
+# lto_b200.jl -- ccall binding of liblto_b200.so (include/lto_b200.h)
+module LtoB200
+const lib = get(ENV, "LTO_B200_LIB", "liblto_b200.so")
+
+mutable struct DirectParams            # == lto_direct_params (7 doubles, 4 int32)
+    MU::Cdouble; DU::Cdouble; TU::Cdouble; Isp::Cdouble; g0::Cdouble; default_mass::Cdouble; tol::Cdouble
+    mode::Int32; err_norm::Int32; max_attempts::Int32; kernel::Int32
+    DirectParams() = (p = new(); ccall((:lto_direct_params_default, lib), Cvoid, (Ref{DirectParams},), p); p)
+end
+mutable struct IndirectParams          # == lto_indirect_params (12 doubles, 4 int32)
+    MU::Cdouble; DU::Cdouble; TU::Cdouble; thrustLimit::Cdouble; mass::Cdouble; time_direction::Cdouble
+    p::Cdouble; rho::Cdouble; Isp::Cdouble; g0::Cdouble; reltol::Cdouble; abstol::Cdouble
+    controller::Int32; err_norm::Int32; max_attempts::Int32; kernel::Int32
+    IndirectParams() = (p = new(); ccall((:lto_indirect_params_default, lib), Cvoid, (Ref{IndirectParams},), p); p)
+end
+
+const handle = Ref{Ptr{Cvoid}}(C_NULL)
+function init(devices::Vector{Int32} = Int32[0])
+    rc = ccall((:lto_init_devices, lib), Cint, (Cint, Ptr{Int32}, Ref{Ptr{Cvoid}}), length(devices), devices, handle)
+    rc == 0 || error("lto_init_devices: ", unsafe_string(ccall((:lto_last_error, lib), Cstring, (Ptr{Cvoid},), C_NULL)))
+end
+check(rc) = rc == 0 || error("liblto_b200: ", unsafe_string(ccall((:lto_last_error, lib), Cstring, (Ptr{Cvoid},), handle[])))
+
+# ---- direct: replaces defectCalc (multiShoot_CRTBP_direct.jl:66-109)
+function defectCalc(X_all::Matrix{Float64}, u_all::Matrix{Float64}, t_TU::Vector{Float64}, nstate, n_nodes, nsteps, Isp, MU, DU, TU)
+    p = DirectParams(); p.MU, p.DU, p.TU, p.Isp = MU, DU, TU, Isp
+    defect = zeros(nstate, n_nodes - 1); errors = zeros(n_nodes - 1); status = zeros(Int32, n_nodes - 1)
+    GC.@preserve X_all u_all t_TU defect errors status check(ccall((:lto_direct_defect_traj, lib), Cint,
+        (Ptr{Cvoid}, Ref{DirectParams}, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        handle[], p, 1, n_nodes, nstate, nsteps, X_all, u_all, t_TU, defect, errors, status))
+    (defect, errors)
+end
+
+# ---- direct: replaces jacobianCalc (:111-166); `defect`, `pert` become unused (variational equations)
+function jacobianCalc(X_all, u_all, t_TU, nstate, n_nodes, nsteps, Isp, MU, DU, TU)
+    p = DirectParams(); p.MU, p.DU, p.TU, p.Isp = MU, DU, TU, Isp
+    nvar = 2 * (nstate + 3)
+    defect = zeros(nstate, n_nodes - 1); errors = zeros(n_nodes - 1); status = zeros(Int32, n_nodes - 1)
+    blocks = zeros(nstate, nvar, n_nodes - 1)              # block i == Jac_temp[(i-1)n+1 : i n, :]  (:139-140)
+    GC.@preserve X_all u_all t_TU defect errors status blocks check(ccall((:lto_direct_defect_jac_traj, lib), Cint,
+        (Ptr{Cvoid}, Ref{DirectParams}, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+        handle[], p, 1, n_nodes, nstate, nsteps, X_all, u_all, t_TU, defect, errors, status, blocks))
+    Jac_full = zeros(nstate * (n_nodes - 1), n_nodes * (nstate + 3))                      # :146
+    for i = 1:(n_nodes - 1)                                                               # :147-162, unchanged
+        rows = ((i - 1) * nstate + 1):(i * nstate)
+        Jac_full[rows, ((i - 1) * nstate + 1):((i + 1) * nstate)] = blocks[:, 1:(2 * nstate), i]
+        c0 = nstate * n_nodes + 3 * (i - 1)
+        Jac_full[rows, (c0 + 1):(c0 + 6)] = blocks[:, (2 * nstate + 1):end, i]
+    end
+    Jac_full
+end
+
+# ---- indirect: replaces defectCalc (multiShoot_CRTBP_indirect.jl:63-90) and jacobianCalc (:93-146)
+function iparams(params)
+    (MU, DU, TU, thrustLimit, mass, td, pp, rho) = params                                 # :260
+    p = IndirectParams(); p.MU, p.DU, p.TU = MU, DU, TU
+    p.thrustLimit, p.mass, p.time_direction, p.p, p.rho = thrustLimit, mass, td, pp, rho
+    p
+end
+function defectCalc_indirect(XC_all::Matrix{Float64}, t_TU::Vector{Float64}, nstate, n_nodes, params)
+    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1)
+    GC.@preserve XC_all t_TU defect status check(ccall((:lto_indirect_defect_traj, lib), Cint,
+        (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL))
+    (defect, zeros(n_nodes - 1))                                                          # errors == 0 (:85)
+end
+function jacobianCalc_indirect(XC_all, t_TU, nstate, n_nodes, params)
+    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1); phi = zeros(m, m, n_nodes - 1)
+    GC.@preserve XC_all t_TU defect status phi check(ccall((:lto_indirect_defect_jac_traj, lib), Cint,
+        (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL, phi))
+    Jac_full = zeros(m * (n_nodes - 1), n_nodes * m)                                      # :127
+    for i = 1:(n_nodes - 1)                                                               # :128-138
+        r = ((i - 1) * m + 1):(i * m)
+        Jac_full[r, ((i - 1) * m + 1):(i * m)] = phi[:, :, i]
+        Jac_full[r, (i * m + 1):((i + 1) * m)] = -Matrix(1.0I, m, m)
+    end
+    Jac_full[:, 1:nstate] .= 0.0; Jac_full[:, (end - 2 * nstate + 1):(end - nstate)] .= 0.0   # :141-142
+    Jac_full
+end
+end # module
