@@ -26,7 +26,7 @@
  *    ordinary (pageable) memory or memory from lto_host_alloc (pinned: faster copies).
  *  - Return value: 0 ok, negative = library failure (see lto_last_error).  Numerical
  *    trouble is per segment in status[] (LTO_ST_*), never a failure.
- *  - A handle is bound to one CUDA device and is not re-entrant.
+ *  - A handle is bound to one CUDA device (lto_init) or a fixed set (lto_init_devices) and is not re-entrant.
  *  - There is no CPU fallback: without a usable sm_100 device lto_init fails.
  */
 #ifndef LTO_B200_H
@@ -91,6 +91,13 @@ void lto_indirect_params_default(lto_indirect_params* p);  /* Earth-Moon constan
 int lto_version(void);
 int lto_device_count(void);
 int lto_init(int device, lto_handle** h);      /* LTO_ERR_NODEVICE when no sm_100 GPU */
+/* One handle over several GPUs of the box, for a single host process (the Julia drop-in): every
+ * host-buffer entry point splits its segments (trajectory forms: whole trajectories) into equal
+ * contiguous ranges, one per device, runs them concurrently (one worker thread per device) and
+ * each device copies its slab of the outputs into the caller's arrays.  The device-pointer entry
+ * points (lto_*_dev, lto_stream) need a single-device handle. */
+int lto_init_devices(int n_devices, const int* devices, lto_handle** h);
+int lto_n_devices(const lto_handle* h);
 void lto_destroy(lto_handle* h);
 const char* lto_last_error(const lto_handle* h);
 void* lto_host_alloc(size_t bytes);            /* pinned host memory (NULL on failure) */

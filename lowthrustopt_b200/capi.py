@@ -23,7 +23,7 @@ LTO_NORM_STATE, LTO_NORM_STATE_SENS = 0, 1
 LTO_KERNEL_AUTO, LTO_KERNEL_GENERIC, LTO_KERNEL_FAST = 0, 1, 2
 
 EXPORTS = [
-    "lto_version", "lto_device_count", "lto_init", "lto_destroy", "lto_last_error", "lto_host_alloc", "lto_host_free",
+    "lto_version", "lto_device_count", "lto_init", "lto_init_devices", "lto_n_devices", "lto_destroy", "lto_last_error", "lto_host_alloc", "lto_host_free",
     "lto_kernel_launches", "lto_last_kernel_ms", "lto_stream", "lto_sync",
     "lto_direct_params_default", "lto_indirect_params_default",
     "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
@@ -72,6 +72,8 @@ def lib():
         L.lto_stream.restype = C.c_void_p
         L.lto_stream.argtypes = [C.c_void_p]
         L.lto_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.lto_init_devices.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        L.lto_n_devices.argtypes = [C.c_void_p]
         L.lto_destroy.argtypes = [C.c_void_p]
         L.lto_sync.argtypes = [C.c_void_p]
         vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
@@ -154,10 +156,16 @@ class Handle:
     (identical memory)."""
 
     def __init__(self, device=0):
+        """device: an int (lto_init) or a sequence of ints (lto_init_devices: one handle over several GPUs,
+        host-buffer entry points only)."""
         self._h = C.c_void_p()
-        rc = lib().lto_init(int(device), C.byref(self._h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = lib().lto_init_devices(len(device), ids, C.byref(self._h))
+        else:
+            rc = lib().lto_init(int(device), C.byref(self._h))
         if rc != 0:
-            raise LtoError("lto_init(%d) failed (%d): %s" % (device, rc, lib().lto_last_error(None).decode()))
+            raise LtoError("lto_init(%s) failed (%d): %s" % (device, rc, lib().lto_last_error(None).decode()))
         self.device = device
 
     def close(self):
@@ -174,6 +182,10 @@ class Handle:
     def _ck(self, rc):
         if rc != 0:
             raise LtoError("liblto_b200 error %d: %s" % (rc, lib().lto_last_error(self._h).decode()))
+
+    @property
+    def n_devices(self):
+        return int(lib().lto_n_devices(self._h))
 
     @property
     def launches(self):

@@ -8,11 +8,14 @@
 #include <cstdarg>
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
+#include <vector>
 
 using namespace lto;
 
 static char g_err[512] = "";
 static const size_t LTO_PROF_WORDS = 8192;
+#define LTO_MAX_DEVICES 16
 
 struct lto_handle {
     int device;
@@ -28,6 +31,8 @@ struct lto_handle {
     int64_t launches;
     double last_ms;
     char err[512];
+    int n_child;                                // > 0: a multi-device handle (lto_init_devices); the work is done by the children
+    lto_handle* child[LTO_MAX_DEVICES];
 };
 
 static int fail(lto_handle* h, int code, const char* fmt, ...) {
@@ -112,8 +117,31 @@ int lto_init(int device, lto_handle** out) {
     return LTO_SUCCESS;
 }
 
+int lto_init_devices(int n_devices, const int* devices, lto_handle** out) {
+    if (!out) return fail(nullptr, LTO_ERR_ARG, "lto_init_devices: null handle pointer");
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > LTO_MAX_DEVICES || !devices)
+        return fail(nullptr, LTO_ERR_ARG, "lto_init_devices: n_devices must be 1..%d", LTO_MAX_DEVICES);
+    if (n_devices == 1) return lto_init(devices[0], out);
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, LTO_ERR_ARG, "lto_init_devices: device %d listed twice", devices[i]);
+    lto_handle* h = (lto_handle*)calloc(1, sizeof(lto_handle));
+    if (!h) return fail(nullptr, LTO_ERR_NOMEM, "lto_init_devices: out of host memory");
+    h->device = -1;
+    for (int i = 0; i < n_devices; ++i) {
+        int rc = lto_init(devices[i], &h->child[i]);
+        if (rc) { for (int j = 0; j < i; ++j) lto_destroy(h->child[j]); free(h); return rc; }
+        h->n_child = i + 1;
+    }
+    h->n_sm = h->child[0]->n_sm;
+    *out = h;
+    return LTO_SUCCESS;
+}
+
 void lto_destroy(lto_handle* h) {
     if (!h) return;
+    if (h->n_child > 0) { for (int i = 0; i < h->n_child; ++i) lto_destroy(h->child[i]); free(h); return; }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
     if (h->d_in) cudaFree(h->d_in);
@@ -135,11 +163,25 @@ void* lto_host_alloc(size_t bytes) {
     return p;
 }
 void lto_host_free(void* p) { if (p) cudaFreeHost(p); }
-int64_t lto_kernel_launches(const lto_handle* h) { return h ? h->launches : 0; }
-double lto_last_kernel_ms(const lto_handle* h) { return h ? h->last_ms : 0.0; }
-void* lto_stream(lto_handle* h) { return h ? (void*)h->s_compute : nullptr; }
+int64_t lto_kernel_launches(const lto_handle* h) {
+    if (!h) return 0;
+    int64_t n = h->launches;
+    for (int i = 0; i < h->n_child; ++i) n += h->child[i]->launches;
+    return n;
+}
+double lto_last_kernel_ms(const lto_handle* h) {
+    if (!h) return 0.0;
+    double ms = h->last_ms;
+    for (int i = 0; i < h->n_child; ++i) ms = std::max(ms, h->child[i]->last_ms);
+    return ms;
+}
+int lto_n_devices(const lto_handle* h) { return h ? (h->n_child > 0 ? h->n_child : 1) : 0; }
+void* lto_stream(lto_handle* h) { return (h && h->n_child == 0) ? (void*)h->s_compute : nullptr; }
 int lto_sync(lto_handle* h) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    for (int i = 0; i < h->n_child; ++i) { int rc = lto_sync(h->child[i]); if (rc) return fail(h, rc, "%s", h->child[i]->err); }
+    if (h->n_child > 0) return LTO_SUCCESS;
+    CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->s_compute));
     return LTO_SUCCESS;
 }
@@ -214,6 +256,45 @@ static long long pick_chunk(long long n_seg, size_t out_bytes_per_seg) {
 }
 
 // ---------------------------------------------------------------------------
+// multi-device handles: contiguous, equal unit ranges (segments, or whole trajectories in the
+// trajectory forms) per device, one host worker thread per device; every device copies its
+// slab of the outputs straight into the caller's arrays, so no collective is needed.
+// ---------------------------------------------------------------------------
+template <class F>
+static int run_children(lto_handle* h, long long n_units, F&& call) {
+    const int nc = h->n_child;
+    std::vector<int> rcs(nc, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < nc; ++i) {
+        const long long u0 = n_units * i / nc, u1 = n_units * (i + 1) / nc;
+        if (u1 <= u0) continue;
+        th.emplace_back([&, i, u0, u1] { rcs[i] = call(h->child[i], u0, u1 - u0); });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < nc; ++i)
+        if (rcs[i]) return fail(h, rcs[i], "device %d: %s", h->child[i]->device, h->child[i]->err);
+    return LTO_SUCCESS;
+}
+
+static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_seg, int npt, long long n_nodes_total,
+                       int nstate, int nsteps, const double* Xa, const double* Xb, const double* ua, const double* ub,
+                       const double* ta, const double* tb, double* defect, double* errors, int32_t* status, double* jac,
+                       bool want_jac);
+static int direct_host_multi(lto_handle* h, const lto_direct_params* p, long long n_seg, int npt, int nstate, int nsteps,
+                             const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta,
+                             const double* tb, double* defect, double* errors, int32_t* status, double* jac, bool want_jac) {
+    if (nstate != 6 && nstate != 7) return fail(h, LTO_ERR_ARG, "nstate must be 6 or 7 (got %d)", nstate);
+    const long long spu = npt > 0 ? npt - 1 : 1, rpu = npt > 0 ? npt : 1;      // segments / input rows per unit
+    const long long NS = nstate, NV = 2 * (NS + 3);
+    return run_children(h, n_seg / spu, [&](lto_handle* c, long long u0, long long nu) {
+        const long long r0 = u0 * rpu, s0 = u0 * spu;
+        return direct_host(c, p, nu * spu, npt, nu * rpu, nstate, nsteps, Xa + r0 * NS, Xb ? Xb + r0 * NS : nullptr, ua + r0 * 3,
+                           ub ? ub + r0 * 3 : nullptr, ta + r0, tb ? tb + r0 : nullptr, defect + s0 * NS, errors ? errors + s0 : nullptr,
+                           status ? status + s0 : nullptr, jac ? jac + s0 * NS * NV : nullptr, want_jac);
+    });
+}
+
+// ---------------------------------------------------------------------------
 // host-buffer direct call
 // ---------------------------------------------------------------------------
 static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_seg, int npt, long long n_nodes_total,
@@ -222,6 +303,11 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
                        bool want_jac) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (n_seg < 0) return fail(h, LTO_ERR_ARG, "negative segment count");
+    if (h->n_child > 0) {
+        if (n_seg > 0 && (!Xa || !ua || !ta || !defect || (npt == 0 && (!Xb || !ub || !tb)) || (want_jac && !jac)))
+            return fail(h, LTO_ERR_ARG, "null array argument");
+        return direct_host_multi(h, p, n_seg, npt, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, jac, want_jac);
+    }
     DirectArgs a; memset(&a, 0, sizeof a);
     int rc = make_direct(h, p, nstate, nsteps, &a);
     if (rc) return rc;
@@ -291,6 +377,18 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
                          int32_t* status, int32_t* nsteps_out, double* phi, bool want_jac) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (n_seg < 0) return fail(h, LTO_ERR_ARG, "negative segment count");
+    if (h->n_child > 0) {
+        if (ndim != 12 && ndim != 14) return fail(h, LTO_ERR_ARG, "ndim must be 12 or 14 (got %d)", ndim);
+        if (n_seg > 0 && (!x0 || !t0 || !defect || (npt == 0 && !t1) || (want_jac && !phi))) return fail(h, LTO_ERR_ARG, "null array argument");
+        const long long spu = npt > 0 ? npt - 1 : 1, rpu = npt > 0 ? npt : 1, ND = ndim;
+        return run_children(h, n_seg / spu, [&](lto_handle* c, long long u0, long long nu) {
+            const long long r0 = u0 * rpu, s0 = u0 * spu;
+            return indirect_host(c, p, nu * spu, npt, nu * rpu, nu, ndim, x0 + r0 * ND, t0 + r0, t1 ? t1 + r0 : nullptr,
+                                 x_target ? x_target + r0 * ND : nullptr, tl_arr ? tl_arr + u0 : nullptr, rho_arr ? rho_arr + u0 : nullptr,
+                                 defect + s0 * ND, status ? status + s0 : nullptr, nsteps_out ? nsteps_out + 2 * s0 : nullptr,
+                                 phi ? phi + s0 * ND * ND : nullptr, want_jac);
+        });
+    }
     IndirectArgs a; memset(&a, 0, sizeof a);
     int rc = make_indirect(h, p, ndim, want_jac, &a);
     if (rc) return rc;
@@ -411,6 +509,7 @@ int lto_direct_dev(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int
                    const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,
                    double* defect, double* errors, int32_t* status, double* jac) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     DirectArgs a; memset(&a, 0, sizeof a);
     int rc = make_direct(h, p, nstate, nsteps, &a); if (rc) return rc;
     if (n_seg <= 0) return n_seg == 0 ? LTO_SUCCESS : fail(h, LTO_ERR_ARG, "negative segment count");
@@ -426,6 +525,7 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
                      const double* t0, const double* t1, const double* x_target, const double* thrustLimit_arr,
                      const double* rho_arr, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     IndirectArgs a; memset(&a, 0, sizeof a);
     int rc = make_indirect(h, p, ndim, phi != nullptr, &a); if (rc) return rc;
     if (n_seg <= 0) return n_seg == 0 ? LTO_SUCCESS : fail(h, LTO_ERR_ARG, "negative segment count");
@@ -443,6 +543,7 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
 
 int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) h = h->child[0];
     if (!h->d_prof) return fail(h, LTO_ERR_ARG, "profiling counters are off (set LTO_ICW_PROF=1 before lto_init)");
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->s_compute));
@@ -452,6 +553,7 @@ int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words) {
 
 int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms_out) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) h = h->child[0];
     CK(h, cudaSetDevice(h->device));
     int rc = ensure(h, &h->d_out, &h->d_out_cap, 4096); if (rc) return rc;
     long long nthreads = 0; int fmas = 0;

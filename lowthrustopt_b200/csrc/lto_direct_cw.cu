@@ -356,16 +356,19 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a
 template <int NS>
 static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
     typedef cw::Cfg<NS> C;
-    static int n_sm = 0;
-    static bool attr = false;
-    if (!attr) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    // per device: a single process may drive several GPUs (lto_init_devices)
+    static int n_sm_dev[64] = {0};
+    static bool attr_dev[64] = {false};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_dev[dev]) {
+        cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(cw::k_direct_cw<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr_dev[dev] = true;
     }
+    const int n_sm = n_sm_dev[dev];
     const long long n_tiles = (a.n_seg + 15) / 16;
     const long long n_pairs = (n_tiles + cw::NTILE - 1) / cw::NTILE;
     const int grid = (int)std::min<long long>(n_pairs, (long long)n_sm);

@@ -585,16 +585,19 @@ size_t indirect_cw_scratch_bytes(int n_sm) { return (size_t)n_sm * icw::SCRATCH_
 
 template <bool JOINT>
 static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
-    static int n_sm = 0;
-    static bool attr = false;
-    if (!attr) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    // per device: a single process may drive several GPUs (lto_init_devices)
+    static int n_sm_dev[64] = {0};
+    static bool attr_dev[64] = {false};
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e; }
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_dev[dev]) {
+        cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(icw::k_indirect_cw<JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw::SMEM);
         if (e != cudaSuccess) return e;
-        attr = true;
+        attr_dev[dev] = true;
     }
+    const int n_sm = n_sm_dev[dev];
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
     const long long per_cta = (long long)icw::NTILE * icw::TS;

@@ -223,3 +223,34 @@ def test_reference_closures_mirror(lto, oracle):
     J2 = indirect.jacobianCalc(XC, t, 6, n_nodes, None, params)
     assert d2.shape == (12, 29) and np.all(e2 == 0) and J2.shape == (12 * 29, 12 * 30)
     assert np.all(J2[:, :6] == 0) and np.array_equal(J2[12:24, 24:36], -np.eye(12))
+
+
+# ------------------------------------------------------------------ one handle over several GPUs (the Julia drop-in's multi-GPU form)
+def test_multi_device_handle_equals_single_device(lto):
+    ndev = capi.lib().lto_device_count()
+    with pytest.raises(capi.LtoError):
+        capi.Handle([0, 0])                                 # a device may be listed once
+    one = capi.Handle([0])
+    assert one.n_devices == 1
+    one.close()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    hm = capi.Handle(list(range(min(ndev, 4))))
+    assert hm.n_devices == min(ndev, 4)
+    b = S.direct_batch(1000 + 37, nstate=7, seed=11)
+    r1 = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"])
+    rm = hm.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"])
+    assert np.array_equal(r1["defect"], rm["defect"]) and np.array_equal(r1["jac"], rm["jac"]) and np.array_equal(r1["errors"], rm["errors"])
+    c = S.continuation_batch(n_traj=9, n_seg_per_traj=12, ndim=12)
+    p = capi.indirect_params(p=1.0, rho=1.0)
+    t1 = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"])
+    tm = hm.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"])
+    assert np.array_equal(t1["defect"], tm["defect"]) and np.array_equal(t1["nsteps"], tm["nsteps"])
+    assert np.abs(t1["phi"] - tm["phi"]).max() < 1e-12      # step control is slot-order independent; allow rounding-level differences only
+    d1 = lto.direct_traj(np.zeros((3, 5, 6)) + 1.0, np.zeros((3, 5, 3)), np.tile(np.linspace(0, 0.4, 5), (3, 1)), jac=False)
+    dm = hm.direct_traj(np.zeros((3, 5, 6)) + 1.0, np.zeros((3, 5, 3)), np.tile(np.linspace(0, 0.4, 5), (3, 1)), jac=False)
+    assert np.array_equal(d1["defect"], dm["defect"])
+    with pytest.raises(capi.LtoError):
+        hm.direct_dev(capi.direct_params(), 1, 0, 7, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)   # device-pointer calls need a single-device handle
+    assert hm.launches > 0
+    hm.close()
