@@ -54,7 +54,7 @@ using namespace cwc;
 // State warp: one RK step of x = [r v (m)] in Nystrom form; publishes the stage
 // linearisations of this step into `rec` (lane-strided) and accumulates maxErr.
 // ---------------------------------------------------------------------------
-template <int NS>
+template <int NS, bool PUB = true>
 __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m, const double (&u)[3], double omega,
                                        double mdot, double h, const EPConst& c, double* __restrict__ rec, double& maxErr) {
     constexpr int SVAL = Cfg<NS>::SVAL;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
     const double kom6 = c.kthr / c.default_mass;
     double a[13][3];
     double ev[3] = {0.0, 0.0, 0.0}, ea[3] = {0.0, 0.0, 0.0};
-    rec[Cfg<NS>::OFF_H * 32] = h;
+    if (PUB) rec[Cfg<NS>::OFF_H * 32] = h;
 #pragma unroll
     for (int j = 0; j < 13; ++j) {
         double R[3], V[3];
@@ -92,7 +92,7 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
         a[j][0] = fma(u[0], kom, fma(-a31, dx1, fma(-a32, dx2, fma(w2, V[1], R[0]))));
         a[j][1] = fma(u[1], kom, fma(gg1, R[1], -w2 * V[0]));
         a[j][2] = fma(u[2], kom, (gg1 - 1.0) * R[2]);
-        if (j != 10) {
+        if (PUB && j != 10) {
             const double a51 = 3.0 * i1s * a31, a52 = 3.0 * i2s * a32;
             const double s5 = a51 + a52;
             const double p1 = a51 * dx1, p2 = a52 * dx2;
@@ -351,7 +351,69 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a
     }
 }
 
+// ---------------------------------------------------------------------------
+// K4 (direct): defect-only -- the line searches (:415-425), the t_f partials (:511-512) and the
+// per-iteration check (:585) of multiShoot_CRTBP_direct.jl.  One thread per leg, the same x_step as the
+// state warps above without publishing anything: 39 stage doubles in registers, no shared memory.
+// ---------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(128) k_direct_state(DirectArgs a) {
+    const int nsteps = a.cfg.nsteps, nstep = nsteps - 1;
+    const int lane = threadIdx.x & 31, back = lane & 1;
+    const double omega = back ? -1.0 : 1.0;
+    const long long n_pairs32 = (a.n_seg + 15) / 16;                       // warps' worth of legs
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp0; w < n_pairs32; w += nwarp) {
+        const long long seg = w * 16 + (lane >> 1);
+        const long long sc = seg < a.n_seg ? seg : a.n_seg - 1;
+        const long long ia = lto_node_a(sc, a.npt);
+        const double* X = (back ? a.Xb : a.Xa) + ia * NS;
+        const double* U = (back ? a.ub : a.ua) + ia * 3;
+        double r[3] = {X[0], X[1], X[2]}, v[3] = {X[3], X[4], X[5]}, m = a.c.default_mass, u[3] = {U[0], U[1], U[2]}, maxErr = 0.0;
+        if (back) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }           // :92
+        if (NS == 7) m = X[6];
+        const double ta = a.ta[ia], tb = a.tb[ia];
+        const double t0 = ta, t1 = ta + (tb - ta) / 2.0;                   // :70
+        const double un = sqrt(fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2])));
+        const double mdot = -omega * un * a.c.cmdot;                       // CRTBP_prop_EP_deriv.jl:42
+        for (int k = 0; k < nstep; ++k) {
+            const double h = linrange_at(t0, t1, nsteps, k + 1) - linrange_at(t0, t1, nsteps, k);   // ode.jl:904
+            x_step<NS, false>(r, v, m, u, omega, mdot, h, a.c, nullptr, maxErr);
+        }
+        const unsigned fullmask = 0xffffffffu;
+        double xe[NS];
+        xe[0] = r[0]; xe[1] = r[1]; xe[2] = r[2];
+        xe[3] = back ? -v[0] : v[0]; xe[4] = back ? -v[1] : v[1]; xe[5] = back ? -v[2] : v[2];
+        if (NS == 7) xe[6] = m;
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const double other = __shfl_xor_sync(fullmask, xe[q], 1);
+            const double d = xe[q] - other;
+            bad |= !(d == d);
+            if (!back && seg < a.n_seg) a.defect[seg * NS + q] = d;       // :101
+        }
+        const double me_o = __shfl_xor_sync(fullmask, maxErr, 1);
+        if (!back && seg < a.n_seg) {
+            if (a.errors) a.errors[seg] = fmax(maxErr, me_o);              // :104
+            if (a.status) a.status[seg] = bad ? LTO_ST_NAN : LTO_OK;
+        }
+    }
+}
+
 }  // namespace cw
+
+template <int NS>
+static cudaError_t launch_state(const DirectArgs& a, cudaStream_t st) {
+    int dev = 0, n_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    const long long n_warps = (a.n_seg + 15) / 16;
+    const long long blocks = (n_warps + 3) / 4;
+    const int grid = (int)std::min<long long>(blocks, (long long)n_sm * 16);
+    cw::k_direct_state<NS><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
 
 template <int NS>
 static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
@@ -378,9 +440,13 @@ static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
 
 cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
-    if (a.cfg.mode != 0 || a.jac == nullptr || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
+    if (a.cfg.mode != 0 || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
     cudaError_t e;
-    if (nstate == 7) e = launch_cw<7>(a, st);
+    if (a.jac == nullptr) {
+        if (nstate == 7) e = launch_state<7>(a, st);
+        else if (nstate == 6) e = launch_state<6>(a, st);
+        else return cudaErrorNotSupported;
+    } else if (nstate == 7) e = launch_cw<7>(a, st);
     else if (nstate == 6) e = launch_cw<6>(a, st);
     else return cudaErrorNotSupported;
     if (e == cudaSuccess) *n_launch = 1;

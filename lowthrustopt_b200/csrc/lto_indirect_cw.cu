@@ -579,6 +579,150 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
 }
 
+// ---------------------------------------------------------------------------
+// K4 (indirect): defect-only -- defectCalc of multiShoot_CRTBP_indirect.jl:63-90 as the SOC step (:197), the
+// 20-point line search (:232-241) and the per-iteration check (:328) call it.  One lane per segment slot, the
+// same RK step, controller and work queue as the state warps above, with nothing published: every warp of the
+// CTA is a "state warp".  Step control over the state alone (a plain `solve`, no dual numbers).
+// ---------------------------------------------------------------------------
+#ifndef LTO_K4I_INLINE
+#define LTO_K4I_INLINE 0
+#endif
+__device__ __noinline__ void sc_eval_state_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
+                                                double m0, double m1, double m2, const SCConst* c, double aL, double rho_inv, double rq, double* out) {
+    const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, v2}, L[3] = {l0, l1, l2}, M[3] = {m0, m1, m2};
+    LawConst lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rho_inv_quarter_aL = rq;
+    double kv[3], kl[3], km[3];
+    sc_eval<false>(R, V, L, M, *c, lw, kv, kl, km, nullptr);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { out[q] = kv[q]; out[3 + q] = kl[q]; out[6 + q] = km[q]; }
+}
+
+template <int J>
+__device__ __forceinline__ void state_only_stage(KStore& K, const double (&x)[ND], double h, double h2, const SCConst& c, const LawConst& lw) {
+    double R[3], V[3], L[3], M[3];
+    stage_input<J>(K, x, h, h2, R, V, L, M);
+#if LTO_K4I_INLINE
+    double kv[3], kl[3], km[3];
+    sc_eval<false>(R, V, L, M, c, lw, kv, kl, km, nullptr);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { K.kv[J][q] = kv[q]; K.kl[J][q] = kl[q]; K.km[J][q] = km[q]; }
+#else
+    double out[9];
+    sc_eval_state_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], &c, lw.aL, lw.rho_inv, lw.rho_inv_quarter_aL, out);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { K.kv[J][q] = out[q]; K.kl[J][q] = out[3 + q]; K.km[J][q] = out[6 + q]; }
+#endif
+}
+
+constexpr int K4I_THREADS = 128;
+
+__global__ void __launch_bounds__(K4I_THREADS, 2) k_indirect_state(IndirectArgs a) {
+    const unsigned fullmask = 0xffffffffu;
+    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
+    double x[ND], xn[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) { x[i] = 0.0; xn[i] = 0.0; }
+    double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
+    LawConst lw; lw.aL = 0.0; lw.rho_inv = 1.0; lw.rho_inv_quarter_aL = 0.0;
+    long long seg = -1, ia = 0;
+    int na = 0, nt = 0, status = 0;
+    bool active = false, lastrej = false, last = false, have = false, exhausted = false;
+    while (true) {
+        bool finished = false;
+        if (have && active) {
+            const double eest = sqrt(esum * (1.0 / (double)ND));
+            if (!(eest == eest)) { status = LTO_ST_NAN; finished = true; }
+            else {
+                double q = (eest == 0.0) ? 5.0 : 0.9 * inv_eighth_root(eest);
+                q = fmin(5.0, fmax(0.2, q));
+                if (eest <= 1.0) {
+                    ++na;
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) x[i] = xn[i];
+                    if (last) { tcur = tf; finished = true; }
+                    else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
+                } else {
+                    lastrej = true; q = fmin(q, 1.0);
+                }
+                h *= q;
+            }
+        }
+        if (active && !finished) {
+            if (h < span * 1e-12) { status = LTO_ST_HMIN; finished = true; }
+            else if (nt >= a.cfg.max_attempts) { status = LTO_ST_MAXSTEPS; finished = true; }
+        }
+        if (active && finished) {
+            bool nan = false;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) nan |= !(x[i] == x[i]);
+            if (nan && status == 0) status = LTO_ST_NAN;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) a.defect[seg * ND + i] = a.x_target ? x[i] - a.x_target[ia * ND + i] : x[i];   // :82
+            if (a.status) a.status[seg] = status;
+            if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
+            active = false;
+        }
+        bool fresh = false;
+        if (!active && !exhausted) {
+            const long long idx = (long long)atomicAdd(a.counter, 1ull);
+            if (idx < a.n_seg) {
+                seg = idx; ia = lto_node_a(seg, a.npt);
+                const long long it = lto_traj_of(seg, a.npt);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) x[i] = a.x0[ia * ND + i];
+                tcur = a.t0[ia]; tf = a.t1[ia];
+                if (!(tcur < tf)) tf = tcur;
+                span = tf - tcur;
+                const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
+                const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
+                lw.aL = tl * a.c.kthr / a.c.mass;                         // CRTBP_stateCostate_deriv.jl:33
+                lw.rho_inv = 1.0 / rho;
+                lw.rho_inv_quarter_aL = lw.aL / (4.0 * rho);
+                na = 0; nt = 0; status = 0; lastrej = false;
+                active = true; fresh = true;
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(fullmask, active)) break;
+        KStore K;
+        state_only_stage<0>(K, x, 0.0, 0.0, a.c, lw);
+        if (__any_sync(fullmask, fresh)) {
+            // Hairer-Norsett-Wanner initial step (drive_rk8 in lto_prop_generic.cuh)
+            double f0[ND], y1[ND];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { f0[q] = x[3 + q]; f0[3 + q] = K.kv[0][q]; f0[6 + q] = K.kl[0][q]; f0[9 + q] = K.km[0][q]; }
+            const double d0 = rms12(x, x, atol, rtol), d1 = rms12(f0, x, atol, rtol);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+            h0 = fmin(h0, span);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) y1[i] = fma(h0, f0[i], x[i]);
+            {
+                const double R1[3] = {y1[0], y1[1], y1[2]}, V1[3] = {y1[3], y1[4], y1[5]}, L1[3] = {y1[6], y1[7], y1[8]}, M1[3] = {y1[9], y1[10], y1[11]};
+                double kv1[3], kl1[3], km1[3];
+                sc_eval<false>(R1, V1, L1, M1, a.c, lw, kv1, kl1, km1, nullptr);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { y1[q] = V1[q] - f0[q]; y1[3 + q] = kv1[q] - f0[3 + q]; y1[6 + q] = kl1[q] - f0[6 + q]; y1[9 + q] = km1[q] - f0[9 + q]; }
+            }
+            const double d2 = rms12(y1, x, atol, rtol) / h0;
+            const double dm = fmax(d1, d2);
+            const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_eighth_root(dm / 0.01);
+            if (fresh) h = fmin(fmin(100.0 * h0, h1), span);
+        }
+        last = false;
+        if (tcur + h >= tf) { h = tf - tcur; last = true; }
+        if (active) ++nt;
+        const double h2 = h * h;
+        state_only_stage<1>(K, x, h, h2, a.c, lw);  state_only_stage<2>(K, x, h, h2, a.c, lw);  state_only_stage<3>(K, x, h, h2, a.c, lw);
+        state_only_stage<4>(K, x, h, h2, a.c, lw);  state_only_stage<5>(K, x, h, h2, a.c, lw);  state_only_stage<6>(K, x, h, h2, a.c, lw);
+        state_only_stage<7>(K, x, h, h2, a.c, lw);  state_only_stage<8>(K, x, h, h2, a.c, lw);  state_only_stage<9>(K, x, h, h2, a.c, lw);
+        state_only_stage<10>(K, x, h, h2, a.c, lw); state_only_stage<11>(K, x, h, h2, a.c, lw); state_only_stage<12>(K, x, h, h2, a.c, lw);
+        esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+        have = true;
+    }
+}
+
 }  // namespace icw
 
 size_t indirect_cw_scratch_bytes(int n_sm) { return (size_t)n_sm * icw::SCRATCH_BYTES_PER_CTA; }
@@ -606,8 +750,24 @@ static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+static cudaError_t launch_k4i(const IndirectArgs& a, cudaStream_t st) {
+    int dev = 0, n_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st); if (e != cudaSuccess) return e;
+    const long long blocks = (a.n_seg + icw::K4I_THREADS - 1) / icw::K4I_THREADS;
+    const int grid = (int)std::min<long long>(blocks, (long long)n_sm * 2);
+    icw::k_indirect_state<<<grid, icw::K4I_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
+    if (ndim == 12 && a.phi == nullptr && a.counter != nullptr && a.cfg.controller == 0 && a.n_seg > 0 && a.n_seg <= 0x7fffffffll) {
+        cudaError_t e = launch_k4i(a, st);
+        if (e == cudaSuccess) *n_launch = 1;
+        return e;
+    }
     if (ndim != 12 || a.phi == nullptr || a.counter == nullptr || a.scratch == nullptr || a.cfg.controller != 0 || a.n_seg <= 0 ||
         a.n_seg > 0x7fffffffll)
         return cudaErrorNotSupported;
