@@ -165,8 +165,9 @@ def workload_config(workload, n_seg, n_gpus):
         desc = {"indirect12_1m": "BASELINE configs[3]: 1,048,576 perturbed indirect-shooting guesses (12-dim reference RHS, adaptive RK8 1e-13, "
                                  "12x12 STM) in TOTAL, sharded across the GPUs, defects + STM blocks all-gathered to every rank",
                 "continuation": "BASELINE configs[4]: 1,024 trajectories x 200 segments (L2_Anderson_2 ballistic stack, thrustLimit ladder 10 -> 0.05 N); "
-                                "one step = one Newton iteration of multiShoot_CRTBP_indirect = 1 STM pass + 22 defect-only passes (SOC + 20 line-search "
-                                "points + check), every pass all-gathered to the solver rank"}[workload]
+                                "one step = one Newton iteration of multiShoot_CRTBP_indirect = 1 STM pass + 22 defect-only passes (SOC, check, and the "
+                                "20 line-search points as ONE batched pass of 20,480 trial trajectories reduced to sum(defect^2) on the device); "
+                                "results all-gathered to the solver rank"}[workload]
         return {"workload": workload, "description": desc, "segments_total": n_seg, "segments_per_gpu": n_seg // n_gpus,
                 "l2": "not flushed: each pass writes more output than the 126 MB L2 holds", "parallelism": "units interleaved across %d GPU(s) "
                 "in chunks; NCCL all-gather of each chunk overlapped with the next chunk's kernel" % n_gpus}
@@ -248,6 +249,17 @@ def run_sharded(args):
     n_seg = n_units * spu
     sh = sharded.ShardedIndirect(h, n_units, n_nodes, nd, dev, n_chunks=args.chunks)
     p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
+    N_ALPHA = 20                                               # lineSearch: alpha_all = LinRange(0.1, 1, 20) (:227)
+    sh_ls = upd = alphas = None
+    if passes_def:
+        # the 20 trial trajectories of every line search form ONE batched pass (n_traj = 20 x 1024) whose merit values
+        # sum(defect^2) are reduced on the device; the trial update is a fixed synthetic direction (Newton steps are host-side)
+        sh_ls = sharded.ShardedIndirect(h, n_units * N_ALPHA, n_nodes, nd, dev, n_chunks=1)
+        upd = torch.empty((n_units, n_nodes, nd), dtype=torch.float64, device=dev)
+        if rank == 0:
+            upd.copy_(torch.from_numpy(1e-4 * np.random.default_rng(20180004).standard_normal((n_units, n_nodes, nd))))
+        sharded._bcast(upd, 0, None)
+        alphas = torch.linspace(0.1, 1.0, N_ALPHA, dtype=torch.float64, device=dev)
     pin_in = pin_out = None
     if rank == 0:
         pin_in = {"XC": capi.PinnedBuffer(XC.shape), "t": capi.PinnedBuffer(tt.shape)}
@@ -258,11 +270,20 @@ def run_sharded(args):
         sh.load(pin_in["XC"].array, pin_in["t"].array, tl, 1.0)
     else:
         sh.load()
+    if sh_ls is not None:
+        sh_ls.t.view(N_ALPHA, n_units, n_nodes).copy_(sh.t.unsqueeze(0).expand(N_ALPHA, -1, -1))
+        sh_ls.tl.view(N_ALPHA, n_units).copy_(sh.tl.unsqueeze(0).expand(N_ALPHA, -1)); sh_ls.rho.fill_(1.0)
 
     def step():
-        out, plan = sh.run(p, jac=True)
-        for _ in range(passes_def):
-            sh.run(p, jac=False)
+        """One Newton iteration's worth of hot-path calls (multiShoot_CRTBP_indirect.jl:290-328)."""
+        out, plan = sh.run(p, jac=True, sync=False)                           # jacobianCalc (:290)
+        if passes_def:
+            sh.run(p, jac=False, sync=False)                                  # SOC defectCalc (:197)
+            torch.add(sh.XC.unsqueeze(0), alphas.view(-1, 1, 1, 1) * upd.unsqueeze(0), out=sh_ls.XC.view(N_ALPHA, n_units, n_nodes, nd))
+            sh_ls.run(p, mode="sumsq", sync=False)                            # lineSearch, 20 alphas in one pass (:232-241)
+            sh.run(p, jac=False, sync=False)                                  # check defectCalc (:328)
+            sh_ls.finish()
+        sh.finish()
         return out
 
     def step_e2e():
@@ -323,7 +344,7 @@ def run_sharded(args):
     roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, units_per_launch, kernel_ms, BYTES_PER_SEG[nd], "indirect12")
     roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
     roof["kernel"] = "k_indirect_cw (the STM pass); launches of %d segments" % units_per_launch
-    gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + passes_def * n_seg * (nd * 8 + 12)
+    gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + (2 * n_seg * (nd * 8 + 12) + n_units * N_ALPHA * 12 if passes_def else 0)
     line = {"metric": "segment-propagations/s (fp64 state+STM)", "value": value, "unit": "segment-propagations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world), "clocks": clocks,

@@ -174,6 +174,10 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
                      const double* thrustLimit_arr, const double* rho_arr,
                      double* defect, int32_t* status, int32_t* nsteps_out, double* phi);
 int lto_sync(lto_handle* h);   /* cudaStreamSynchronize(lto_stream(h)) */
+/* out[r] = sum_i v[r*row_len + i]^2 on the device (enqueue-only, lto_stream): the merit value of the reference's
+ * line searches, er[ind] = sum(defect[:].^2) (multiShoot_CRTBP_indirect.jl:241; multiShoot_CRTBP_direct.jl:425), one row
+ * per trial trajectory, so that a batched line search returns one double per trial instead of every defect. */
+int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_len, double* out);
 
 /* FP64 issue-rate probe used by bench.py for the roofline denominator: runs a
  * register-resident DFMA loop on every SM and returns achieved FLOP/s (FMA = 2). */

@@ -28,7 +28,7 @@ EXPORTS = [
     "lto_direct_params_default", "lto_indirect_params_default",
     "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
-    "lto_direct_dev", "lto_indirect_dev", "lto_fp64_peak_probe", "lto_debug_profile",
+    "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_fp64_peak_probe", "lto_debug_profile",
 ]
 
 
@@ -87,6 +87,7 @@ def lib():
         L.lto_indirect_defect_jac_traj.argtypes = [vp, vp, i64, ci, ci] + [vp] * 4 + [vp] * 4
         L.lto_direct_dev.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 6 + [vp] * 4
         L.lto_indirect_dev.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
+        L.lto_sumsq_dev.argtypes = [vp, vp, i64, i64, vp]
         L.lto_fp64_peak_probe.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lto_debug_profile.argtypes = [vp, vp, ci]
         _lib = L
@@ -301,6 +302,9 @@ class Handle:
         self._ck(lib().lto_direct_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(nstate), int(nsteps), _ptr(Xa),
                                       _ptr(Xb), _ptr(ua), _ptr(ub), _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status),
                                       _ptr(jac)))
+
+    def sumsq_dev(self, v, n_rows, row_len, out):
+        self._ck(lib().lto_sumsq_dev(self._h, _ptr(v), int(n_rows), int(row_len), _ptr(out)))
 
     def indirect_dev(self, params, n_seg, n_nodes, ndim, x0, t0, t1, x_target, thrustLimit, rho, defect, status, nsteps_out, phi):
         self._ck(lib().lto_indirect_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(ndim), _ptr(x0), _ptr(t0),

@@ -541,6 +541,17 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
     return dispatch_indirect(h, a, ndim, p->kernel);
 }
 
+int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_len, double* out) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
+    if (n_rows < 0 || row_len < 0 || (n_rows > 0 && (!v || !out))) return fail(h, LTO_ERR_ARG, "bad argument");
+    CK(h, cudaSetDevice(h->device));
+    cudaError_t e = launch_sumsq_rows(v, n_rows, row_len, out, h->s_compute);
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "sumsq launch: %s", cudaGetErrorString(e));
+    if (n_rows > 0) h->launches += 1;
+    return LTO_SUCCESS;
+}
+
 int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) h = h->child[0];

@@ -44,6 +44,7 @@ cudaError_t launch_indirect_generic(const IndirectArgs& a, int ndim, cudaStream_
 cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch);
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch);
 size_t indirect_cw_scratch_bytes(int n_sm);
+cudaError_t launch_sumsq_rows(const double* v, long long n_rows, long long len, double* out, cudaStream_t st);
 cudaError_t launch_fp64_probe(int iters, double* d_sink, int n_sm, cudaStream_t st, long long* n_threads, int* chains);
 
 }  // namespace lto

@@ -116,6 +116,31 @@ cudaError_t launch_indirect_generic(const IndirectArgs& a, int ndim, cudaStream_
 }
 
 // ---------------------------------------------------------------------------
+// Row sums of squares: out[r] = sum_i v[r*len + i]^2 -- the line searches' merit value
+// er[ind] = sum(defect[:].^2) (multiShoot_CRTBP_indirect.jl:241, multiShoot_CRTBP_direct.jl:425) per trial
+// trajectory, so that only one double per trajectory leaves the GPU.  One warp per row, fixed summation
+// order (deterministic).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sumsq_rows(const double* __restrict__ v, long long n_rows, long long len, double* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const double* p = v + row * len;
+    double s = 0.0;
+    for (long long i = lane; i < len; i += 32) s = fma(p[i], p[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[row] = s;
+}
+
+cudaError_t launch_sumsq_rows(const double* v, long long n_rows, long long len, double* out, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_rows * 32 + 255) / 256);
+    k_sumsq_rows<<<grid, 256, 0, st>>>(v, n_rows, len, out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // FP64 issue-rate probe: CHAINS independent DFMA chains per thread, register resident.
 // ---------------------------------------------------------------------------
 constexpr int PROBE_CHAINS = 8;

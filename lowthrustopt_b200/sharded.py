@@ -67,12 +67,16 @@ class ShardedRunner:
             self._bufs = {"key": key, "full": full, "loc": loc}
         return self._bufs["full"], self._bufs["loc"]
 
-    def run(self, n_units, compute, compute_stream=None):
+    def run(self, n_units, compute, compute_stream=None, sync=True):
         """compute(unit0, count, outs) fills outs[name][:count] for units [unit0, unit0+count) -- on `compute_stream`
-        (a torch.cuda stream object wrapping the library's stream) when on CUDA, synchronously on CPU."""
+        (a torch.cuda stream object wrapping the library's stream) when on CUDA, synchronously on CPU.
+        sync=False (CUDA): return without waiting on the host; the results are ordered on `self.comm_stream`
+        (world > 1) / `compute_stream` (world == 1) -- call finish() before reading them from another stream."""
         plan = ShardPlan(n_units, self.world, self.n_chunks)
         full, loc = self._buffers(plan)
         works = []
+        if self.cuda and self.world > 1 and compute_stream is not None:
+            compute_stream.wait_stream(self.comm_stream)       # the previous pass's gathers still read the local chunk buffers
         for c in range(plan.n_chunks):
             u0, cnt = plan.local(self.rank, c)
             outs = {k: loc[k][c] for k in self.spec}
@@ -106,10 +110,16 @@ class ShardedRunner:
             with torch.cuda.stream(self.comm_stream):
                 for w in works:
                     w.wait()
-            self.comm_stream.synchronize()
-            if compute_stream is not None:
-                compute_stream.synchronize()
+            self._last_stream = compute_stream
+            if sync:
+                self.finish()
         return {k: v[:n_units] for k, v in full.items()}, plan
+
+    def finish(self):
+        if self.cuda:
+            self.comm_stream.synchronize()
+            if getattr(self, "_last_stream", None) is not None:
+                self._last_stream.synchronize()
 
 
 def _bcast(t, src, group):
@@ -130,8 +140,11 @@ class ShardedIndirect:
         f64, i32 = torch.float64, torch.int32
         self.spec_def = {"defect": ((spu, ndim), f64), "status": ((spu,), i32), "nsteps": ((spu, 2), i32)}
         self.spec_jac = dict(self.spec_def, phi=((spu, ndim, ndim), f64))
+        self.spec_ls = {"sumsq": ((), f64), "bad": ((), i32)}
         self.run_def = ShardedRunner(self.spec_def, device, group, n_chunks)
         self.run_jac = ShardedRunner(self.spec_jac, device, group, n_chunks)
+        self.run_ls = ShardedRunner(self.spec_ls, device, group, 1)
+        self._ls_scratch = None
         self._compute = compute
         self.XC = torch.empty((n_traj, n_nodes, ndim), dtype=f64, device=self.device)
         self.t = torch.empty((n_traj, n_nodes), dtype=f64, device=self.device)
@@ -146,7 +159,10 @@ class ShardedIndirect:
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         for dst, a in ((self.XC, XC_all), (self.t, t_TU), (self.tl, thrustLimit), (self.rho, rho)):
             if rank == src:
-                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), tuple(dst.shape)))   # scalars allowed for tl / rho
+                a = np.asarray(a, dtype=np.float64)
+                if a.shape != tuple(dst.shape):
+                    a = np.broadcast_to(a, tuple(dst.shape)).copy()                 # scalars allowed for tl / rho
+                a = np.ascontiguousarray(a)
                 dst.copy_(torch.from_numpy(a), non_blocking=True)
             _bcast(dst, src, self.group)
 
@@ -159,20 +175,43 @@ class ShardedIndirect:
                            outs["nsteps"].data_ptr(), outs["phi"].data_ptr() if jac else None)
         return compute
 
-    def run(self, params, jac=True):
-        """One pass over all trajectories.  Returns {defect, status, nsteps[, phi]} as full, globally ordered tensors
-        (n_traj, n_nodes-1, ...) on every rank's device."""
-        runner = self.run_jac if jac else self.run_def
+    def _gpu_compute_sumsq(self, params):
+        """Line-search form: propagate, then reduce sum(defect^2) per trajectory on the device (lto_sumsq_dev);
+        only one double (+ a status flag) per trajectory is gathered."""
+        h, nn, nd = self.h, self.n_nodes, self.nd
+        spu = nn - 1
+
+        def compute(u0, cnt, outs):
+            if self._ls_scratch is None or self._ls_scratch[0].shape[0] < cnt:
+                self._ls_scratch = (torch.empty((cnt, spu, nd), dtype=torch.float64, device=self.device),
+                                    torch.empty((cnt, spu), dtype=torch.int32, device=self.device))
+            d, st = self._ls_scratch
+            h.indirect_dev(params, cnt * spu, nn, nd, self.XC[u0].data_ptr(), self.t[u0].data_ptr(), None, None,
+                           self.tl[u0:].data_ptr(), self.rho[u0:].data_ptr(), d.data_ptr(), st.data_ptr(), None, None)
+            h.sumsq_dev(d.data_ptr(), cnt, spu * nd, outs["sumsq"].data_ptr())
+            with torch.cuda.stream(self.stream):
+                outs["bad"][:cnt].copy_(st[:cnt].amax(dim=1))
+        return compute
+
+    def run(self, params, jac=True, mode=None, sync=True):
+        """One pass over all trajectories.  mode "jac" / "defect": returns {defect, status, nsteps[, phi]} as full,
+        globally ordered tensors (n_traj, n_nodes-1, ...) on every rank's device; mode "sumsq": {sumsq, bad} (n_traj,)."""
+        mode = mode or ("jac" if jac else "defect")
+        runner = {"jac": self.run_jac, "defect": self.run_def, "sumsq": self.run_ls}[mode]
         if self._compute is not None:
-            compute = lambda u0, cnt, outs: self._compute(self, params, jac, u0, cnt, outs)   # noqa: E731
+            compute = lambda u0, cnt, outs: self._compute(self, params, mode if mode == "sumsq" else (mode == "jac"), u0, cnt, outs)   # noqa: E731
         else:
             if self.h is None:
                 raise capi.LtoError("ShardedIndirect needs a liblto_b200 handle: there is no CPU propagation path")
-            compute = self._gpu_compute(params, jac)
+            compute = self._gpu_compute_sumsq(params) if mode == "sumsq" else self._gpu_compute(params, mode == "jac")
             if self.stream is not None:                       # inputs were produced on torch's current stream
                 self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        out, plan = runner.run(self.n_traj, compute, self.stream)
+        out, plan = runner.run(self.n_traj, compute, self.stream, sync=sync)
         return out, plan
+
+    def finish(self):
+        for r in (self.run_jac, self.run_def, self.run_ls):
+            r.finish()
 
 
 class ShardedDirect:

@@ -254,3 +254,30 @@ def test_multi_device_handle_equals_single_device(lto):
         hm.direct_dev(capi.direct_params(), 1, 0, 7, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)   # device-pointer calls need a single-device handle
     assert hm.launches > 0
     hm.close()
+
+
+def test_sumsq_dev_and_sharded_line_search_single_rank(lto):
+    """lto_sumsq_dev = the line searches' er[ind] = sum(defect[:].^2); the sharded layer's "sumsq" mode (world 1) equals
+    the defect-only pass reduced on the host."""
+    import torch
+    from lowthrustopt_b200 import sharded
+    dev = torch.device("cuda", 0)
+    v = torch.randn((37, 2400), dtype=torch.float64, device=dev)
+    out = torch.empty(37, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    lto.sumsq_dev(v.data_ptr(), 37, 2400, out.data_ptr()); lto.sync()
+    ref = (v.cpu().numpy() ** 2).sum(axis=1)
+    assert np.abs(out.cpu().numpy() / ref - 1.0).max() < 1e-14
+    c = S.continuation_batch(n_traj=11, n_seg_per_traj=20, ndim=12)
+    sh = sharded.ShardedIndirect(lto, 11, 21, 12, dev, n_chunks=2)
+    sh.load(c["XC_all"], c["t_TU"], c["thrustLimit"], 1.0)
+    p = capi.indirect_params(p=1.0, rho=1.0)
+    d, _ = sh.run(p, jac=False)
+    ls, _ = sh.run(p, mode="sumsq")
+    r = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"], jac=False)
+    assert np.array_equal(d["defect"].cpu().numpy().reshape(-1, 12), r["defect"])
+    assert np.abs(ls["sumsq"].cpu().numpy() / (r["defect"].reshape(11, -1) ** 2).sum(axis=1) - 1.0).max() < 1e-13
+    assert int(ls["bad"].max()) == 0
+    j, _ = sh.run(p, jac=True)
+    rj = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"], jac=True)
+    assert np.abs(j["phi"].cpu().numpy().reshape(-1, 12, 12) - rj["phi"]).max() < 1e-12
