@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
     ap.add_argument("--chunks", type=int, default=4, help="all-gather / compute overlap chunks of the sharded paths")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="sharded workloads: deliver results to the solver rank by the kernels' own stores into its HBM over NVLink "
+                         "peer memory (fused, default) or by a chunked NCCL all-gather")
     return ap.parse_args()
 
 
@@ -247,14 +250,19 @@ def run_sharded(args):
             XC, tt, tl = c["XC_all"], c["t_TU"], c["thrustLimit"]
     spu = n_nodes - 1
     n_seg = n_units * spu
-    sh = sharded.ShardedIndirect(h, n_units, n_nodes, nd, dev, n_chunks=args.chunks)
+    peer = args.gather == "peer"
+    if peer:
+        sh = sharded.PeerIndirect(h, n_units, n_nodes, nd, dev)
+    else:
+        sh = sharded.ShardedIndirect(h, n_units, n_nodes, nd, dev, n_chunks=args.chunks)
     p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
     N_ALPHA = 20                                               # lineSearch: alpha_all = LinRange(0.1, 1, 20) (:227)
     sh_ls = upd = alphas = None
     if passes_def:
         # the 20 trial trajectories of every line search form ONE batched pass (n_traj = 20 x 1024) whose merit values
         # sum(defect^2) are reduced on the device; the trial update is a fixed synthetic direction (Newton steps are host-side)
-        sh_ls = sharded.ShardedIndirect(h, n_units * N_ALPHA, n_nodes, nd, dev, n_chunks=1)
+        sh_ls = (sharded.PeerIndirect(h, n_units * N_ALPHA, n_nodes, nd, dev) if peer else
+                 sharded.ShardedIndirect(h, n_units * N_ALPHA, n_nodes, nd, dev, n_chunks=1))
         upd = torch.empty((n_units, n_nodes, nd), dtype=torch.float64, device=dev)
         if rank == 0:
             upd.copy_(torch.from_numpy(1e-4 * np.random.default_rng(20180004).standard_normal((n_units, n_nodes, nd))))
@@ -274,8 +282,21 @@ def run_sharded(args):
         sh_ls.t.view(N_ALPHA, n_units, n_nodes).copy_(sh.t.unsqueeze(0).expand(N_ALPHA, -1, -1))
         sh_ls.tl.view(N_ALPHA, n_units).copy_(sh.tl.unsqueeze(0).expand(N_ALPHA, -1)); sh_ls.rho.fill_(1.0)
 
+    def step_peer():
+        out = sh.run(p, jac=True, wait=not passes_def)                        # jacobianCalc (:290)
+        if passes_def:
+            sh.run(p, jac=False, wait=False)                                  # SOC defectCalc (:197)
+            torch.add(sh.XC.unsqueeze(0), alphas.view(-1, 1, 1, 1) * upd.unsqueeze(0), out=sh_ls.XC.view(N_ALPHA, n_units, n_nodes, nd))
+            sh_ls.run(p, mode="sumsq", wait=False)                            # lineSearch, 20 alphas in one pass (:232-241)
+            sh.run(p, jac=False, wait=True)                                   # check defectCalc (:328); flags are monotone: all earlier passes have landed too
+            sh_ls.pg_ls.wait_all()
+        h.sync()
+        return out
+
     def step():
         """One Newton iteration's worth of hot-path calls (multiShoot_CRTBP_indirect.jl:290-328)."""
+        if peer:
+            return step_peer()
         out, plan = sh.run(p, jac=True, sync=False)                           # jacobianCalc (:290)
         if passes_def:
             sh.run(p, jac=False, sync=False)                                  # SOC defectCalc (:197)
@@ -292,12 +313,15 @@ def run_sharded(args):
         else:
             sh.load()
         out = step()
+        r = 0.0
         if rank == 0:
             for k in pin_out:
                 pin_out[k].copy_(out[k], non_blocking=True)
             torch.cuda.synchronize()
-            return float(pin_out["defect"][0, 0, 0])
-        return 0.0
+            r = float(pin_out["defect"][0, 0, 0])
+        if peer and world > 1:
+            dist.barrier()                                    # the solver rank has consumed the arrays: peers may overwrite them
+        return r
 
     def barrier():
         if world > 1:
@@ -309,7 +333,8 @@ def run_sharded(args):
     barrier()
     sampler = ClockSampler(local); sampler.start(); time.sleep(0.3)
     l0 = h.launches
-    sh.run_jac.timing = []
+    if not peer:
+        sh.run_jac.timing = []
     stream = sh.stream
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
@@ -323,10 +348,26 @@ def run_sharded(args):
     if world > 1:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
     ms_per_step = float(t_total.item()) / args.steps
-    kt = [(a.elapsed_time(b), cnt) for a, b, cnt in sh.run_jac.timing]
-    sh.run_jac.timing = None
-    kernel_ms = float(np.mean([x[0] for x in kt])); units_per_launch = int(np.mean([x[1] for x in kt])) * spu
-    nst = out["nsteps"].cpu().numpy().reshape(-1, 2)
+    if peer:
+        # the dominant kernel alone: this rank's STM launch into its own (local) scratch, CUDA events on the library stream
+        u0, u1 = sh.pg.slab()
+        cnt = u1 - u0
+        sc = {k: torch.empty((cnt,) + tuple(sp), dtype=dt, device=dev) for k, (sp, dt) in sh.spec_jac.items()}
+        ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        for i in range(reps + 1):
+            if i == 1:
+                ka.record(stream)
+            h.indirect_dev(p, cnt * spu, n_nodes, nd, sh.XC[u0].data_ptr(), sh.t[u0].data_ptr(), None, None, sh.tl[u0:].data_ptr(),
+                           sh.rho[u0:].data_ptr(), sc["defect"].data_ptr(), sc["status"].data_ptr(), sc["nsteps"].data_ptr(), sc["phi"].data_ptr())
+        kb.record(stream); h.sync()
+        kernel_ms = ka.elapsed_time(kb) / reps; units_per_launch = cnt * spu
+        nst = sc["nsteps"].cpu().numpy().reshape(-1, 2)
+    else:
+        kt = [(a.elapsed_time(b), cnt) for a, b, cnt in sh.run_jac.timing]
+        sh.run_jac.timing = None
+        kernel_ms = float(np.mean([x[0] for x in kt])); units_per_launch = int(np.mean([x[1] for x in kt])) * spu
+        nst = out["nsteps"].cpu().numpy().reshape(-1, 2)
     attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
     passes = 1 + passes_def
     value = n_seg * passes / (ms_per_step * 1e-3)
@@ -349,8 +390,11 @@ def run_sharded(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world), "clocks": clocks,
             "passes_per_step": {"stm": 1, "defect_only": passes_def},
-            "collective": {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor)", "chunks": args.chunks,
-                           "bytes_gathered_per_rank_per_step": int(gathered)},
+            "collective": ({"kind": "none: kernels store their slab into the solver rank's HBM over NVLink peer memory (CUDA IPC), "
+                                    "stream-ordered completion flags", "bytes_into_solver_rank_per_step": int(gathered * (world - 1) // world)}
+                           if peer else
+                           {"kind": "ncclAllGather (torch.distributed all_gather_into_tensor)", "chunks": args.chunks,
+                            "bytes_gathered_per_rank_per_step": int(gathered)}),
             "e2e": {"value": n_seg * passes * args.steps / float(t_e2e.item()), "unit": "segment-propagations/s",
                     "h2d_bytes_per_step": int(n_units * n_nodes * (nd + 1) * 8), "d2h_bytes_per_step": int(n_seg * (nd * 8 + nd * nd * 8 + 4)),
                     "timing": "host wall clock on the solver rank: pinned host inputs -> H2D -> broadcast -> sharded passes + all-gather -> "
@@ -358,6 +402,12 @@ def run_sharded(args):
             "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if peer:
+        for o in (sh, sh_ls):
+            if o is not None:
+                o.pg.close()
+                if o.pg_ls is not None:
+                    o.pg_ls.close()
     h.close()
     if world > 1:
         dist.destroy_process_group()
@@ -398,9 +448,46 @@ def allgather_leg(args, h, dev, wl, n_seg, world, rank, batch, p):
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.steps
-    return {"value": total / (ms * 1e-3), "unit": "segment-propagations/s", "ms_per_step": ms, "chunks": args.chunks,
-            "bytes_received_per_rank_per_step": int(per_unit * n_seg * (world - 1)),
-            "what": "same batch, outputs of all ranks all-gathered (NCCL over NVLink) into every rank's HBM, max over ranks"}
+    res = {"value": total / (ms * 1e-3), "unit": "segment-propagations/s", "ms_per_step": ms, "chunks": args.chunks,
+           "bytes_received_per_rank_per_step": int(per_unit * n_seg * (world - 1)),
+           "what": "same batch, outputs of all ranks all-gathered (NCCL over NVLink) into every rank's HBM, max over ranks"}
+    # ---- fused alternative: every rank's kernel stores its slab straight into the solver rank's HBM (NVLink peer memory)
+    if wl.startswith("direct"):
+        pe = sharded.PeerDirect(h, total, ns, dev)
+        for k in pe.inp:
+            pe.inp[k].copy_(sh.inp[k])
+    else:
+        pe = sharded.PeerIndirect(h, total, 2, nd, dev)
+        pe.XC.copy_(sh.XC); pe.t.copy_(sh.t); pe.tl.copy_(sh.tl); pe.rho.copy_(sh.rho)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        pe.run(p, jac=True)
+    h.sync(); dist.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(pe.stream)
+    for _ in range(args.steps):
+        out = pe.run(p, jac=True)
+    e1.record(pe.stream)
+    h.sync(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t.item()) / args.steps
+    # the gathered arrays on the solver rank must equal the all-gathered ones
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        ref, _ = sh.run(p, jac=True)
+        key = "jac" if wl.startswith("direct") else "phi"
+        same = torch.equal(out["defect"].reshape(-1), ref["defect"].reshape(-1)) and bool(((out[key].reshape(-1) - ref[key].reshape(-1)).abs().max() < 1e-11).item())
+        ok[0] = 1 if same else 0
+    else:
+        sh.run(p, jac=True)
+    dist.broadcast(ok, src=0)
+    res["peer_gather"] = {"value": total / (ms2 * 1e-3), "unit": "segment-propagations/s", "ms_per_step": ms2,
+                          "bytes_into_solver_rank_per_step": int(per_unit * n_seg * (world - 1)), "matches_allgather": bool(ok.item()),
+                          "what": "same batch, one launch per rank, kernels store their slab into the solver rank's HBM over NVLink peer memory; "
+                                  "timed on the library streams incl. the solver rank's wait for every rank's completion flag, max over ranks"}
+    pe.pg.close()
+    return res
 
 
 def run_ours(args):

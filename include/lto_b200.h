@@ -179,6 +179,26 @@ int lto_sync(lto_handle* h);   /* cudaStreamSynchronize(lto_stream(h)) */
  * per trial trajectory, so that a batched line search returns one double per trial instead of every defect. */
 int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_len, double* out);
 
+/* ---- peer memory: one process per GPU, results delivered to the solver rank without a collective --------
+ * The rank that runs the Newton step allocates its full output arrays with lto_dev_alloc and exports them
+ * (lto_ipc_export: a 64-byte cudaIpcMemHandle_t to send to the other processes by any means); every other rank
+ * maps them (lto_ipc_open, NVLink peer access) and passes the mapped addresses, offset to its own slab, as the OUTPUT
+ * pointers of lto_direct_dev / lto_indirect_dev: the kernels' epilogue stores then travel over NVLink into the solver
+ * rank's HBM while the kernel is still computing (fused compute + gather, no SM taken from the propagation).
+ * lto_push_async is the DMA-engine alternative: copy a finished local chunk to (peer) memory on the copy stream,
+ * ordered after the work enqueued so far on lto_stream. */
+void* lto_dev_alloc(lto_handle* h, size_t bytes);
+void lto_dev_free(lto_handle* h, void* p);
+int lto_ipc_export(lto_handle* h, void* dev_ptr, void* handle64);
+int lto_ipc_open(lto_handle* h, const void* handle64, void** dev_ptr);
+int lto_ipc_close(lto_handle* h, void* dev_ptr);
+int lto_push_async(lto_handle* h, void* dst, const void* src, size_t bytes);
+int lto_sync_copies(lto_handle* h);
+/* Stream-ordered flags on lto_stream: lto_signal_dev writes `value` to the 64-bit word at `flag` (device or peer-mapped
+ * memory) once everything enqueued before it has completed; lto_wait_dev holds the stream until *flag >= value. */
+int lto_signal_dev(lto_handle* h, void* flag, uint64_t value);
+int lto_wait_dev(lto_handle* h, void* flag, uint64_t value);
+
 /* FP64 issue-rate probe used by bench.py for the roofline denominator: runs a
  * register-resident DFMA loop on every SM and returns achieved FLOP/s (FMA = 2). */
 int lto_fp64_peak_probe(lto_handle* h, int iters, double* flops_per_s, double* ms);

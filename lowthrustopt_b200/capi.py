@@ -28,7 +28,8 @@ EXPORTS = [
     "lto_direct_params_default", "lto_indirect_params_default",
     "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
-    "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_fp64_peak_probe", "lto_debug_profile",
+    "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_dev_alloc", "lto_dev_free", "lto_ipc_export", "lto_ipc_open", "lto_ipc_close",
+    "lto_push_async", "lto_sync_copies", "lto_signal_dev", "lto_wait_dev", "lto_fp64_peak_probe", "lto_debug_profile",
 ]
 
 
@@ -88,6 +89,16 @@ def lib():
         L.lto_direct_dev.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 6 + [vp] * 4
         L.lto_indirect_dev.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
         L.lto_sumsq_dev.argtypes = [vp, vp, i64, i64, vp]
+        L.lto_dev_alloc.restype = vp
+        L.lto_dev_alloc.argtypes = [vp, C.c_size_t]
+        L.lto_dev_free.argtypes = [vp, vp]
+        L.lto_ipc_export.argtypes = [vp, vp, vp]
+        L.lto_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+        L.lto_ipc_close.argtypes = [vp, vp]
+        L.lto_push_async.argtypes = [vp, vp, vp, C.c_size_t]
+        L.lto_sync_copies.argtypes = [vp]
+        L.lto_signal_dev.argtypes = [vp, vp, C.c_uint64]
+        L.lto_wait_dev.argtypes = [vp, vp, C.c_uint64]
         L.lto_fp64_peak_probe.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lto_debug_profile.argtypes = [vp, vp, ci]
         _lib = L
@@ -302,6 +313,41 @@ class Handle:
         self._ck(lib().lto_direct_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(nstate), int(nsteps), _ptr(Xa),
                                       _ptr(Xb), _ptr(ua), _ptr(ub), _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status),
                                       _ptr(jac)))
+
+    # ---- peer memory --------------------------------------------------
+    def dev_alloc(self, nbytes):
+        p = lib().lto_dev_alloc(self._h, int(nbytes))
+        if not p:
+            raise LtoError("lto_dev_alloc(%d) failed: %s" % (nbytes, lib().lto_last_error(self._h).decode()))
+        return int(p)
+
+    def dev_free(self, ptr):
+        lib().lto_dev_free(self._h, C.c_void_p(ptr))
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        self._ck(lib().lto_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return bytes(buf.raw)
+
+    def ipc_open(self, handle64):
+        out = C.c_void_p()
+        self._ck(lib().lto_ipc_open(self._h, C.create_string_buffer(handle64, 64), C.byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, ptr):
+        self._ck(lib().lto_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def push_async(self, dst, src, nbytes):
+        self._ck(lib().lto_push_async(self._h, C.c_void_p(dst), C.c_void_p(src), int(nbytes)))
+
+    def sync_copies(self):
+        self._ck(lib().lto_sync_copies(self._h))
+
+    def signal_dev(self, flag_ptr, value):
+        self._ck(lib().lto_signal_dev(self._h, C.c_void_p(flag_ptr), int(value)))
+
+    def wait_dev(self, flag_ptr, value):
+        self._ck(lib().lto_wait_dev(self._h, C.c_void_p(flag_ptr), int(value)))
 
     def sumsq_dev(self, v, n_rows, row_len, out):
         self._ck(lib().lto_sumsq_dev(self._h, _ptr(v), int(n_rows), int(row_len), _ptr(out)))

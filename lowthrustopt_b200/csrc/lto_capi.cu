@@ -552,6 +552,92 @@ int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_le
     return LTO_SUCCESS;
 }
 
+// ---- peer memory (multi-process multi-GPU: outputs written straight into the solver rank's HBM over NVLink) ----
+void* lto_dev_alloc(lto_handle* h, size_t bytes) {
+    if (!h || h->n_child > 0) return nullptr;
+    if (cudaSetDevice(h->device) != cudaSuccess) return nullptr;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 256) != cudaSuccess) { cudaGetLastError(); fail(h, LTO_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void lto_dev_free(lto_handle* h, void* p) {
+    if (!h || !p) return;
+    cudaSetDevice(h->device);
+    cudaFree(p);
+}
+int lto_ipc_export(lto_handle* h, void* dev_ptr, void* handle64) {
+    if (!h || !dev_ptr || !handle64) return fail(h, LTO_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CK(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    CK(h, cudaIpcGetMemHandle(&mh, dev_ptr));
+    memcpy(handle64, &mh, 64);
+    return LTO_SUCCESS;
+}
+int lto_ipc_open(lto_handle* h, const void* handle64, void** dev_ptr) {
+    if (!h || !handle64 || !dev_ptr) return fail(h, LTO_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handle64, 64);
+    CK(h, cudaIpcOpenMemHandle(dev_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    return LTO_SUCCESS;
+}
+int lto_ipc_close(lto_handle* h, void* dev_ptr) {
+    if (!h || !dev_ptr) return fail(h, LTO_ERR_ARG, "null argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaIpcCloseMemHandle(dev_ptr));
+    return LTO_SUCCESS;
+}
+// dst/src: device pointers (local or peer-mapped).  Enqueued on the copy stream after everything enqueued so far on the
+// compute stream, i.e. a DMA-engine push that overlaps the next kernel.  lto_sync_copies waits for all of them.
+int lto_push_async(lto_handle* h, void* dst, const void* src, size_t bytes) {
+    if (!h || h->n_child > 0) return fail(h, LTO_ERR_ARG, "needs a single-device handle");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaEventRecord(h->ev_in, h->s_compute));
+    CK(h, cudaStreamWaitEvent(h->s_copy, h->ev_in, 0));
+    if (bytes) CK(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->s_copy));
+    return LTO_SUCCESS;
+}
+int lto_sync_copies(lto_handle* h) {
+    if (!h || h->n_child > 0) return fail(h, LTO_ERR_ARG, "needs a single-device handle");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaStreamSynchronize(h->s_copy));
+    return LTO_SUCCESS;
+}
+
+// Stream-ordered 64-bit flags (driver stream memory operations, resolved at run time so that the library does not
+// link libcuda): "my slab is written" signals from every rank into the solver rank's memory, awaited on its stream.
+typedef int (*lto_cu_stream_val_fn)(void* stream, unsigned long long addr, unsigned long long value, unsigned int flags);
+static lto_cu_stream_val_fn g_cu_write64 = nullptr, g_cu_wait64 = nullptr;
+static int resolve_stream_memops(lto_handle* h) {
+    if (g_cu_write64 && g_cu_wait64) return 0;
+    void* fw = nullptr; void* fq = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fw, cudaEnableDefault, &qr) != cudaSuccess || !fw ||
+        cudaGetDriverEntryPoint("cuStreamWaitValue64", &fq, cudaEnableDefault, &qr) != cudaSuccess || !fq) {
+        cudaGetLastError();
+        return fail(h, LTO_ERR_CUDA, "stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64) are not available");
+    }
+    g_cu_write64 = (lto_cu_stream_val_fn)fw; g_cu_wait64 = (lto_cu_stream_val_fn)fq;
+    return 0;
+}
+int lto_signal_dev(lto_handle* h, void* flag, uint64_t value) {
+    if (!h || h->n_child > 0 || !flag) return fail(h, LTO_ERR_ARG, "needs a single-device handle and a flag address");
+    CK(h, cudaSetDevice(h->device));
+    int rc = resolve_stream_memops(h); if (rc) return rc;
+    int e = g_cu_write64((void*)h->s_compute, (unsigned long long)(uintptr_t)flag, (unsigned long long)value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+    if (e != 0) return fail(h, LTO_ERR_CUDA, "cuStreamWriteValue64 -> CUresult %d", e);
+    return LTO_SUCCESS;
+}
+int lto_wait_dev(lto_handle* h, void* flag, uint64_t value) {
+    if (!h || h->n_child > 0 || !flag) return fail(h, LTO_ERR_ARG, "needs a single-device handle and a flag address");
+    CK(h, cudaSetDevice(h->device));
+    int rc = resolve_stream_memops(h); if (rc) return rc;
+    int e = g_cu_wait64((void*)h->s_compute, (unsigned long long)(uintptr_t)flag, (unsigned long long)value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (e != 0) return fail(h, LTO_ERR_CUDA, "cuStreamWaitValue64 -> CUresult %d", e);
+    return LTO_SUCCESS;
+}
+
 int lto_debug_profile(lto_handle* h, unsigned long long* out, int n_words) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) h = h->child[0];

@@ -28,6 +28,16 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// ---- TMA bulk store shared::cta -> global (one elected thread).  The generic-proxy writes of the staging buffer are
+// made visible to the async proxy by fence_proxy_async() in every writing thread before the barrier that precedes it.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gptr, unsigned smem_addr, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr), "r"(smem_addr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- Branch-free 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H /
 // MUFU.RCP64H, ~2^-20) + one cubically convergent correction (error ~2^-60 before
 // rounding).  No slow-path subroutine: keeps a state warp's dependent chain and its

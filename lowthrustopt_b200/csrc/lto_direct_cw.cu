@@ -45,7 +45,11 @@ struct Cfg {
     static constexpr int OFF_BM = OFF_H + 1;                 // bm[3] (nstate 7)
     static constexpr int STEP_DOUBLES = OFF_BM + ((NS == 7) ? 3 : 0);
     static constexpr size_t REC_BYTES = (size_t)NTILE * NSLOT * STEP_DOUBLES * 32 * sizeof(double);
-    static constexpr size_t SMEM = REC_BYTES + (size_t)NTILE * NSLOT * 2 * sizeof(unsigned long long);
+    static constexpr int NV = 2 * (NS + 3);
+    static constexpr size_t OUT_TILE_BYTES = (size_t)16 * NS * NV * sizeof(double);      // one tile's Jacobian blocks, in the output's own layout
+    static constexpr size_t OUT_BYTES = (size_t)NTILE * OUT_TILE_BYTES;
+    static constexpr size_t BAR_OFF = REC_BYTES + OUT_BYTES;
+    static constexpr size_t SMEM = BAR_OFF + (size_t)NTILE * NSLOT * 2 * sizeof(unsigned long long);
 };
 
 using namespace cwc;
@@ -215,13 +219,11 @@ __device__ __forceinline__ void col_init(ColState& c, int col) {
 //   forward leg  +S        -> columns [X_a | u_a]
 //   backward leg -(R S R)  -> columns [X_b]      -(R S) -> [u_b]      
 template <int NS>
-__device__ __forceinline__ void col_store(const DirectArgs& a, const ColState& c, long long tile, int col, int lane) {
+__device__ __forceinline__ void col_store(double* __restrict__ stage, const ColState& c, int col, int lane) {
     constexpr int NV = 2 * (NS + 3);
     const int back = lane & 1, gc = col - NS;
-    const long long seg = tile * 16 + (lane >> 1);
-    if (seg >= a.n_seg) return;
     const int ocol = (gc >= 0) ? (2 * NS + (back ? 3 : 0) + gc) : ((back ? NS : 0) + col);
-    double* J = a.jac + seg * (long long)(NS * NV) + (long long)ocol * NS;
+    double* J = stage + (lane >> 1) * (NS * NV) + ocol * NS;
     const double rj = (col >= 3 && col < 6) ? -1.0 : 1.0;
     const double sp = back ? -rj : 1.0;       // sign of the r / m rows
     const double sq = back ? rj : 1.0;        // sign of the v rows
@@ -231,7 +233,7 @@ __device__ __forceinline__ void col_store(const DirectArgs& a, const ColState& c
 }
 
 template <int NS>
-__device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_tiles, int col, int lane, double* recs, unsigned bars) {
+__device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_tiles, int col, int lane, double* recs, double* outs, unsigned bars) {
     typedef Cfg<NS> C;
     const int nstep = a.cfg.nsteps - 1;
     const double omega = (lane & 1) ? -1.0 : 1.0;
@@ -253,10 +255,28 @@ __device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_til
                 if (NS == 7 && k == 0 && gc >= 0) cs[t].bm = rec[(C::OFF_BM + gc) * 32];
                 col_step<NS>(cs[t].sr, cs[t].sv, cs[t].sm, cs[t].bm, ec, omega, kom6, rec);
                 mbar_arrive(empty);
-                if (k == nstep - 1) col_store<NS>(a, cs[t], pair * NTILE + t, col, lane);
+                if (k == nstep - 1) {
+                    // ---- this tile's 16 Jacobian blocks are one contiguous run of the output: stage them in shared memory in
+                    // the output's own layout and let the TMA engine write the run (one bulk store, fully coalesced, also when
+                    // `jac` is NVLink peer memory of another GPU).
+                    const long long tile = pair * NTILE + t;
+                    const long long seg0 = tile * 16;
+                    double* stage = outs + (size_t)t * (C::OUT_TILE_BYTES / sizeof(double));
+                    const bool leader = (col == 0 && lane == 0);
+                    if (leader) bulk_store_wait_read();                          // the previous store from this buffer has been read out
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
+                    col_store<NS>(stage, cs[t], col, lane);
+                    fence_proxy_async();
+                    asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
+                    if (leader && seg0 < a.n_seg) {
+                        const long long nseg = (a.n_seg - seg0 < 16) ? (a.n_seg - seg0) : 16;
+                        bulk_store(a.jac + seg0 * (long long)(NS * C::NV), smem_u32(stage), (unsigned)(nseg * NS * C::NV * sizeof(double)));
+                    }
+                }
             }
         }
     }
+    if (col == 0 && lane == 0) bulk_store_wait_all();        // the last bulk stores must have completed before the CTA retires
 }
 
 template <int NS>
@@ -333,7 +353,8 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a
     typedef Cfg<NS> C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* recs = reinterpret_cast<double*>(smem_raw);
-    const unsigned bars = smem_u32(smem_raw + C::REC_BYTES);
+    double* outs = reinterpret_cast<double*>(smem_raw + C::REC_BYTES);
+    const unsigned bars = smem_u32(smem_raw + C::BAR_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a
         state_warp<NS>(a, n_tiles, warp - XW0, lane, recs, bars);
     } else {
         const int col = warp < XW0 ? warp : warp - NTILE;
-        column_warp<NS>(a, n_tiles, col, lane, recs, bars);
+        column_warp<NS>(a, n_tiles, col, lane, recs, outs, bars);
     }
 }
 
@@ -441,6 +462,7 @@ static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
 cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
     if (a.cfg.mode != 0 || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
+    if (a.jac != nullptr && (reinterpret_cast<uintptr_t>(a.jac) & 15u) != 0) return cudaErrorNotSupported;   // bulk stores need 16-byte alignment
     cudaError_t e;
     if (a.jac == nullptr) {
         if (nstate == 7) e = launch_state<7>(a, st);

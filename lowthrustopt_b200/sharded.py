@@ -257,3 +257,159 @@ class ShardedDirect:
                 self.stream.wait_stream(torch.cuda.current_stream(self.device))
         out, plan = runner.run(self.n_seg, compute, self.stream)
         return out, plan
+
+
+# --------------------------------------------------------------------------- fused compute + gather over NVLink peer memory
+class _DevArray:
+    """Raw device memory seen as a torch tensor (no copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 2, "strides": None}
+
+
+_TYPESTR = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8"}
+
+
+class PeerGather:
+    """The solver rank (`root`) owns the full output arrays; every other rank maps them over NVLink (CUDA IPC) and the
+    propagation kernels are launched with those mapped addresses as their OUTPUT pointers, so each rank's slab is stored
+    straight into the solver rank's HBM by the kernel's own epilogue -- no collective, no SM taken from the propagation,
+    the transfer overlaps the computation segment by segment.  Completion is a stream-ordered 64-bit flag per rank in the
+    solver rank's memory (lto_signal_dev / lto_wait_dev): nothing in the steady state touches the host.
+
+    Units are split into contiguous, equal slabs (rank r: [n*r/W, n*(r+1)/W)).  spec: name -> (per-unit shape, dtype)."""
+
+    def __init__(self, handle, spec, n_units, device, group=None, root=0):
+        self.h, self.spec, self.n_units, self.device, self.group, self.root = handle, dict(spec), int(n_units), torch.device(device), group, root
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.unit_bytes = {k: int(np.prod(s, dtype=np.int64)) * torch.empty((), dtype=dt).element_size() for k, (s, dt) in self.spec.items()}
+        self.seq = 0
+        self._owned, self._mapped = {}, {}
+        if self.rank == root:
+            for k in self.spec:
+                self._owned[k] = handle.dev_alloc(max(256, self.n_units * self.unit_bytes[k]))
+            self._owned["__flags"] = handle.dev_alloc(256)
+            self.flags_t = torch.as_tensor(_DevArray(self._owned["__flags"], (32,), "<i8"), device=self.device)
+            self.flags_t.zero_()
+            torch.cuda.synchronize(self.device)
+            payload = [{k: handle.ipc_export(p) for k, p in self._owned.items()}]
+        else:
+            payload = [None]
+        if self.world > 1:
+            dist.broadcast_object_list(payload, src=root, group=group)
+        if self.rank == root:
+            self.ptr = dict(self._owned)
+        else:
+            self._mapped = {k: handle.ipc_open(hd) for k, hd in payload[0].items()}
+            self.ptr = dict(self._mapped)
+
+    def slab(self, rank=None):
+        r = self.rank if rank is None else rank
+        return self.n_units * r // self.world, self.n_units * (r + 1) // self.world
+
+    def out_ptr(self, name, unit0):
+        return self.ptr[name] + unit0 * self.unit_bytes[name]
+
+    def signal(self):
+        """Enqueue on the library stream: "everything this rank enqueued so far has been written"."""
+        self.h.signal_dev(self.ptr["__flags"] + 8 * self.rank, self.seq)
+
+    def begin(self):
+        self.seq += 1
+
+    def wait_all(self):
+        """Solver rank: hold the library stream until every rank's slab of pass `seq` has landed."""
+        if self.rank == self.root:
+            for r in range(self.world):
+                self.h.wait_dev(self.ptr["__flags"] + 8 * r, self.seq)
+
+    def tensors(self):
+        """Solver rank: the full arrays as torch tensors (views of the gathered memory)."""
+        assert self.rank == self.root
+        return {k: torch.as_tensor(_DevArray(self._owned[k], (self.n_units,) + tuple(s), _TYPESTR[dt]), device=self.device)
+                for k, (s, dt) in self.spec.items()}
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self._mapped.values():
+            self.h.ipc_close(p)
+        self._mapped = {}
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self._owned.values():
+            self.h.dev_free(p)
+        self._owned = {}
+
+
+class PeerIndirect(ShardedIndirect):
+    """ShardedIndirect with the results delivered by PeerGather instead of an all-gather: one kernel launch per rank and
+    pass over the rank's contiguous block of trajectories, output pointers in the solver rank's memory."""
+
+    def __init__(self, handle, n_traj, n_nodes, ndim, device, group=None, root=0):
+        super().__init__(handle, n_traj, n_nodes, ndim, device, group, n_chunks=1)
+        self.root = root
+        self.pg = PeerGather(handle, self.spec_jac, n_traj, device, group, root)
+        self.pg_ls = None
+
+    def run(self, params, jac=True, wait=True, mode=None):
+        """Enqueue one pass.  With wait=True the solver rank's library stream is held until all slabs have landed, so work
+        enqueued afterwards on that stream (or after lto_sync) sees the complete arrays.  Returns them on the solver rank.
+        mode "sumsq": the line-search form, one sum(defect^2) (+ a status flag) per trajectory."""
+        nn, nd = self.n_nodes, self.nd
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if mode == "sumsq":
+            if self.pg_ls is None:
+                self.pg_ls = PeerGather(self.h, self.spec_ls, self.n_traj, self.device, self.group, self.root)
+                self._bad_view = torch.as_tensor(_DevArray(self.pg_ls.ptr["bad"], (self.n_traj,), "<i4"), device=self.device)
+            pg = self.pg_ls
+            u0, u1 = pg.slab()
+            pg.begin()
+            if u1 > u0:
+                cnt, spu = u1 - u0, nn - 1
+                if self._ls_scratch is None or self._ls_scratch[0].shape[0] < cnt:
+                    self._ls_scratch = (torch.empty((cnt, spu, nd), dtype=torch.float64, device=self.device),
+                                        torch.empty((cnt, spu), dtype=torch.int32, device=self.device))
+                d, st = self._ls_scratch
+                self.h.indirect_dev(params, cnt * spu, nn, nd, self.XC[u0].data_ptr(), self.t[u0].data_ptr(), None, None,
+                                    self.tl[u0:].data_ptr(), self.rho[u0:].data_ptr(), d.data_ptr(), st.data_ptr(), None, None)
+                self.h.sumsq_dev(d.data_ptr(), cnt, spu * nd, pg.out_ptr("sumsq", u0))
+                with torch.cuda.stream(self.stream):
+                    self._bad_view[u0:u1].copy_(st[:cnt].amax(dim=1))
+            pg.signal()
+            if wait:
+                pg.wait_all()
+            return pg.tensors() if pg.rank == pg.root else None
+        pg = self.pg
+        u0, u1 = pg.slab()
+        pg.begin()
+        if u1 > u0:
+            self.h.indirect_dev(params, (u1 - u0) * (nn - 1), nn, nd, self.XC[u0].data_ptr(), self.t[u0].data_ptr(), None, None,
+                                self.tl[u0:].data_ptr(), self.rho[u0:].data_ptr(), pg.out_ptr("defect", u0), pg.out_ptr("status", u0),
+                                pg.out_ptr("nsteps", u0), pg.out_ptr("phi", u0) if jac else None)
+        pg.signal()
+        if wait:
+            pg.wait_all()
+        return pg.tensors() if pg.rank == pg.root else None
+
+
+class PeerDirect(ShardedDirect):
+    def __init__(self, handle, n_seg, nstate, device, group=None, nsteps=10, root=0):
+        super().__init__(handle, n_seg, nstate, device, group, n_chunks=1, nsteps=nsteps)
+        self.pg = PeerGather(handle, self.spec_jac, n_seg, device, group, root)
+
+    def run(self, params, jac=True, wait=True):
+        pg, ns, i = self.pg, self.ns, self.inp
+        u0, u1 = pg.slab()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        pg.begin()
+        if u1 > u0:
+            self.h.direct_dev(params, u1 - u0, 0, ns, self.nsteps, i["Xa"][u0:].data_ptr(), i["Xb"][u0:].data_ptr(), i["ua"][u0:].data_ptr(),
+                              i["ub"][u0:].data_ptr(), i["ta"][u0:].data_ptr(), i["tb"][u0:].data_ptr(), pg.out_ptr("defect", u0),
+                              pg.out_ptr("errors", u0), pg.out_ptr("status", u0), pg.out_ptr("jac", u0) if jac else None)
+        pg.signal()
+        if wait:
+            pg.wait_all()
+        return pg.tensors() if pg.rank == pg.root else None
