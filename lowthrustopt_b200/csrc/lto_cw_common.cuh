@@ -38,6 +38,19 @@ __device__ __forceinline__ void bulk_store(void* gptr, unsigned smem_addr, unsig
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// try_wait with a suspend-time hint: the hardware parks the thread instead of spinning on the issue port
+__device__ __forceinline__ void mbar_wait_parked(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAITP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONEP;\n"
+        "bra LAB_WAITP;\n"
+        "DONEP:\n"
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+
 // ---- Branch-free 1/sqrt(x) and 1/x for normal positive x: hardware seed (MUFU.RSQ64H /
 // MUFU.RCP64H, ~2^-20) + one cubically convergent correction (error ~2^-60 before
 // rounding).  No slow-path subroutine: keeps a state warp's dependent chain and its

@@ -25,9 +25,9 @@
 //                 hidden behind the column work of the other tile.
 // Step control uses the joint norm over x and Phi (LTO_NORM_STATE_SENS, the ForwardDiff
 // semantics) or x alone: each column thread returns its partial sum of squared scaled
-// errors and the state warp decides.  Between visits a column's current value lives in a
-// shared-memory stash and its candidate in an L2-resident scratch, so rejecting a step
-// costs nothing extra.
+// errors and the state warp decides.  Between visits a column's candidate lives in a
+// shared-memory stash and its current (last accepted) value in an L2-resident scratch, so an
+// accepted step never waits on L2 and a rejected one costs one L2 read.
 // The initial step is Hairer's estimate over the state components (the generic kernel
 // and the CPU checker take it over x and Phi): the two paths may choose different step
 // sequences and agree to the integration tolerance, not to rounding.
@@ -57,7 +57,7 @@ constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);      // st
 constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
 constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);        // current columns, both halves
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
-constexpr size_t XN_BYTES = (size_t)ND * TS * sizeof(double);              // the state's candidate
+constexpr size_t XN_BYTES = (size_t)2 * ND * TS * sizeof(double);          // the state x and its candidate (double buffer; keeps 24 registers free in the state warps)
 constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
 constexpr size_t BAR_BYTES = 128;                                          // 13 stage barriers, done, tile_done
 constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
@@ -233,6 +233,7 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
     const double w2 = 2.0 * a.c.omega;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     double* cand_base = a.scratch + (size_t)blockIdx.x * (SCRATCH_BYTES_PER_CTA / sizeof(double)) + ct;
+    const bool wide = (reinterpret_cast<uintptr_t>(a.phi) & 31u) == 0;
     unsigned alive = (1u << NTILE) - 1u;
     unsigned visit = 0;
     long long c_wait = 0, c_work = 0, n_work = 0;
@@ -243,7 +244,7 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
             if (!(alive & (1u << t))) continue;
             const TileSmem S = tile_smem(smem, t);
             const long long c0 = clock64();
-            mbar_wait(S.bar_full, visit & 1);                           // header + stage 0
+            mbar_wait_parked(S.bar_full, visit & 1);                    // header + stage 0
             if (STAGE_PIPE && !*S.tile_done) mbar_wait(S.bar_full + 8 * START_STAGE, visit & 1);
             const long long c1 = clock64();
             c_wait += c1 - c0;
@@ -255,28 +256,39 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 const double h = S.hval[slot];
                 double* sc = S.cur + (size_t)hf * ND * NCT + ct;
                 double* sn = cand_base + (size_t)(t * 2 + hf) * ND * NCT;
+                // The CANDIDATE of the previous attempt lives in shared memory (sc), the CURRENT column (last accepted value) in
+                // the L2-resident scratch (sn): an accepted step -- 99.7 % of them -- reads shared memory and refreshes the
+                // scratch with fire-and-forget stores; only a rejected step pays an L2 read.
                 double p[ND];
                 if (hc.x & F_ACCEPT) {
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) { p[i] = __ldcg(sn + i * NCT); sc[i * NCT] = p[i]; }
+                    for (int i = 0; i < ND; ++i) { p[i] = sc[i * NCT]; __stcg(sn + i * NCT, p[i]); }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) p[i] = sc[i * NCT];
+                    for (int i = 0; i < ND; ++i) p[i] = __ldcg(sn + i * NCT);
                 }
                 if (hc.x & F_STORE) {                                  // column `col` of ForwardDiff.jacobian(f, x0) (:121)
+                    // three 32-byte stores per column (96 contiguous bytes, 32-byte aligned): wide enough to travel as full
+                    // packets when `phi` is NVLink peer memory of the solver rank
                     double* out = a.phi + (long long)hc.y * (ND * ND) + col * ND;
+                    if (wide) {
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) out[i] = p[i];
+                        for (int i = 0; i < ND; i += 4)
+                            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(out + i), "d"(p[i]), "d"(p[i + 1]), "d"(p[i + 2]), "d"(p[i + 3]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < ND; ++i) out[i] = p[i];
+                    }
                 }
                 if (hc.x & F_RESET) {
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; sc[i * NCT] = p[i]; }
+                    for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; __stcg(sn + i * NCT, p[i]); }
                 }
                 if (done) continue;
                 double pn[ND];
                 const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, S.bar_full, visit & 1, atol, rtol, pn);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) __stcg(sn + i * NCT, pn[i]);
+                for (int i = 0; i < ND; ++i) sc[i * NCT] = pn[i];
                 if (JOINT) S.errp[col * TS + slot] = es;
             }
             if (done) alive &= ~(1u << t);
@@ -380,15 +392,21 @@ __device__ __forceinline__ void sc_eval(const double (&R)[3], const double (&V)[
 // One out-of-line copy of the right-hand side serves all 13 stages: the state warp's code
 // must stay small, or its instruction stream evicts the column warps' loop body from the
 // instruction cache (ncu: stall_no_inst was the top stall of BOTH warp kinds).
-__device__ __noinline__ void sc_eval_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
-                                          double m0, double m1, double m2, const SCConst* c, double aL, double rho_inv, double rq,
-                                          double2* w, double* out) {
+struct Out9 { double v[9]; };
+// Arguments and results travel in registers (the device ABI returns this struct in registers): no local-memory round trip
+// on the state warp's dependent chain.
+__device__ __noinline__ Out9 sc_eval_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
+                                          double m0, double m1, double m2, double mu, double mu1, double omega, double pexp, double aL,
+                                          double rho_inv, double rq, double2* w) {
     const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, v2}, L[3] = {l0, l1, l2}, M[3] = {m0, m1, m2};
+    SCConst c; c.mu = mu; c.m1 = mu1; c.omega = omega; c.p = pexp;
     LawConst lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rho_inv_quarter_aL = rq;
     double kv[3], kl[3], km[3];
-    sc_eval<true>(R, V, L, M, *c, lw, kv, kl, km, w);
+    sc_eval<true>(R, V, L, M, c, lw, kv, kl, km, w);
+    Out9 o;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { out[q] = kv[q]; out[3 + q] = kl[q]; out[6 + q] = km[q]; }
+    for (int q = 0; q < 3; ++q) { o.v[q] = kv[q]; o.v[3 + q] = kl[q]; o.v[6 + q] = km[q]; }
+    return o;
 }
 
 template <int J>
@@ -396,12 +414,21 @@ __device__ __forceinline__ void state_stage(KStore& K, const double (&x)[ND], do
                                             double2* __restrict__ rec, unsigned bar) {
     double R[3], V[3], L[3], M[3];
     stage_input<J>(K, x, h, h2, R, V, L, M);
-    double out[9];
-    sc_eval_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], &c, lw.aL, lw.rho_inv, lw.rho_inv_quarter_aL,
-                 rec + J * NC2 * TS, out);
+    const Out9 o = sc_eval_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], c.mu, c.m1, c.omega, c.p, lw.aL, lw.rho_inv,
+                                lw.rho_inv_quarter_aL, rec + J * NC2 * TS);
     if (STAGE_PIPE && J > 0) mbar_arrive(bar + 8 * J);     // stage J's record is published (stage 0 goes out with the header)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { K.kv[J][q] = out[q]; K.kl[J][q] = out[3 + q]; K.km[J][q] = out[6 + q]; }
+    for (int q = 0; q < 3; ++q) { K.kv[J][q] = o.v[q]; K.kl[J][q] = o.v[3 + q]; K.km[J][q] = o.v[6 + q]; }
+}
+
+// state warps keep x in shared memory (stride TS between components): loaded per stage, live only through the combination
+template <int J>
+__device__ __forceinline__ void state_stage_s(KStore& K, const double* __restrict__ xs, double h, double h2, const SCConst& c, const LawConst& lw,
+                                              double2* __restrict__ rec, unsigned bar) {
+    double x[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
+    state_stage<J>(K, x, h, h2, c, lw, rec, bar);
 }
 
 __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
@@ -418,9 +445,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
-    double x[ND];
+    int xi = 0;                                                           // which half of the double buffer holds x
+    double* const xbuf = S.xn + slot;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) x[i] = 0.0;
+    for (int i = 0; i < ND; ++i) { xbuf[i * TS] = 0.0; xbuf[(ND + i) * TS] = 0.0; }
     double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
     LawConst lw; lw.aL = 0.0; lw.rho_inv = 1.0; lw.rho_inv_quarter_aL = 0.0;
     long long seg = -1, ia = 0;
@@ -436,7 +464,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         const long long c0 = clock64();
         long long c1 = c0;
         if (have) {
-            mbar_wait(S.bar_done, (visit - 1) & 1);
+            mbar_wait_parked(S.bar_done, (visit - 1) & 1);
             c1 = clock64();
             c_wait += c1 - c0;
             if (active) {
@@ -452,8 +480,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                     q = fmin(5.0, fmax(0.2, q));
                     if (eest <= 1.0) {
                         ++na; flags |= F_ACCEPT;
-#pragma unroll
-                        for (int i = 0; i < ND; ++i) x[i] = S.xn[i * TS + slot];
+                        xi ^= 1;                                          // the candidate becomes x
                         if (last) { tcur = tf; finished = true; }
                         else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
                     } else {
@@ -470,11 +497,14 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         if (active && finished) {
             // ---- defect = x(t1) - XC_all[:, i+1] (multiShoot_CRTBP_indirect.jl:82)
             bool nan = false;
+            const double* xs = xbuf + xi * ND * TS;
 #pragma unroll
-            for (int i = 0; i < ND; ++i) nan |= !(x[i] == x[i]);
+            for (int i = 0; i < ND; ++i) {
+                const double xv = xs[i * TS];
+                nan |= !(xv == xv);
+                a.defect[seg * ND + i] = a.x_target ? xv - a.x_target[ia * ND + i] : xv;
+            }
             if (nan && status == 0) status = LTO_ST_NAN;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) a.defect[seg * ND + i] = a.x_target ? x[i] - a.x_target[ia * ND + i] : x[i];
             if (a.status) a.status[seg] = status;
             if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
             flags |= F_STORE; store_seg = (int)seg;
@@ -487,7 +517,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                 seg = idx; ia = lto_node_a(seg, a.npt);
                 const long long it = lto_traj_of(seg, a.npt);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) x[i] = a.x0[ia * ND + i];
+                for (int i = 0; i < ND; ++i) xbuf[(xi * ND + i) * TS] = a.x0[ia * ND + i];
                 tcur = a.t0[ia]; tf = a.t1[ia];
                 if (!(tcur < tf)) tf = tcur;                              // empty span: one zero-length step, Phi = I
                 span = tf - tcur;
@@ -512,10 +542,13 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         const long long c2 = clock64();
         c_pre += c2 - c1;
         KStore K;
-        state_stage<0>(K, x, 0.0, 0.0, a.c, lw, rec, S.bar_full);
+        const double* xs = xbuf + xi * ND * TS;
+        state_stage_s<0>(K, xs, 0.0, 0.0, a.c, lw, rec, S.bar_full);
         if (__any_sync(fullmask, fresh)) {
             // Hairer-Norsett-Wanner initial step over the state components (drive_rk8 in lto_prop_generic.cuh)
-            double f0[ND], y1[ND];
+            double f0[ND], y1[ND], x[ND];
+#pragma unroll
+            for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
 #pragma unroll
             for (int q = 0; q < 3; ++q) { f0[q] = x[3 + q]; f0[3 + q] = K.kv[0][q]; f0[6 + q] = K.kl[0][q]; f0[9 + q] = K.km[0][q]; }
             const double d0 = rms12(x, x, atol, rtol), d1 = rms12(f0, x, atol, rtol);
@@ -541,15 +574,18 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg);
         if (STAGE_PIPE) mbar_arrive(S.bar_full);                         // header + stage 0
         const double h2 = h * h;
-        state_stage<1>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<2>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<3>(K, x, h, h2, a.c, lw, rec, S.bar_full);
-        state_stage<4>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<5>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<6>(K, x, h, h2, a.c, lw, rec, S.bar_full);
-        state_stage<7>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<8>(K, x, h, h2, a.c, lw, rec, S.bar_full);  state_stage<9>(K, x, h, h2, a.c, lw, rec, S.bar_full);
-        state_stage<10>(K, x, h, h2, a.c, lw, rec, S.bar_full); state_stage<11>(K, x, h, h2, a.c, lw, rec, S.bar_full); state_stage<12>(K, x, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage_s<1>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<2>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<3>(K, xs, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage_s<4>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<5>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<6>(K, xs, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage_s<7>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<8>(K, xs, h, h2, a.c, lw, rec, S.bar_full);  state_stage_s<9>(K, xs, h, h2, a.c, lw, rec, S.bar_full);
+        state_stage_s<10>(K, xs, h, h2, a.c, lw, rec, S.bar_full); state_stage_s<11>(K, xs, h, h2, a.c, lw, rec, S.bar_full); state_stage_s<12>(K, xs, h, h2, a.c, lw, rec, S.bar_full);
         {
-            double xn[ND];
-            esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+            double x[ND], xn[ND];
 #pragma unroll
-            for (int i = 0; i < ND; ++i) S.xn[i * TS + slot] = xn[i];
+            for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
+            esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+            double* xc = xbuf + (xi ^ 1) * ND * TS;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
         }
         if (!STAGE_PIPE) mbar_arrive(S.bar_full);                        // the whole attempt's record
         c_work += clock64() - c2;
@@ -725,7 +761,7 @@ __global__ void __launch_bounds__(K4I_THREADS, 2) k_indirect_state(IndirectArgs 
 
 }  // namespace icw
 
-size_t indirect_cw_scratch_bytes(int n_sm) { return (size_t)n_sm * icw::SCRATCH_BYTES_PER_CTA; }
+size_t indirect_cwv2_scratch_bytes(int n_sm) { return (size_t)n_sm * icw::SCRATCH_BYTES_PER_CTA; }
 
 template <bool JOINT>
 static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
