@@ -624,14 +624,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
 #ifndef LTO_K4I_INLINE
 #define LTO_K4I_INLINE 0
 #endif
-__device__ __noinline__ void sc_eval_state_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
-                                                double m0, double m1, double m2, const SCConst* c, double aL, double rho_inv, double rq, double* out) {
+__device__ __noinline__ Out9 sc_eval_state_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
+                                                double m0, double m1, double m2, double mu, double mu1, double omega, double pexp, double aL,
+                                                double rho_inv, double rq) {
     const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, v2}, L[3] = {l0, l1, l2}, M[3] = {m0, m1, m2};
+    SCConst c; c.mu = mu; c.m1 = mu1; c.omega = omega; c.p = pexp;
     LawConst lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rho_inv_quarter_aL = rq;
     double kv[3], kl[3], km[3];
-    sc_eval<false>(R, V, L, M, *c, lw, kv, kl, km, nullptr);
+    sc_eval<false>(R, V, L, M, c, lw, kv, kl, km, nullptr);
+    Out9 o;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { out[q] = kv[q]; out[3 + q] = kl[q]; out[6 + q] = km[q]; }
+    for (int q = 0; q < 3; ++q) { o.v[q] = kv[q]; o.v[3 + q] = kl[q]; o.v[6 + q] = km[q]; }
+    return o;
 }
 
 template <int J>
@@ -644,10 +648,10 @@ __device__ __forceinline__ void state_only_stage(KStore& K, const double (&x)[ND
 #pragma unroll
     for (int q = 0; q < 3; ++q) { K.kv[J][q] = kv[q]; K.kl[J][q] = kl[q]; K.km[J][q] = km[q]; }
 #else
-    double out[9];
-    sc_eval_state_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], &c, lw.aL, lw.rho_inv, lw.rho_inv_quarter_aL, out);
+    const Out9 o = sc_eval_state_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], c.mu, c.m1, c.omega, c.p, lw.aL,
+                                      lw.rho_inv, lw.rho_inv_quarter_aL);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { K.kv[J][q] = out[q]; K.kl[J][q] = out[3 + q]; K.km[J][q] = out[6 + q]; }
+    for (int q = 0; q < 3; ++q) { K.kv[J][q] = o.v[q]; K.kl[J][q] = o.v[3 + q]; K.km[J][q] = o.v[6 + q]; }
 #endif
 }
 
