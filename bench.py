@@ -622,6 +622,10 @@ def run_ours(args):
     # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
     per_gpu_ms = float(np.mean(times))
     roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl)
+    if wl.endswith("adaptive"):
+        # the direct entry points do not return step counts, so the algorithmic FLOPs of an ADAPTIVE pass are not known here
+        roof["achieved"] = None; roof["frac"] = None; roof["flops_per_unit"] = None
+        roof["note"] = "ode78 controller: steps per leg vary (4+ at tol 1e-13 vs the fixed grid's 9); no FLOP count is claimed for this workload"
     if attempted is not None:
         roof["attempted_steps_per_segment"] = attempted
         roof["accepted_steps_per_segment"] = accepted

@@ -49,7 +49,8 @@ struct Cfg {
     static constexpr size_t OUT_TILE_BYTES = (size_t)16 * NS * NV * sizeof(double);      // one tile's Jacobian blocks, in the output's own layout
     static constexpr size_t OUT_BYTES = (size_t)NTILE * OUT_TILE_BYTES;
     static constexpr size_t BAR_OFF = REC_BYTES + OUT_BYTES;
-    static constexpr size_t SMEM = BAR_OFF + (size_t)NTILE * NSLOT * 2 * sizeof(unsigned long long);
+    static constexpr size_t FLAG_OFF = BAR_OFF + (size_t)NTILE * NSLOT * 2 * sizeof(unsigned long long);
+    static constexpr size_t SMEM = FLAG_OFF + (size_t)NTILE * NSLOT * sizeof(int);      // ADAPTIVE: "last step of this tile" per ring slot
 };
 
 using namespace cwc;
@@ -59,8 +60,8 @@ using namespace cwc;
 // linearisations of this step into `rec` (lane-strided) and accumulates maxErr.
 // ---------------------------------------------------------------------------
 template <int NS, bool PUB = true>
-__device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m, const double (&u)[3], double omega,
-                                       double mdot, double h, const EPConst& c, double* __restrict__ rec, double& maxErr) {
+__device__ __forceinline__ double x_step(double (&r)[3], double (&v)[3], double& m, const double (&u)[3], double omega,
+                                         double mdot, double h, const EPConst& c, double* __restrict__ rec, double& maxErr) {
     constexpr int SVAL = Cfg<NS>::SVAL;
     const double h2 = h * h;
     const double w2 = 2.0 * omega;
@@ -137,6 +138,7 @@ __device__ __forceinline__ void x_step(double (&r)[3], double (&v)[3], double& m
     if (NS == 7) m = fma(h, mdot, m);
     delta *= fabs(h * lto_tab::ERRC);                       // ode.jl:940-943 (mass row is identically 0)
     maxErr = fmax(maxErr, delta);                           // ode.jl:946-948
+    return delta;
 }
 
 // ---------------------------------------------------------------------------
@@ -348,7 +350,173 @@ __device__ __forceinline__ void state_warp(const DirectArgs& a, long long n_tile
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// K2: the same layout with the reference's ode78 controller (GeneralCode/ode.jl:477-534) in the state warps, norms over
+// the state (LTO_NORM_STATE): the step sequence of a leg depends on x alone, so the state warp still runs ahead of the
+// columns.  It retries rejected attempts by itself and publishes ACCEPTED steps only -- the column warps never see a
+// rejection.  Legs of a tile take different numbers of steps: a finished leg publishes zero-length steps (h = 0, zero
+// linearisation: the column is left unchanged) until the slowest leg of the tile is through; a per-slot flag tells the
+// column warps which step is the tile's last.
+// ---------------------------------------------------------------------------
 template <int NS>
+__device__ __forceinline__ void state_warp_adapt(const DirectArgs& a, long long n_tiles, int t, int lane, double* recs, unsigned bars, volatile int* lastf) {
+    typedef Cfg<NS> C;
+    const int back = lane & 1;
+    const double omega = back ? -1.0 : 1.0;
+    const unsigned fullmask = 0xffffffffu;
+    double r[3], v[3], m = a.c.default_mass, u[3], bm[3] = {0.0, 0.0, 0.0}, mdot = 0.0, dummy = 0.0;
+    unsigned g = 0;
+    for (long long pair = blockIdx.x; pair * NTILE < n_tiles; pair += gridDim.x) {
+        const long long seg = (pair * NTILE + t) * 16 + (lane >> 1);
+        const long long sc = seg < a.n_seg ? seg : a.n_seg - 1;
+        const long long ia = lto_node_a(sc, a.npt);
+        const double* X = (back ? a.Xb : a.Xa) + ia * NS;
+        const double* U = (back ? a.ub : a.ua) + ia * 3;
+        r[0] = X[0]; r[1] = X[1]; r[2] = X[2];
+        v[0] = X[3]; v[1] = X[4]; v[2] = X[5];
+        if (back) { v[0] = -v[0]; v[1] = -v[1]; v[2] = -v[2]; }
+        if (NS == 7) m = X[6];
+        u[0] = U[0]; u[1] = U[1]; u[2] = U[2];
+        const double ta = a.ta[ia], tb = a.tb[ia];
+        const double t0 = ta, tfinal = ta + (tb - ta) / 2.0;
+        const double un = sqrt(fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2])));
+        mdot = -omega * un * a.c.cmdot;
+        if (NS == 7) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const double uh = (un > 0.0) ? u[q] / un : 1.0; bm[q] = -omega * a.c.cmdot * uh; }
+        }
+        // ---- drive_ode78 (lto_prop_generic.cuh) / ode78 (ode.jl:477-534)
+        const double hmax = (tfinal - t0) / 2.5, hmin = (tfinal - t0) / 1e7;
+        double tt = t0, h = (tfinal - t0) / 50.0;
+        int status = 0, nt = 0;
+        bool done = !((tt < tfinal) && (h >= hmin));
+        while (true) {
+            const unsigned slot = g & (NSLOT - 1), use = g / NSLOT;
+            double* rec = recs + (size_t)(t * NSLOT + slot) * C::STEP_DOUBLES * 32 + lane;
+            const unsigned full = bars + (unsigned)((t * NSLOT + slot) * 16), empty = full + 8;
+            if (use > 0) mbar_wait(empty, (use - 1) & 1);
+            if (NS == 7) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) rec[(C::OFF_BM + q) * 32] = bm[q];
+            }
+            bool pending = !done;
+            if (done) {                                                      // zero-length step: leaves the column unchanged
+#pragma unroll
+                for (int j = 0; j < 13 * C::SVAL; ++j) rec[j * 32] = 0.0;
+                rec[C::OFF_H * 32] = 0.0;
+            }
+            while (__any_sync(fullmask, pending)) {
+                if (pending) {
+                    if (tt + h > tfinal) h = tfinal - tt;
+                    if (nt >= a.cfg.max_attempts) { status = LTO_ST_MAXSTEPS; done = true; pending = false; }
+                }
+                if (pending) {
+                    ++nt;
+                    double r2[3] = {r[0], r[1], r[2]}, v2[3] = {v[0], v[1], v[2]}, m2 = m;
+                    const double xn = fmax(fmax(fmax(fabs(r[0]), fabs(r[1])), fmax(fabs(r[2]), fabs(v[0]))), fmax(fmax(fabs(v[1]), fabs(v[2])), NS == 7 ? fabs(m) : 0.0));
+                    double delta = x_step<NS>(r2, v2, m2, u, omega, mdot, h, a.c, rec, dummy);
+                    if (!(delta == delta)) { status = LTO_ST_NAN; done = true; pending = false; }
+                    else {
+                        const double tau = a.cfg.tol * fmax(xn, 1.0);
+                        if (delta <= tau) {                                  // accepted: this record goes out
+                            tt += h;
+                            r[0] = r2[0]; r[1] = r2[1]; r[2] = r2[2]; v[0] = v2[0]; v[1] = v2[1]; v[2] = v2[2]; m = m2;
+                            pending = false;
+                        }
+                        if (delta == 0.0) delta = 1e-16;
+                        h = fmin(hmax, 0.8 * h * pow(tau / delta, 0.125));
+                        if (!((tt < tfinal) && (h >= hmin))) { done = true; if (pending) { status = LTO_ST_HMIN; pending = false; } }
+                    }
+                }
+            }
+            if (status != 0) {                                               // a failed leg must not hand a rejected attempt to the columns
+#pragma unroll
+                for (int j = 0; j < 13 * C::SVAL; ++j) rec[j * 32] = 0.0;
+                rec[C::OFF_H * 32] = 0.0;
+            }
+            const bool all_done = __all_sync(fullmask, done);
+            if (lane == 0) lastf[t * NSLOT + slot] = all_done ? 1 : 0;
+            mbar_arrive(full);
+            ++g;
+            if (all_done) break;
+        }
+        if (status == 0 && tt < tfinal) status = LTO_ST_HMIN;
+        double xe[NS];
+        xe[0] = r[0]; xe[1] = r[1]; xe[2] = r[2];
+        xe[3] = back ? -v[0] : v[0]; xe[4] = back ? -v[1] : v[1]; xe[5] = back ? -v[2] : v[2];
+        if (NS == 7) xe[6] = m;
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const double other = __shfl_xor_sync(fullmask, xe[q], 1);
+            const double d = xe[q] - other;
+            bad |= !(d == d);
+            if (!back && seg < a.n_seg) a.defect[seg * NS + q] = d;
+        }
+        const int st_o = __shfl_xor_sync(fullmask, status, 1);
+        if (!back && seg < a.n_seg) {
+            if (a.errors) a.errors[seg] = 0.0;
+            if (a.status) a.status[seg] = status ? status : (st_o ? st_o : (bad ? LTO_ST_NAN : LTO_OK));
+        }
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void column_warp_adapt(const DirectArgs& a, long long n_tiles, int col, int lane, double* recs, double* outs, unsigned bars,
+                                                  volatile int* lastf) {
+    typedef Cfg<NS> C;
+    const double omega = (lane & 1) ? -1.0 : 1.0;
+    const double kom6 = a.c.kthr / a.c.default_mass;
+    const int gc = col - NS;
+    const double ec[3] = {gc == 0 ? 1.0 : 0.0, gc == 1 ? 1.0 : 0.0, gc == 2 ? 1.0 : 0.0};
+    ColState cs[NTILE];
+    unsigned g[NTILE];
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) g[t] = 0;
+    for (long long pair = blockIdx.x; pair * NTILE < n_tiles; pair += gridDim.x) {
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) col_init<NS>(cs[t], col);
+        unsigned alive = (1u << NTILE) - 1u, first = alive;
+        while (alive) {
+#pragma unroll
+            for (int t = 0; t < NTILE; ++t) {
+                if (!(alive & (1u << t))) continue;
+                const unsigned slot = g[t] & (NSLOT - 1), par = (g[t] / NSLOT) & 1;
+                const double* rec = recs + (size_t)(t * NSLOT + slot) * C::STEP_DOUBLES * 32 + lane;
+                const unsigned full = bars + (unsigned)((t * NSLOT + slot) * 16), empty = full + 8;
+                mbar_wait(full, par);
+                if (NS == 7 && (first & (1u << t)) && gc >= 0) cs[t].bm = rec[(C::OFF_BM + gc) * 32];
+                first &= ~(1u << t);
+                const bool last = lastf[t * NSLOT + slot] != 0;
+                col_step<NS>(cs[t].sr, cs[t].sv, cs[t].sm, cs[t].bm, ec, omega, kom6, rec);
+                mbar_arrive(empty);
+                ++g[t];
+                if (last) alive &= ~(1u << t);
+            }
+        }
+        // ---- both tiles of the pair are through: stage and bulk-store their Jacobian blocks (as in column_warp)
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t) {
+            const long long tile = pair * NTILE + t;
+            const long long seg0 = tile * 16;
+            double* stage = outs + (size_t)t * (C::OUT_TILE_BYTES / sizeof(double));
+            const bool leader = (col == 0 && lane == 0);
+            if (leader) bulk_store_wait_read();
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
+            col_store<NS>(stage, cs[t], col, lane);
+            fence_proxy_async();
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
+            if (leader && seg0 < a.n_seg) {
+                const long long nseg = (a.n_seg - seg0 < 16) ? (a.n_seg - seg0) : 16;
+                bulk_store(a.jac + seg0 * (long long)(NS * C::NV), smem_u32(stage), (unsigned)(nseg * NS * C::NV * sizeof(double)));
+            }
+        }
+    }
+    if (col == 0 && lane == 0) bulk_store_wait_all();
+}
+
+template <int NS, bool ADAPT>
 __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a, long long n_tiles) {
     typedef Cfg<NS> C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -364,11 +532,14 @@ __global__ void __launch_bounds__(Cfg<NS>::NTHREADS, 1) k_direct_cw(DirectArgs a
         }
     }
     __syncthreads();
+    volatile int* lastf = reinterpret_cast<volatile int*>(smem_raw + C::FLAG_OFF);
     if (warp >= XW0 && warp < XW0 + NTILE) {
-        state_warp<NS>(a, n_tiles, warp - XW0, lane, recs, bars);
+        if (ADAPT) state_warp_adapt<NS>(a, n_tiles, warp - XW0, lane, recs, bars, lastf);
+        else state_warp<NS>(a, n_tiles, warp - XW0, lane, recs, bars);
     } else {
         const int col = warp < XW0 ? warp : warp - NTILE;
-        column_warp<NS>(a, n_tiles, col, lane, recs, outs, bars);
+        if (ADAPT) column_warp_adapt<NS>(a, n_tiles, col, lane, recs, outs, bars, lastf);
+        else column_warp<NS>(a, n_tiles, col, lane, recs, outs, bars);
     }
 }
 
@@ -436,7 +607,7 @@ static cudaError_t launch_state(const DirectArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int NS>
+template <int NS, bool ADAPT>
 static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
     typedef cw::Cfg<NS> C;
     // per device: a single process may drive several GPUs (lto_init_devices)
@@ -447,7 +618,7 @@ static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_dev[dev]) {
         cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(cw::k_direct_cw<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        e = cudaFuncSetAttribute(cw::k_direct_cw<NS, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
         attr_dev[dev] = true;
     }
@@ -455,21 +626,26 @@ static cudaError_t launch_cw(const DirectArgs& a, cudaStream_t st) {
     const long long n_tiles = (a.n_seg + 15) / 16;
     const long long n_pairs = (n_tiles + cw::NTILE - 1) / cw::NTILE;
     const int grid = (int)std::min<long long>(n_pairs, (long long)n_sm);
-    cw::k_direct_cw<NS><<<grid, C::NTHREADS, C::SMEM, st>>>(a, n_tiles);
+    cw::k_direct_cw<NS, ADAPT><<<grid, C::NTHREADS, C::SMEM, st>>>(a, n_tiles);
     return cudaGetLastError();
 }
 
 cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
-    if (a.cfg.mode != 0 || a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
+    if (a.n_seg <= 0 || a.n_seg > (1ll << 34)) return cudaErrorNotSupported;
+    if (a.cfg.mode != 0 && (a.cfg.err_norm != 0 || a.jac == nullptr)) return cudaErrorNotSupported;   // K2 covers the state-norm controller with Jacobian
     if (a.jac != nullptr && (reinterpret_cast<uintptr_t>(a.jac) & 15u) != 0) return cudaErrorNotSupported;   // bulk stores need 16-byte alignment
     cudaError_t e;
     if (a.jac == nullptr) {
         if (nstate == 7) e = launch_state<7>(a, st);
         else if (nstate == 6) e = launch_state<6>(a, st);
         else return cudaErrorNotSupported;
-    } else if (nstate == 7) e = launch_cw<7>(a, st);
-    else if (nstate == 6) e = launch_cw<6>(a, st);
+    } else if (a.cfg.mode != 0) {
+        if (nstate == 7) e = launch_cw<7, true>(a, st);
+        else if (nstate == 6) e = launch_cw<6, true>(a, st);
+        else return cudaErrorNotSupported;
+    } else if (nstate == 7) e = launch_cw<7, false>(a, st);
+    else if (nstate == 6) e = launch_cw<6, false>(a, st);
     else return cudaErrorNotSupported;
     if (e == cudaSuccess) *n_launch = 1;
     return e;
