@@ -179,6 +179,39 @@ int lto_sync(lto_handle* h);   /* cudaStreamSynchronize(lto_stream(h)) */
  * per trial trajectory, so that a batched line search returns one double per trial instead of every defect. */
 int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_len, double* out);
 
+/* ---- Newton update and batched solver of the indirect method (device-side) --------------
+ * lto_indirect_newton: optimizeTraj_OLS's linear solve, src/multiShoot_CRTBP_indirect.jl:149-183,
+ *     xc_update = -sparse(Jac_full) \ defect_vec
+ * for n_traj trajectories of n_nodes nodes (12-dim: the reference's solver hard-codes the 12-dim RHS, :258), directly from
+ * the Phi_i blocks and defects of lto_indirect_defect_jac_traj -- Jac_full (:127-142) is never formed.  The emptied columns
+ * (first / last node's states :141-142; with flag_adjointsOnly every node's states :169-178) get a zero update, as
+ * SuiteSparseQR's basic solution does.
+ *   phi        per segment 12 x 12 column-major (n_traj*(n_nodes-1) blocks), 16-byte aligned
+ *   defect     12 x (n_nodes-1) per trajectory
+ *   xc_update  12 x n_nodes per trajectory (what optimizeTraj_OLS reshapes at :185)
+ *   status     n_traj, LTO_ST_OK / LTO_ST_NAN (singular or non-finite system); may be NULL
+ * The _dev form takes device pointers and only enqueues on lto_stream(h). */
+int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly,
+                        const double* phi, const double* defect, double* xc_update, int32_t* status);
+int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly,
+                            const double* phi, const double* defect, double* xc_update, int32_t* status);
+/* lto_indirect_solve_batch: multiShoot_CRTBP_indirect (src/multiShoot_CRTBP_indirect.jl:58-345) for n_traj independent
+ * trajectories at once, all arrays resident on the device between iterations: first nominal run (:274), then per
+ * iteration jacobianCalc (:290), optimizeTraj_OLS with the second-order correction (:149-218; applied per trajectory where
+ * norm(xc_update, Inf) < 1e-1), the 20-point line search from the 4th iteration on (:298-302, :221-246; all
+ * 20 x n_traj trial trajectories in one launch), the update (:304) and the defect check (:328-336).  A trajectory stops
+ * iterating exactly when the reference's loop would (er <= 1e-10, er > 1e3, NaN, or max_iter reached); the others go on.
+ *   XC_all       in/out, 12 x n_nodes per trajectory (host)
+ *   t_TU         n_nodes per trajectory
+ *   thrustLimit_traj, rho_traj: optional per-trajectory overrides of p->thrustLimit / p->rho (continuation ladders)
+ *   defect       out, 12 x (n_nodes-1) per trajectory, at the returned XC_all; may be NULL
+ *   status_flag  out, n_traj: 0 converged, 1 max_iter / abort, 2 NaN (:282-286, :333-341); may be NULL
+ *   iters        out, n_traj: iterations performed; may be NULL.   er_out: out, n_traj: final norm(defect, Inf); may be NULL */
+int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int max_iter,
+                             int flag_adjointsOnly, double* XC_all, const double* t_TU,
+                             const double* thrustLimit_traj, const double* rho_traj,
+                             double* defect, int32_t* status_flag, int32_t* iters, double* er_out);
+
 /* ---- peer memory: one process per GPU, results delivered to the solver rank without a collective --------
  * The rank that runs the Newton step allocates its full output arrays with lto_dev_alloc and exports them
  * (lto_ipc_export: a 64-byte cudaIpcMemHandle_t to send to the other processes by any means); every other rank

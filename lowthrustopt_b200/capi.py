@@ -30,6 +30,7 @@ EXPORTS = [
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
     "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_dev_alloc", "lto_dev_free", "lto_ipc_export", "lto_ipc_open", "lto_ipc_close",
     "lto_push_async", "lto_sync_copies", "lto_signal_dev", "lto_wait_dev", "lto_fp64_peak_probe", "lto_debug_profile",
+    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_solve_batch",
 ]
 
 
@@ -101,6 +102,9 @@ def lib():
         L.lto_wait_dev.argtypes = [vp, vp, C.c_uint64]
         L.lto_fp64_peak_probe.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.lto_debug_profile.argtypes = [vp, vp, ci]
+        L.lto_indirect_newton.argtypes = [vp, i64, ci, ci] + [vp] * 4
+        L.lto_indirect_newton_dev.argtypes = [vp, i64, ci, ci] + [vp] * 4
+        L.lto_indirect_solve_batch.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 8
         _lib = L
     return _lib
 
@@ -356,3 +360,41 @@ class Handle:
         self._ck(lib().lto_indirect_dev(self._h, C.addressof(params), int(n_seg), int(n_nodes), int(ndim), _ptr(x0), _ptr(t0),
                                         _ptr(t1), _ptr(x_target), _ptr(thrustLimit), _ptr(rho), _ptr(defect), _ptr(status),
                                         _ptr(nsteps_out), _ptr(phi)))
+
+    # ---- Newton update / batched solver of the indirect method (device side) ----
+    def indirect_newton(self, phi, defect, flag_adjointsOnly=False):
+        """xc_update = -sparse(Jac_full) \\ defect_vec (multiShoot_CRTBP_indirect.jl:181-182) for a batch of trajectories.
+        phi: (n_traj, n_nodes-1, 12, 12) column-major blocks as the propagation returns them ([.., col, row]);
+        defect: (n_traj, n_nodes-1, 12).  Returns (xc_update (n_traj, n_nodes, 12), status (n_traj,))."""
+        phi, defect = _f64(phi), _f64(defect)
+        if phi.ndim == 3:
+            phi, defect = phi[None], defect[None]
+        n_traj, nseg, m, m2 = phi.shape
+        if m != 12 or m2 != 12 or defect.shape != (n_traj, nseg, 12):
+            raise ValueError("phi must be (n_traj, n_nodes-1, 12, 12) and defect (n_traj, n_nodes-1, 12)")
+        upd = np.empty((n_traj, nseg + 1, 12)); status = np.empty(n_traj, dtype=np.int32)
+        self._ck(lib().lto_indirect_newton(self._h, n_traj, nseg + 1, int(bool(flag_adjointsOnly)), _ptr(phi), _ptr(defect), _ptr(upd),
+                                           _ptr(status)))
+        return upd, status
+
+    def indirect_newton_dev(self, n_traj, n_nodes, flag_adjointsOnly, phi, defect, xc_update, status=None):
+        self._ck(lib().lto_indirect_newton_dev(self._h, int(n_traj), int(n_nodes), int(bool(flag_adjointsOnly)), _ptr(phi), _ptr(defect),
+                                               _ptr(xc_update), _ptr(status)))
+
+    def indirect_solve_batch(self, XC_all, t_TU, params=None, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False):
+        """multiShoot_CRTBP_indirect (:58-345) for n_traj trajectories at once, iterated on the device.
+        XC_all: (n_traj, n_nodes, 12); t_TU: (n_traj, n_nodes).  Returns dict(XC_all, defect, status_flag, iters, er)."""
+        p = params or indirect_params()
+        XC = np.array(XC_all, dtype=np.float64, order="C"); t_TU = _f64(t_TU)
+        if XC.ndim == 2:
+            XC, t_TU = XC[None], t_TU[None]
+        n_traj, n_nodes, nd = XC.shape
+        if nd != 12:
+            raise ValueError("the reference's indirect solver is 12-dimensional (multiShoot_CRTBP_indirect.jl:258)")
+        tl = None if thrustLimit is None else _f64(thrustLimit)
+        rh = None if rho is None else _f64(rho)
+        defect = np.empty((n_traj, n_nodes - 1, nd)); flag = np.empty(n_traj, dtype=np.int32); iters = np.empty(n_traj, dtype=np.int32)
+        er = np.empty(n_traj)
+        self._ck(lib().lto_indirect_solve_batch(self._h, C.addressof(p), n_traj, n_nodes, int(max_iter), int(bool(flag_adjointsOnly)),
+                                                _ptr(XC), _ptr(t_TU), _ptr(tl), _ptr(rh), _ptr(defect), _ptr(flag), _ptr(iters), _ptr(er)))
+        return dict(XC_all=XC, defect=defect, status_flag=flag, iters=iters, er=er)

@@ -3,6 +3,7 @@
 // across the boundary, no exceptions, no CPU fallback.
 #include "../../include/lto_b200.h"
 #include "lto_internal.h"
+#include "lto_handle.h"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -14,42 +15,16 @@
 using namespace lto;
 
 static char g_err[512] = "";
-static const size_t LTO_PROF_WORDS = 8192;
-#define LTO_MAX_DEVICES 16
 
-struct lto_handle {
-    int device;
-    int n_sm;
-    cudaStream_t s_compute, s_copy;
-    cudaEvent_t ev_in, ev_t0, ev_t1;
-    cudaEvent_t ev_chunk[8];
-    void* d_in; size_t d_in_cap;
-    void* d_out; size_t d_out_cap;
-    unsigned long long* d_ctr;
-    void* d_scr; size_t d_scr_cap;
-    unsigned long long* d_prof;                 // LTO_ICW_PROF=1: per-warp cycle counters of the last indirect throughput launch
-    int64_t launches;
-    double last_ms;
-    char err[512];
-    int n_child;                                // > 0: a multi-device handle (lto_init_devices); the work is done by the children
-    lto_handle* child[LTO_MAX_DEVICES];
-};
-
-static int fail(lto_handle* h, int code, const char* fmt, ...) {
+int lto_fail(lto_handle* h, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     snprintf(g_err, sizeof g_err, "%s", buf);
     if (h) snprintf(h->err, sizeof h->err, "%s", buf);
     return code;
 }
-#define CK(h, call)                                                                                   \
-    do {                                                                                              \
-        cudaError_t e__ = (call);                                                                     \
-        if (e__ != cudaSuccess)                                                                       \
-            return fail(h, LTO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-    } while (0)
 
-static int ensure(lto_handle* h, void** p, size_t* cap, size_t need) {
+int lto_ensure(lto_handle* h, void** p, size_t* cap, size_t need) {
     if (need <= *cap) return 0;
     if (*p) { cudaError_t e = cudaFree(*p); *p = nullptr; *cap = 0; if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e)); }
     size_t want = need + need / 4 + 4096;
@@ -58,8 +33,6 @@ static int ensure(lto_handle* h, void** p, size_t* cap, size_t need) {
     *cap = want;
     return 0;
 }
-
-static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" {
 
@@ -149,6 +122,8 @@ void lto_destroy(lto_handle* h) {
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->d_scr) cudaFree(h->d_scr);
     if (h->d_prof) cudaFree(h->d_prof);
+    if (h->d_nwt) cudaFree(h->d_nwt);
+    if (h->d_slv) cudaFree(h->d_slv);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);

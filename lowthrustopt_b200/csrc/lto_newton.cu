@@ -1,0 +1,250 @@
+// lto_newton.cu -- the Newton update of the indirect solver on the device, batched over trajectories
+// (SURVEY section 8(f) row 1): optimizeTraj_OLS of src/multiShoot_CRTBP_indirect.jl:149-218, i.e.
+//
+//     xc_update = -sparse(Jac_full) \ defect_vec                                   (:181-182)
+//
+// where Jac_full is the block-bidiagonal band [Phi_i | -I] of jacobianCalc (:114-138) with the columns of
+// the first node's and the last node's states emptied (:141-142) and, with flag_adjointsOnly, the state
+// columns of nodes 1..N-1 removed (:169-178).  The reference hands that matrix to SuiteSparseQR; the
+// structurally empty columns get a zero update.  Here the same least-squares problem is solved by a
+// Householder QR that walks the band node by node (the classical sequential orthogonal factorisation of an
+// almost-block-diagonal boundary-value system), so nothing but Phi_i, defect_i and the update ever exists
+// -- no Jac_full, no 255 MB device-to-host copy per iteration, no serial sparse QR per trajectory.
+//
+//   full mode (NU = 12 unknowns per node).  The pinned end states are kept as unknowns and pinned by the
+//     six equations [I6 0] delta_1 = 0 / [I6 0] delta_N = 0: the system is square and non-singular, so this
+//     is the same solution (the pinned entries are returned as exact zeros).  Node i's panel is
+//         rows 0..5   carry   [ C_i    0   | c_i ]     (i = 1: [I6 0 | 0])
+//         rows 6..17  defects [ Phi_i  -I  | -d_i ]    (i = N: [I6 0 | 0], zero rows)
+//     12 reflections annihilate the delta_i columns: rows 0..11 = [R_i S_i | s_i] are stored, rows 12..17
+//     involve delta_{i+1} only and become the next carry.
+//   adjoints-only mode (NU = 6: the costate columns of every node).  Over-determined; after the 6
+//     reflections on delta_i the 12 remaining rows are compressed onto the 6 columns of delta_{i+1} by 6
+//     more reflections, rows 6..11 are carried, rows 12..17 are pure residual and dropped.
+//   back substitution  R_i delta_i = s_i - S_i delta_{i+1},  i = N..1.
+//
+// Mapping: ONE WARP PER TRAJECTORY.  Forward sweep: lane = panel column (25 or 13 of them), the column's 18
+// rows live in registers with compile-time indices; the Householder vector of the pivot lane is handed to the
+// other lanes through a per-warp shared-memory buffer (one __syncwarp per reflection).  The stored factor
+// rows go to a workspace in HBM (coalesced: lanes = consecutive columns of one row).  Back substitution:
+// lane = row.  The sweep is a dependent chain (latency bound, ~2-3 k cycles per node); throughput comes
+// from the 1,024 trajectories of a continuation batch running side by side (7 warps per SM).
+#include "lto_internal.h"
+#include <algorithm>
+
+namespace lto {
+namespace nwt {
+
+constexpr int ND = 12;            // the reference's indirect solver is 12-dim (multiShoot_CRTBP_indirect.jl:258, :324-325)
+constexpr int NR = 18;            // panel rows: 6 carried + 12 defect equations
+constexpr int WROW = 26;          // doubles per stored factor row (25 used; 16-byte aligned rows)
+constexpr int WARPS = 4;          // trajectories per CTA
+constexpr int VBUF = 20;          // doubles per Householder hand-off buffer (18 + gamma)
+
+__host__ __device__ constexpr size_t wbytes_per_node() { return (size_t)ND * WROW * sizeof(double); }
+
+template <int NU>
+__device__ __forceinline__ void load_rows(double (&nx)[ND], int lane, bool have, const double* __restrict__ phi_seg,
+                                          const double* __restrict__ d_seg) {
+    // rows 6..17 of the next panel: [Phi_i(:, kept) | -I(:, kept) | -d_i]
+    constexpr int C0 = ND - NU;   // first kept column of a node (0, or 6 = the costates)
+#pragma unroll
+    for (int r = 0; r < ND; ++r) nx[r] = 0.0;
+    if (!have) return;
+    if (lane < NU) {
+        const double2* p = reinterpret_cast<const double2*>(phi_seg + (C0 + lane) * ND);     // column-major block: 96 contiguous bytes
+#pragma unroll
+        for (int r = 0; r < ND; r += 2) { const double2 v = __ldg(p + r / 2); nx[r] = v.x; nx[r + 1] = v.y; }
+    } else if (lane < 2 * NU) {
+#pragma unroll
+        for (int r = 0; r < ND; ++r) nx[r] = (r == C0 + lane - NU) ? -1.0 : 0.0;
+    } else if (lane == 2 * NU) {
+#pragma unroll
+        for (int r = 0; r < ND; ++r) nx[r] = -__ldg(d_seg + r);
+    }
+}
+
+// One Householder reflection: pivot column = lane PL, pivot row PR; rows PR..17; applied to lanes > PL.
+template <int PL, int PR>
+__device__ __forceinline__ void reflect(double (&a)[NR], int lane, double* __restrict__ vb) {
+    double* v = vb + ((PL & 1) ? VBUF : 0);                       // double buffer: one __syncwarp per reflection
+    if (lane == PL) {
+        double sig = 0.0;
+#pragma unroll
+        for (int r = PR + 1; r < NR; ++r) sig = fma(a[r], a[r], sig);
+        const double nrm = sqrt(fma(a[PR], a[PR], sig));
+        const double alpha = (a[PR] >= 0.0) ? -nrm : nrm;
+        const double vk = a[PR] - alpha;
+        const double gamma = (nrm > 0.0) ? 1.0 / (alpha * vk) : 0.0;   // H y = y + v (v.y) / (alpha v_k)
+        v[PR] = vk;
+#pragma unroll
+        for (int r = PR + 1; r < NR; ++r) { v[r] = a[r]; a[r] = 0.0; }
+        v[NR] = gamma;
+        a[PR] = alpha;
+    }
+    __syncwarp();
+    if (lane > PL) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = PR; r < NR; ++r) s = fma(v[r], a[r], s);
+        s *= v[NR];
+#pragma unroll
+        for (int r = PR; r < NR; ++r) a[r] = fma(v[r], s, a[r]);
+    }
+}
+
+template <int NU, int K>
+struct Sweep {
+    static __device__ __forceinline__ void run(double (&a)[NR], int lane, double* vb) {
+        reflect<K, K>(a, lane, vb);
+        Sweep<NU, K + 1>::run(a, lane, vb);
+    }
+};
+template <int NU>
+struct Sweep<NU, NU> {
+    static __device__ __forceinline__ void run(double (&)[NR], int, double*) {}
+};
+// compression of rows NU..17 onto the next node's columns (adjoints-only mode)
+template <int NU, int K>
+struct Compress {
+    static __device__ __forceinline__ void run(double (&a)[NR], int lane, double* vb) {
+        reflect<NU + K, NU + K>(a, lane, vb);
+        Compress<NU, K + 1>::run(a, lane, vb);
+    }
+};
+template <int NU>
+struct Compress<NU, 6> {
+    static __device__ __forceinline__ void run(double (&)[NR], int, double*) {}
+};
+
+template <int NU>
+__global__ void __launch_bounds__(32 * WARPS) k_indirect_newton(const double* __restrict__ phi, const double* __restrict__ defect,
+                                                                 double* __restrict__ W, double* __restrict__ update,
+                                                                 int32_t* __restrict__ status, long long n_traj, int n_nodes) {
+    __shared__ double vbuf[WARPS][2 * VBUF];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long traj = (long long)blockIdx.x * WARPS + wid;
+    if (traj >= n_traj) return;
+    constexpr int NCOL = 2 * NU + 1;
+    const int N = n_nodes;
+    const double* phi_t = phi + traj * (long long)(N - 1) * ND * ND;
+    const double* d_t = defect + traj * (long long)(N - 1) * ND;
+    double* W_t = W + traj * (long long)N * ND * WROW;
+    double* vb = vbuf[wid];
+    const unsigned full = 0xffffffffu;
+
+    // ---------------- forward sweep
+    double a[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) a[r] = 0.0;
+    if (NU == ND && lane < 6) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) a[r] = (r == lane) ? 1.0 : 0.0;       // [I6 0] delta_1 = 0  (:141)
+    }
+    double nx[ND];
+    load_rows<NU>(nx, lane, N > 1, phi_t, d_t);
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        if (i < N - 1) {
+#pragma unroll
+            for (int r = 0; r < ND; ++r) a[6 + r] = nx[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < ND; ++r) a[6 + r] = 0.0;
+            if (NU == ND && lane < 6) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) a[6 + r] = (r == lane) ? 1.0 : 0.0;   // [I6 0] delta_N = 0  (:142)
+            }
+        }
+        // prefetch the next node's block while this one is factorised
+        load_rows<NU>(nx, lane, i + 1 < N - 1, phi_t + (long long)(i + 1) * ND * ND, d_t + (long long)(i + 1) * ND);
+        Sweep<NU, 0>::run(a, lane, vb);
+        if (NU < ND) Compress<NU, 0>::run(a, lane, vb);
+        if (lane < NCOL) {
+            double* w = W_t + (long long)i * ND * WROW + lane;
+#pragma unroll
+            for (int r = 0; r < NU; ++r) w[r * WROW] = a[r];
+        }
+        // carry: rows NU..NU+5 of the next node's columns (+ rhs) become rows 0..5 of the next panel
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double up = __shfl_sync(full, a[NU + r], (lane + NU) & 31);
+            a[r] = (lane < NU) ? up : ((lane == 2 * NU) ? a[NU + r] : 0.0);
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ---------------- back substitution: lane = row
+    double dn[NU];                      // delta_{i+1}, replicated in every lane
+#pragma unroll
+    for (int c = 0; c < NU; ++c) dn[c] = 0.0;
+    bool bad = false;
+    const int rl = (lane < NU) ? lane : 0;
+    double2 rowv[WROW / 2], nxt[WROW / 2];
+    {
+        const double2* p = reinterpret_cast<const double2*>(W_t + ((long long)(N - 1) * ND + rl) * WROW);
+#pragma unroll
+        for (int q = 0; q < WROW / 2; ++q) nxt[q] = p[q];
+    }
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; --i) {
+#pragma unroll
+        for (int q = 0; q < WROW / 2; ++q) rowv[q] = nxt[q];
+        if (i > 0) {
+            const double2* p = reinterpret_cast<const double2*>(W_t + ((long long)(i - 1) * ND + rl) * WROW);
+#pragma unroll
+            for (int q = 0; q < WROW / 2; ++q) nxt[q] = p[q];
+        }
+        double row[WROW];
+#pragma unroll
+        for (int q = 0; q < WROW / 2; ++q) { row[2 * q] = rowv[q].x; row[2 * q + 1] = rowv[q].y; }
+        double y = row[2 * NU];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) y = fma(-row[NU + j], dn[j], y);
+        double diag = 1.0;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) diag = (lane == c) ? row[c] : diag;
+        const double invd = 1.0 / diag;
+        double mine = 0.0;
+#pragma unroll
+        for (int c = NU - 1; c >= 0; --c) {
+            const double xc = __shfl_sync(full, y * invd, c);
+            dn[c] = xc;
+            mine = (lane == c) ? xc : mine;
+            if (lane < c) y = fma(-row[c], xc, y);
+        }
+        if (NU == ND && (i == 0 || i == N - 1)) {                 // pinned end states: structurally empty columns (:141-142)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dn[c] = 0.0;
+            if (lane < 6) mine = 0.0;
+        }
+        bad |= !(fabs(mine) <= 1.79e308);
+        double* out = update + (traj * (long long)N + i) * ND;
+        if (NU == ND) { if (lane < ND) out[lane] = mine; }
+        else if (lane < ND) {                                      // costates only (:169-178)
+            const double lam = __shfl_sync(0x00000fffu, mine, lane >= NU ? lane - NU : lane);
+            out[lane] = (lane < NU) ? 0.0 : lam;
+        }
+    }
+    const bool anybad = __any_sync(full, bad && lane < NU);
+    if (status && lane == 0) status[traj] = anybad ? LTO_ST_NAN : 0;
+}
+
+}  // namespace nwt
+
+size_t indirect_newton_workspace_bytes(long long n_traj, int n_nodes) {
+    return (size_t)n_traj * (size_t)n_nodes * nwt::wbytes_per_node();
+}
+
+cudaError_t launch_indirect_newton(const double* phi, const double* defect, double* work, double* update, int32_t* status,
+                                   long long n_traj, int n_nodes, bool adjoints_only, cudaStream_t st) {
+    if (n_traj <= 0 || n_nodes < 2) return cudaErrorInvalidValue;
+    const long long blocks = (n_traj + nwt::WARPS - 1) / nwt::WARPS;
+    if (blocks > 0x7fffffffll) return cudaErrorInvalidValue;
+    if (adjoints_only) nwt::k_indirect_newton<6><<<(int)blocks, 32 * nwt::WARPS, 0, st>>>(phi, defect, work, update, status, n_traj, n_nodes);
+    else nwt::k_indirect_newton<12><<<(int)blocks, 32 * nwt::WARPS, 0, st>>>(phi, defect, work, update, status, n_traj, n_nodes);
+    return cudaGetLastError();
+}
+
+}  // namespace lto

@@ -1,0 +1,292 @@
+// lto_solve.cu -- C ABI of the device-side Newton update and of the batched indirect solver
+// (include/lto_b200.h).
+//
+//   lto_indirect_newton[_dev]   optimizeTraj_OLS's  xc_update = -sparse(Jac_full) \ defect_vec
+//                               (src/multiShoot_CRTBP_indirect.jl:149-183) for n_traj trajectories, straight from the
+//                               Phi_i blocks and defects the propagation kernels leave in HBM (lto_newton.cu)
+//   lto_indirect_solve_batch    the whole iteration loop of multiShoot_CRTBP_indirect (:254-345) for n_traj independent
+//                               trajectories at once, every array resident on the device: STM pass, Newton update, second
+//                               order correction (:187-214), 20-point line search (:221-246), end-state pins (:324-325),
+//                               defect check (:328-336).  Per iteration the host reads back ONE integer (how many
+//                               trajectories are still iterating).
+// Built on the public device-pointer entry points (lto_indirect_dev, lto_sumsq_dev) and a few row-wise helper kernels.
+#include "lto_internal.h"
+#include "lto_handle.h"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace lto {
+size_t indirect_newton_workspace_bytes(long long n_traj, int n_nodes);
+cudaError_t launch_indirect_newton(const double* phi, const double* defect, double* work, double* update, int32_t* status,
+                                   long long n_traj, int n_nodes, bool adjoints_only, cudaStream_t st);
+
+namespace slv {
+
+constexpr int NA = 20;      // line-search points: alpha_all = LinRange(0.1, 1, 20)  (multiShoot_CRTBP_indirect.jl:227)
+
+// out[r] = max_i |v[r*len + i]|  (NaN propagates: norm(defect[:], Inf) of :332 is NaN when any entry is)
+__global__ void __launch_bounds__(256) k_rowmaxabs(const double* __restrict__ v, long long n_rows, long long len, double* __restrict__ out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const double* p = v + row * len;
+    double m = 0.0; bool bad = false;
+    for (long long i = lane; i < len; i += 32) { const double x = fabs(p[i]); bad |= !(x == x); m = fmax(m, x); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) out[row] = bad ? nan("") : m;
+}
+
+// out[a][j][e] = x[j][e] + scale[a*n_rows + j] * u[j][e]   (a = blockIdx.y; in-place on x or u allowed when gridDim.y == 1)
+__global__ void __launch_bounds__(256) k_axpy_rows(const double* x, const double* u, const double* __restrict__ scale, double* out,
+                                                   long long n_rows, long long len) {
+    const long long total = n_rows * len;
+    const long long a = blockIdx.y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i / len;
+        const double s = scale[a * n_rows + j];
+        out[a * total + i] = (s == 0.0) ? x[i] : fma(s, u[i], x[i]);   // a masked row is copied exactly (its update may hold NaN)
+    }
+}
+
+// second-order-correction mask (:190): active && norm(xc_update, Inf) < 1e-1
+__global__ void k_soc_mask(const double* __restrict__ umax, const int* __restrict__ active, double* __restrict__ mask, long long n) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) mask[j] = (active[j] && umax[j] < 1e-1) ? 1.0 : 0.0;
+}
+
+// line search (:243-245): alpha = alpha_all[er .== minimum(er)][1]; scale = alpha for iterating trajectories, 0 otherwise
+__global__ void k_pick_alpha(const double* __restrict__ ers, const double* __restrict__ alpha_all, const int* __restrict__ active,
+                             double* __restrict__ alpha, double* __restrict__ scale, long long n, int use_ls) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double al = 1.0;
+    if (use_ls) {
+        // minimum() propagates NaN in Julia, and then no entry compares equal: the reference would throw.  Here a NaN merit
+        // value never wins; if all are NaN the full step is taken and the NaN surfaces in the defect check.
+        double best = INFINITY; int ib = -1;
+        for (int a = 0; a < NA; ++a) { const double e = ers[(long long)a * n + j]; if (e < best) { best = e; ib = a; } }
+        al = ib >= 0 ? alpha_all[ib] : 1.0;
+    }
+    alpha[j] = al;
+    scale[j] = active[j] ? al : 0.0;
+}
+
+// tile the per-trajectory parameter arrays for the NA trial copies
+__global__ void k_tile(const double* __restrict__ src, double* __restrict__ dst, long long n, int reps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * reps) dst[i] = src[i % n];
+}
+
+// end of an iteration (:328-341): er = norm(defect[:], Inf); iterCount += 1; abort above 1e3; loop condition er > 1e-10
+//   flag: 0 converged / still iterating, 1 gave up (maxIter or abort)
+__global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ active, int* __restrict__ iters, int* __restrict__ flag,
+                           unsigned long long* __restrict__ n_active, long long n, int it, int max_iter) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (!active[j]) return;
+    const double e = er[j];
+    if (it > 0) iters[j] = it;
+    bool go = e > 1e-10;                                  // NaN -> false: the reference's while-condition ends the loop as well
+    if (go && !(e <= 1e3)) { go = false; flag[j] = 1; }   // "Not likely to converge. Aborting." (:333-336)
+    if (go && it >= max_iter) { go = false; flag[j] = 1; }   // "Reached max iteration count" (:282-286)
+    active[j] = go ? 1 : 0;
+    if (go) atomicAdd(n_active, 1ull);
+}
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace slv
+}  // namespace lto
+
+using namespace lto;
+
+extern "C" {
+
+int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
+                            const double* defect, double* xc_update, int32_t* status) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!phi || !defect || !xc_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    if (((uintptr_t)phi & 15u) != 0) return fail(h, LTO_ERR_ARG, "phi must be 16-byte aligned");
+    CK(h, cudaSetDevice(h->device));
+    int rc = ensure(h, &h->d_nwt, &h->d_nwt_cap, indirect_newton_workspace_bytes(n_traj, n_nodes)); if (rc) return rc;
+    cudaError_t e = launch_indirect_newton(phi, defect, (double*)h->d_nwt, xc_update, status, n_traj, n_nodes, flag_adjointsOnly != 0, h->s_compute);
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "newton kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return LTO_SUCCESS;
+}
+
+int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
+                        const double* defect, double* xc_update, int32_t* status) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return lto_indirect_newton(h->child[0], n_traj, n_nodes, flag_adjointsOnly, phi, defect, xc_update, status);
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!phi || !defect || !xc_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    const long long ns = n_traj * (long long)(n_nodes - 1), nn = n_traj * (long long)n_nodes;
+    const size_t bP = al(ns * 144 * 8), bD = al(ns * 12 * 8), bU = al(nn * 12 * 8), bS = al(n_traj * 4);
+    int rc = ensure(h, &h->d_out, &h->d_out_cap, bP + bD + bU + bS); if (rc) return rc;
+    char* q = (char*)h->d_out;
+    double* dP = (double*)q; q += bP; double* dD = (double*)q; q += bD; double* dU = (double*)q; q += bU; int32_t* dS = (int32_t*)q;
+    CK(h, cudaMemcpyAsync(dP, phi, ns * 144 * 8, cudaMemcpyHostToDevice, h->s_compute));
+    CK(h, cudaMemcpyAsync(dD, defect, ns * 12 * 8, cudaMemcpyHostToDevice, h->s_compute));
+    CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    rc = lto_indirect_newton_dev(h, n_traj, n_nodes, flag_adjointsOnly, dP, dD, dU, dS); if (rc) return rc;
+    CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CK(h, cudaMemcpyAsync(xc_update, dU, nn * 12 * 8, cudaMemcpyDeviceToHost, h->s_compute));
+    if (status) CK(h, cudaMemcpyAsync(status, dS, n_traj * 4, cudaMemcpyDeviceToHost, h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    return LTO_SUCCESS;
+}
+
+int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int max_iter,
+                             int flag_adjointsOnly, double* XC_all, const double* t_TU, const double* thrustLimit_traj,
+                             const double* rho_traj, double* defect, int32_t* status_flag, int32_t* iters, double* er_out) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) {
+        // whole trajectories per device, one worker per device would be the natural split; kept simple: device 0
+        return lto_indirect_solve_batch(h->child[0], p, n_traj, n_nodes, max_iter, flag_adjointsOnly, XC_all, t_TU, thrustLimit_traj,
+                                        rho_traj, defect, status_flag, iters, er_out);
+    }
+    if (!p) return fail(h, LTO_ERR_ARG, "null params");
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (max_iter < 0) return fail(h, LTO_ERR_ARG, "negative max_iter");
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!XC_all || !t_TU) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    const int ND = 12, N = n_nodes, NA = slv::NA;
+    const long long T = n_traj, ns = T * (N - 1), nn = T * N;
+    cudaStream_t st = h->s_compute;
+    // ---- device arrays
+    const size_t bXC = al(nn * ND * 8), bT = al(nn * 8), bPar = al(T * 8), bDef = al(ns * ND * 8), bPhi = al(ns * ND * ND * 8);
+    const size_t bTrX = al((size_t)NA * nn * ND * 8), bTrD = al((size_t)NA * ns * ND * 8), bTrT = al((size_t)NA * nn * 8), bTrP = al((size_t)NA * T * 8);
+    const size_t bVec = al((size_t)NA * T * 8), bInt = al(T * 4);
+    size_t need = bXC * 3 + bT + bPar * 2 + bDef * 2 + bPhi + bTrX + bTrD + bTrT + bTrP * 2 + bVec * 7 + bInt * 3 + al(NA * 8) + 256;
+    int rc = ensure(h, &h->d_slv, &h->d_slv_cap, need); if (rc) return rc;
+    char* q = (char*)h->d_slv;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    double* dXC = (double*)take(bXC); double* dXS = (double*)take(bXC); double* dUp = (double*)take(bXC); double* dUp2 = dXS;   // the SOC state buffer is free again when the SOC update is computed
+    double* dT = (double*)take(bT);
+    double* dTL = thrustLimit_traj ? (double*)take(bPar) : nullptr; double* dRH = rho_traj ? (double*)take(bPar) : nullptr;
+    double* dDef = (double*)take(bDef); double* dDs = (double*)take(bDef); double* dPhi = (double*)take(bPhi);
+    double* dTrX = (double*)take(bTrX); double* dTrD = (double*)take(bTrD); double* dTrT = (double*)take(bTrT);
+    double* dTrTL = thrustLimit_traj ? (double*)take(bTrP) : nullptr; double* dTrRH = rho_traj ? (double*)take(bTrP) : nullptr;
+    double* dEr = (double*)take(bVec); double* dUmax = (double*)take(bVec); double* dMask = (double*)take(bVec);
+    double* dErs = (double*)take(bVec); double* dAlpha = (double*)take(bVec); double* dScale = (double*)take(bVec);
+    double* dLsTable = (double*)take(bVec);
+    int* dActive = (int*)take(bInt); int* dIters = (int*)take(bInt); int* dFlag = (int*)take(bInt);
+    double* dAlphaAll = (double*)take(al(NA * 8));
+    unsigned long long* dCount = (unsigned long long*)take(256);
+    // ---- inputs
+    CK(h, cudaMemcpyAsync(dXC, XC_all, nn * ND * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dT, t_TU, nn * 8, cudaMemcpyHostToDevice, st));
+    if (dTL) CK(h, cudaMemcpyAsync(dTL, thrustLimit_traj, T * 8, cudaMemcpyHostToDevice, st));
+    if (dRH) CK(h, cudaMemcpyAsync(dRH, rho_traj, T * 8, cudaMemcpyHostToDevice, st));
+    double alpha_all[slv::NA];
+    for (int a = 0; a < NA; ++a) alpha_all[a] = 0.1 + (double)a * ((1.0 - 0.1) / (double)(NA - 1));      // LinRange(0.1, 1, 20)
+    alpha_all[NA - 1] = 1.0;
+    CK(h, cudaMemcpyAsync(dAlphaAll, alpha_all, NA * 8, cudaMemcpyHostToDevice, st));
+    // line-search scale table: scale[a*T + j] = alpha_a; and the tiled per-trajectory inputs of the NA trial copies
+    {
+        std::vector<double> sc((size_t)NA * T);
+        for (int a = 0; a < NA; ++a) for (long long j = 0; j < T; ++j) sc[(size_t)a * T + j] = alpha_all[a];
+        CK(h, cudaMemcpyAsync(dLsTable, sc.data(), (size_t)NA * T * 8, cudaMemcpyHostToDevice, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    slv::k_tile<<<slv::nblk((long long)NA * nn, 256), 256, 0, st>>>(dT, dTrT, nn, NA);
+    if (dTL) slv::k_tile<<<slv::nblk((long long)NA * T, 256), 256, 0, st>>>(dTL, dTrTL, T, NA);
+    if (dRH) slv::k_tile<<<slv::nblk((long long)NA * T, 256), 256, 0, st>>>(dRH, dTrRH, T, NA);
+    CK(h, cudaMemsetAsync(dIters, 0, T * 4, st));
+    CK(h, cudaMemsetAsync(dFlag, 0, T * 4, st));
+    {
+        std::vector<int> ones((size_t)T, 1);
+        CK(h, cudaMemcpyAsync(dActive, ones.data(), T * 4, cudaMemcpyHostToDevice, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    h->launches += 1 + (dTL ? 1 : 0) + (dRH ? 1 : 0);
+    CK(h, cudaEventRecord(h->ev_t0, st));
+
+    auto defect_pass = [&](const double* X, const double* T_, const double* tl, const double* rh, long long ntr, double* D) -> int {
+        return lto_indirect_dev(h, p, ntr * (N - 1), N, ND, X, T_, nullptr, nullptr, tl, rh, D, nullptr, nullptr, nullptr);
+    };
+    auto rowmax = [&](const double* v, long long rows, long long len, double* out) {
+        slv::k_rowmaxabs<<<slv::nblk(rows * 32, 256), 256, 0, st>>>(v, rows, len, out); h->launches += 1;
+    };
+    auto axpy = [&](const double* x, const double* u, const double* scale, double* out, long long rows, long long len, int reps) {
+        dim3 g(std::min<unsigned>(slv::nblk(rows * len, 256), 148u * 16u), (unsigned)reps);
+        slv::k_axpy_rows<<<g, 256, 0, st>>>(x, u, scale, out, rows, len); h->launches += 1;
+    };
+    auto iter_end = [&](int it) -> int {
+        CK(h, cudaMemsetAsync(dCount, 0, 8, st));
+        slv::k_iter_end<<<slv::nblk(T, 256), 256, 0, st>>>(dEr, dActive, dIters, dFlag, dCount, T, it, max_iter); h->launches += 1;
+        return 0;
+    };
+
+    // ---- first nominal run (:274)
+    rc = defect_pass(dXC, dT, dTL, dRH, T, dDef); if (rc) return rc;
+    rowmax(dDef, T, (long long)(N - 1) * ND, dEr);
+    rc = iter_end(0); if (rc) return rc;
+    unsigned long long n_active = 0;
+    CK(h, cudaMemcpyAsync(&n_active, dCount, 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    int it = 0;
+    while (n_active > 0 && it < max_iter) {
+        ++it;
+        // jacobianCalc (:290): one launch, Phi_i of every segment of every trajectory (and the defects, unchanged)
+        rc = lto_indirect_dev(h, p, ns, N, ND, dXC, dT, nullptr, nullptr, dTL, dRH, dDef, nullptr, nullptr, dPhi); if (rc) return rc;
+        // optimizeTraj_OLS (:149-183)
+        rc = lto_indirect_newton_dev(h, T, N, flag_adjointsOnly, dPhi, dDef, dUp, nullptr); if (rc) return rc;
+        // second-order correction (:187-214), only where norm(xc_update, Inf) < 1e-1
+        rowmax(dUp, T, (long long)N * ND, dUmax);
+        slv::k_soc_mask<<<slv::nblk(T, 256), 256, 0, st>>>(dUmax, dActive, dMask, T); h->launches += 1;
+        axpy(dXC, dUp, dMask, dXS, T, (long long)N * ND, 1);                                   // XC_all_soc (:194)
+        rc = defect_pass(dXS, dT, dTL, dRH, T, dDs); if (rc) return rc;                        // :197
+        rc = lto_indirect_newton_dev(h, T, N, flag_adjointsOnly, dPhi, dDs, dUp2, nullptr); if (rc) return rc;   // :207 (same Jacobian)
+        axpy(dUp, dUp2, dMask, dUp, T, (long long)N * ND, 1);                                  // xc_update += xc_update_soc (:213)
+        // line search (:298-302)
+        const int use_ls = it > 3;
+        if (use_ls) {
+            axpy(dXC, dUp, dLsTable, dTrX, T, (long long)N * ND, NA);                          // XC_all + xc_update*alpha (:235)
+            rc = defect_pass(dTrX, dTrT, dTrTL, dTrRH, (long long)NA * T, dTrD); if (rc) return rc;   // :238, all 20 x n_traj trials in one launch
+            rc = lto_sumsq_dev(h, dTrD, (long long)NA * T, (long long)(N - 1) * ND, dErs); if (rc) return rc;   // er[ind] = sum(defect[:].^2) (:241)
+        }
+        slv::k_pick_alpha<<<slv::nblk(T, 256), 256, 0, st>>>(dErs, dAlphaAll, dActive, dAlpha, dScale, T, use_ls); h->launches += 1;
+        axpy(dXC, dUp, dScale, dXC, T, (long long)N * ND, 1);                                  // XC_all = XC_all + xc_update*alpha (:304)
+        // the end states cannot have moved (:324-325): their update entries are exact zeros (lto_newton.cu)
+        rc = defect_pass(dXC, dT, dTL, dRH, T, dDef); if (rc) return rc;                       // :328
+        rowmax(dDef, T, (long long)(N - 1) * ND, dEr);                                         // :332
+        rc = iter_end(it); if (rc) return rc;
+        CK(h, cudaMemcpyAsync(&n_active, dCount, 8, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+    }
+    CK(h, cudaEventRecord(h->ev_t1, st));
+    // ---- outputs
+    CK(h, cudaMemcpyAsync(XC_all, dXC, nn * ND * 8, cudaMemcpyDeviceToHost, st));
+    if (defect) CK(h, cudaMemcpyAsync(defect, dDef, ns * ND * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(h, cudaMemcpyAsync(iters, dIters, T * 4, cudaMemcpyDeviceToHost, st));
+    if (er_out) CK(h, cudaMemcpyAsync(er_out, dEr, T * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> flag((size_t)T);
+    CK(h, cudaMemcpyAsync(flag.data(), dFlag, T * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    if (status_flag) {
+        for (long long j = 0; j < T; ++j) {
+            int f = flag[(size_t)j];
+            if (std::isnan(XC_all[(size_t)j * N * ND])) f = 2;                                 // :339-341
+            status_flag[j] = f;
+        }
+    }
+    return LTO_SUCCESS;
+}
+
+}  // extern "C"

@@ -72,6 +72,17 @@ class GpuBackend:
         self.calls += 1
         return self.h.indirect(x0, t0, t1, params=self._ip(params), jac=False)["defect"]
 
+    def indirect_newton(self, phi, defect, flag_adjointsOnly):
+        """-sparse(Jac_full) \\ defect_vec on the device (lto_indirect_newton); phi (B, N-1, m, m) [.., row, col] -> (B, N, m)."""
+        self.calls += 1
+        upd, status = self.h.indirect_newton(np.ascontiguousarray(phi.transpose(0, 1, 3, 2)), defect, flag_adjointsOnly)
+        return upd
+
+    def indirect_solve_batch(self, XC, t, params, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False):
+        self.calls += 1
+        return self.h.indirect_solve_batch(XC, t, params=self._ip(params), thrustLimit=thrustLimit, rho=rho, max_iter=max_iter,
+                                           flag_adjointsOnly=flag_adjointsOnly)
+
 
 _default_backend = None
 
@@ -292,8 +303,9 @@ def _band_indirect(phi, nstate, N):
 
 
 def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLimit, plot_yn=False, flag_adjointsOnly=False,
-                              maxIter=50, p=1.0, rho=1.0, backend=None, log=None):
-    """(XC_all, defect, status_flag) = multiShoot_CRTBP_indirect(...)   (:58-59, :344)."""
+                              maxIter=50, p=1.0, rho=1.0, backend=None, log=None, device_newton=False):
+    """(XC_all, defect, status_flag) = multiShoot_CRTBP_indirect(...)   (:58-59, :344).
+    device_newton: solve the update on the GPU (lto_indirect_newton) instead of the dense host least squares."""
     be = backend or default_backend()
     XC_all = np.array(XC_all, dtype=np.float64); t_TU = np.asarray(t_TU, dtype=np.float64)
     nstate = XC_all.shape[0] // 2; m = 2 * nstate; N = n_nodes
@@ -313,6 +325,8 @@ def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLi
 
     def solve(J, dvec):
         """-sparse(J) \\ d (:181-182): least squares over the structurally non-empty columns, 0 elsewhere."""
+        if device_newton:
+            return be.indirect_newton(phi, dvec.reshape(1, N - 1, m), flag_adjointsOnly)[0].T
         Jk = J[:, keep]
         live = np.any(Jk != 0.0, axis=0)
         sol = np.zeros(Jk.shape[1])
@@ -329,7 +343,7 @@ def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLi
             status_flag = 1
             break
         _, phi = be.indirect_blocks(XC_all.T[None], t_TU[None], params)                                   # :290
-        Jac_full = _band_indirect(phi[0], nstate, N)
+        Jac_full = None if device_newton else _band_indirect(phi[0], nstate, N)
         xc_update = solve(Jac_full, defect.T.ravel())
         if np.max(np.abs(xc_update)) < 1e-1:                                                              # SOC :190-214
             d_soc = defectCalc(XC_all + xc_update)
@@ -354,6 +368,23 @@ def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLi
     if np.isnan(XC_all[0, 0]):                                                                            # :339-341
         status_flag = 2
     return XC_all, defect, status_flag
+
+
+def multiShoot_CRTBP_indirect_batch(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLimit, flag_adjointsOnly=False, maxIter=50, p=1.0,
+                                    rho=1.0, backend=None):
+    """multiShoot_CRTBP_indirect for a BATCH of independent trajectories, iterated entirely on the device
+    (lto_indirect_solve_batch).  XC_all: (n_traj, 12, n_nodes) in the reference's per-trajectory shape; t_TU: (n_traj, n_nodes);
+    thrustLimit / rho: scalars or per-trajectory arrays (continuation ladders).  Returns (XC_all, defect (n_traj, 12, n_nodes-1),
+    status_flag (n_traj,), iters (n_traj,))."""
+    be = backend or default_backend()
+    XC = np.ascontiguousarray(np.asarray(XC_all, dtype=np.float64).transpose(0, 2, 1))
+    T = XC.shape[0]
+    tl = np.broadcast_to(np.asarray(thrustLimit, dtype=np.float64), (T,)).copy()
+    rh = np.broadcast_to(np.asarray(rho, dtype=np.float64), (T,)).copy()
+    params = (MU, DU, TU, float(tl[0]), mass0, 1.0, p, float(rh[0]))
+    r = be.indirect_solve_batch(XC, np.asarray(t_TU, dtype=np.float64), params, thrustLimit=tl, rho=rh, max_iter=maxIter,
+                                flag_adjointsOnly=flag_adjointsOnly)
+    return r["XC_all"].transpose(0, 2, 1).copy(), r["defect"].transpose(0, 2, 1).copy(), r["status_flag"], r["iters"]
 
 
 def reduceFuel_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rho_current, rho_target, backend=None, rng=None,
