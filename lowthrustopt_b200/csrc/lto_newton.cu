@@ -30,6 +30,7 @@
 // lane = row.  The sweep is a dependent chain (latency bound, ~2-3 k cycles per node); throughput comes
 // from the 1,024 trajectories of a continuation batch running side by side (7 warps per SM).
 #include "lto_internal.h"
+#include "lto_cw_common.cuh"
 #include <algorithm>
 
 namespace lto {
@@ -65,31 +66,43 @@ __device__ __forceinline__ void load_rows(double (&nx)[ND], int lane, bool have,
 }
 
 // One Householder reflection: pivot column = lane PL, pivot row PR; rows PR..17; applied to lanes > PL.
+// The pivot lane only publishes its raw column x; every lane forms x.a_c (the pivot lane thereby |x|^2), and alpha, v_k, gamma
+// are computed redundantly by all lanes from one shuffled scalar, so nothing waits on a single lane's sqrt / reciprocal:
+//     v = x - alpha e_k,   H y = y + v (v.y) / (alpha v_k),   v.y = x.y - alpha y_k,   alpha v_k = -|x| (|x_k| + |x|)
 template <int PL, int PR>
 __device__ __forceinline__ void reflect(double (&a)[NR], int lane, double* __restrict__ vb) {
     double* v = vb + ((PL & 1) ? VBUF : 0);                       // double buffer: one __syncwarp per reflection
     if (lane == PL) {
-        double sig = 0.0;
 #pragma unroll
-        for (int r = PR + 1; r < NR; ++r) sig = fma(a[r], a[r], sig);
-        const double nrm = sqrt(fma(a[PR], a[PR], sig));
-        const double alpha = (a[PR] >= 0.0) ? -nrm : nrm;
-        const double vk = a[PR] - alpha;
-        const double gamma = (nrm > 0.0) ? 1.0 / (alpha * vk) : 0.0;   // H y = y + v (v.y) / (alpha v_k)
-        v[PR] = vk;
-#pragma unroll
-        for (int r = PR + 1; r < NR; ++r) { v[r] = a[r]; a[r] = 0.0; }
-        v[NR] = gamma;
-        a[PR] = alpha;
+        for (int r = PR; r < NR; ++r) v[r] = a[r];
     }
     __syncwarp();
+    double x[NR];
+#pragma unroll
+    for (int r = PR; r < NR; ++r) x[r] = v[r];
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = PR; r < NR; ++r) d[(r - PR) & 3] = fma(x[r], a[r], d[(r - PR) & 3]);
+    const double dot = (d[0] + d[1]) + (d[2] + d[3]);
+    const double sigma = __shfl_sync(0xffffffffu, dot, PL);      // |x|^2
+    double alpha = 0.0, vk = 0.0, gamma = 0.0;
+    if (sigma > 0.0) {
+        const double inv = cwc::fast_rsqrt(sigma), nrm = sigma * inv;
+        alpha = (x[PR] >= 0.0) ? -nrm : nrm;
+        vk = x[PR] - alpha;
+        gamma = -inv * cwc::fast_rcp(fabs(x[PR]) + nrm);
+    } else if (!(sigma == 0.0)) {
+        alpha = sigma; gamma = sigma;                            // NaN: propagate (reported through status[])
+    }
     if (lane > PL) {
-        double s = 0.0;
+        const double t = fma(-alpha, a[PR], dot) * gamma;
+        a[PR] = fma(vk, t, a[PR]);
 #pragma unroll
-        for (int r = PR; r < NR; ++r) s = fma(v[r], a[r], s);
-        s *= v[NR];
+        for (int r = PR + 1; r < NR; ++r) a[r] = fma(x[r], t, a[r]);
+    } else if (lane == PL) {
+        a[PR] = alpha;
 #pragma unroll
-        for (int r = PR; r < NR; ++r) a[r] = fma(v[r], s, a[r]);
+        for (int r = PR + 1; r < NR; ++r) a[r] = 0.0;
     }
 }
 
@@ -121,7 +134,7 @@ template <int NU>
 __global__ void __launch_bounds__(32 * WARPS) k_indirect_newton(const double* __restrict__ phi, const double* __restrict__ defect,
                                                                  double* __restrict__ W, double* __restrict__ update,
                                                                  int32_t* __restrict__ status, long long n_traj, int n_nodes) {
-    __shared__ double vbuf[WARPS][2 * VBUF];
+    __shared__ __align__(16) double vbuf[WARPS][2 * VBUF];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long traj = (long long)blockIdx.x * WARPS + wid;
     if (traj >= n_traj) return;
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_indirect_newton(const double* __
         double diag = 1.0;
 #pragma unroll
         for (int c = 0; c < NU; ++c) diag = (lane == c) ? row[c] : diag;
-        const double invd = 1.0 / diag;
+        const double invd = cwc::fast_rcp(diag);
         double mine = 0.0;
 #pragma unroll
         for (int c = NU - 1; c >= 0; --c) {
