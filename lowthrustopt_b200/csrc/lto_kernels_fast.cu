@@ -2,12 +2,15 @@
 #include "lto_internal.h"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace lto {
 
 cudaError_t launch_direct_cw(const DirectArgs& a, int nstate, cudaStream_t st, int* n_launch);
 cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch);
 cudaError_t launch_indirect_q3(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch);
+cudaError_t launch_indirect_cw14(const IndirectArgs& a, cudaStream_t st, int* n_launch);
+size_t indirect_cw14_scratch_bytes(int n_sm);
 size_t indirect_cwv2_scratch_bytes(int n_sm);
 size_t indirect_q3_scratch_bytes(int n_sm);
 
@@ -24,13 +27,14 @@ static bool use_q3() {
 }
 
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
+    if (ndim == 14) return launch_indirect_cw14(a, st, n_launch);
     if (a.phi != nullptr && use_q3()) return launch_indirect_q3(a, ndim, st, n_launch);
     return launch_indirect_cw(a, ndim, st, n_launch);
 }
 
 size_t indirect_cw_scratch_bytes(int n_sm) {
-    const size_t x = indirect_cwv2_scratch_bytes(n_sm), y = indirect_q3_scratch_bytes(n_sm);
-    return x > y ? x : y;
+    const size_t x = indirect_cwv2_scratch_bytes(n_sm), y = indirect_q3_scratch_bytes(n_sm), z = indirect_cw14_scratch_bytes(n_sm);
+    return std::max(x, std::max(y, z));
 }
 
 }  // namespace lto
