@@ -6,9 +6,9 @@
 // exactly as lto_math.cuh sc_stage<14> / sc_col<14> state them.
 //
 // Same column-warp layout as lto_indirect_cw.cu (K3), with what the two extra components change:
-//   * 14 columns -> 7 column warps (warp w carries columns 2w, 2w+1 of 16 slots per half-phase) + 2 state
-//     warps = 9 warps, 224 registers per thread.  Warps 7 and 8 are the state warps: the column warps then sit
-//     2-2-2-1 on the four SM sub-partitions.
+//   * 14 columns -> 7 column warps (warp w carries columns 2w, 2w+1 of 16 slots per half-phase) + ONE state warp
+//     that serves both tiles alternately = 8 warps, 255 registers per thread; the column warps sit 2-2-2-1 on the
+//     four SM sub-partitions, the state warp shares the last one.
 //   * the mass-costate lm enters no right-hand side, so lm (and the lm-row of every STM column) is a pure
 //     quadrature: no stage values are stored for it, only the running 8th-order sum and error combination.
 //   * G = du/dlv is published as its generators (lh, uon, cd): G plv = -uon plv + cd (lh.plv) lh, and the mass
@@ -32,7 +32,7 @@ constexpr int HS = 16;
 constexpr int NCW = 7;
 constexpr int NCT = 32 * NCW;     // 224 column threads
 constexpr int NC2 = 11;           // double2 per stage record: U[6] W[6] lh[3] uon cd cgm cml clml mm lmm
-constexpr int NW = NTILE + NCW;   // 9 warps
+constexpr int NW = 1 + NCW;       // 8 warps: 7 column warps + ONE state warp serving both tiles
 constexpr int NTHREADS = 32 * NW;
 
 enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };
@@ -448,129 +448,155 @@ __device__ __forceinline__ double initial_step(const KStore& K, const double (&x
     return fmin(fmin(100.0 * h0, h1), span);
 }
 
+// Persistent per-slot controller state of one tile.  ONE state warp serves both tiles alternately: in steady state a tile's next
+// attempt is computed while the column warps work on the other tile, so a second state warp would never run concurrently with
+// the first (it only shortens the start-up) -- and with 8 warps instead of 9 every thread keeps 255 registers (the register
+// file is split per SM sub-partition: a third warp on one sub-partition caps all threads at 168).
+struct SlotCtl {
+    double tcur, tf, h, span, esum, tk, rho_inv, rq;
+    long long seg, ia;
+    int na, nt, status, xi;
+    bool active, lastrej, last, have;
+    unsigned visit;
+};
+
 template <bool JOINT>
-__device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
-    const TileSmem S = tile_smem(smem, t);
+__device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsigned char* smem) {
     const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
-    int xi = 0;
-    double* const xbuf = S.xn + slot;
+    SlotCtl ctl[NTILE];
 #pragma unroll
-    for (int i = 0; i < ND; ++i) { xbuf[i * TS] = (i == 6) ? 1.0 : 0.0; xbuf[(ND + i) * TS] = (i == 6) ? 1.0 : 0.0; }
-    double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
-    LawConst lw; lw.tk = 0.0; lw.rho_inv = 1.0; lw.rho_inv_quarter = 0.25;
-    long long seg = -1, ia = 0;
-    int na = 0, nt = 0, status = 0;
-    bool active = false, lastrej = false, last = false, have = false, exhausted = false;
-    unsigned visit = 0;
-    double2* rec = S.rec + slot;
-    while (true) {
-        int flags = 0, store_seg = 0;
-        bool finished = false;
-        if (have) {
-            mbar_wait_parked(S.bar_done, (visit - 1) & 1);
-            if (active) {
-                double s2 = esum;
-                if (JOINT) {
+    for (int t = 0; t < NTILE; ++t) {
+        SlotCtl& c = ctl[t];
+        c.tcur = 0.0; c.tf = 0.0; c.h = 0.0; c.span = 1.0; c.esum = 0.0; c.tk = 0.0; c.rho_inv = 1.0; c.rq = 0.25;
+        c.seg = -1; c.ia = 0; c.na = 0; c.nt = 0; c.status = 0; c.xi = 0;
+        c.active = false; c.lastrej = false; c.last = false; c.have = false; c.visit = 0;
+        double* const xb = tile_smem(smem, t).xn + slot;
 #pragma unroll
-                    for (int c = 0; c < ND; ++c) s2 += S.errp[c * TS + slot];
-                }
-                const double eest = sqrt(s2 * inv_ne);
-                if (!(eest == eest)) { status = LTO_ST_NAN; finished = true; }
-                else {
-                    double q = (eest == 0.0) ? 5.0 : 0.9 * inv_eighth_root(eest);
-                    q = fmin(5.0, fmax(0.2, q));
-                    if (eest <= 1.0) {
-                        ++na; flags |= F_ACCEPT;
-                        xi ^= 1;
-                        if (last) { tcur = tf; finished = true; }
-                        else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
-                    } else {
-                        lastrej = true; q = fmin(q, 1.0);
+        for (int i = 0; i < ND; ++i) { xb[i * TS] = (i == 6) ? 1.0 : 0.0; xb[(ND + i) * TS] = (i == 6) ? 1.0 : 0.0; }
+    }
+    bool exhausted = false;
+    unsigned alive = (1u << NTILE) - 1u;
+    while (alive) {
+#pragma unroll 1
+        for (int t = 0; t < NTILE; ++t) {
+            if (!(alive & (1u << t))) continue;
+            const TileSmem S = tile_smem(smem, t);
+            SlotCtl c = ctl[t];
+            double* const xbuf = S.xn + slot;
+            double2* const rec = S.rec + slot;
+            int flags = 0, store_seg = 0;
+            bool finished = false;
+            if (c.have) {
+                mbar_wait_parked(S.bar_done, (c.visit - 1) & 1);
+                if (c.active) {
+                    double s2 = c.esum;
+                    if (JOINT) {
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) s2 += S.errp[k * TS + slot];
                     }
-                    h *= q;
+                    const double eest = sqrt(s2 * inv_ne);
+                    if (!(eest == eest)) { c.status = LTO_ST_NAN; finished = true; }
+                    else {
+                        double q = (eest == 0.0) ? 5.0 : 0.9 * inv_eighth_root(eest);
+                        q = fmin(5.0, fmax(0.2, q));
+                        if (eest <= 1.0) {
+                            ++c.na; flags |= F_ACCEPT;
+                            c.xi ^= 1;
+                            if (c.last) { c.tcur = c.tf; finished = true; }
+                            else { c.tcur += c.h; if (c.lastrej) q = fmin(q, 1.0); c.lastrej = false; }
+                        } else {
+                            c.lastrej = true; q = fmin(q, 1.0);
+                        }
+                        c.h *= q;
+                    }
                 }
             }
-        }
-        if (active && !finished) {
-            if (h < span * 1e-12) { status = LTO_ST_HMIN; finished = true; }
-            else if (nt >= a.cfg.max_attempts) { status = LTO_ST_MAXSTEPS; finished = true; }
-        }
-        if (active && finished) {
-            bool nan = false;
-            const double* xs = xbuf + xi * ND * TS;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) {
-                const double xv = xs[i * TS];
-                nan |= !(xv == xv);
-                a.defect[seg * ND + i] = a.x_target ? xv - a.x_target[ia * ND + i] : xv;     // :82
+            if (c.active && !finished) {
+                if (c.h < c.span * 1e-12) { c.status = LTO_ST_HMIN; finished = true; }
+                else if (c.nt >= a.cfg.max_attempts) { c.status = LTO_ST_MAXSTEPS; finished = true; }
             }
-            if (nan && status == 0) status = LTO_ST_NAN;
-            if (a.status) a.status[seg] = status;
-            if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
-            flags |= F_STORE; store_seg = (int)seg;
-            active = false;
-        }
-        bool fresh = false;
-        if (!active && !exhausted) {
-            const long long idx = (long long)atomicAdd(a.counter, 1ull);
-            if (idx < a.n_seg) {
-                seg = idx; ia = lto_node_a(seg, a.npt);
-                const long long it = lto_traj_of(seg, a.npt);
+            if (c.active && finished) {
+                bool nan = false;
+                const double* xs = xbuf + c.xi * ND * TS;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) xbuf[(xi * ND + i) * TS] = a.x0[ia * ND + i];
-                tcur = a.t0[ia]; tf = a.t1[ia];
-                if (!(tcur < tf)) tf = tcur;
-                span = tf - tcur;
-                const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
-                const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
-                lw.tk = tl * a.c.kthr;
-                lw.rho_inv = 1.0 / rho;
-                lw.rho_inv_quarter = 0.25 / rho;
-                na = 0; nt = 0; status = 0; lastrej = false;
-                active = true; fresh = true; flags |= F_RESET;
-            } else {
-                exhausted = true;
+                for (int i = 0; i < ND; ++i) {
+                    const double xv = xs[i * TS];
+                    nan |= !(xv == xv);
+                    a.defect[c.seg * ND + i] = a.x_target ? xv - a.x_target[c.ia * ND + i] : xv;     // :82
+                }
+                if (nan && c.status == 0) c.status = LTO_ST_NAN;
+                if (a.status) a.status[c.seg] = c.status;
+                if (a.nsteps_out) { a.nsteps_out[2 * c.seg] = c.na; a.nsteps_out[2 * c.seg + 1] = c.nt; }
+                flags |= F_STORE; store_seg = (int)c.seg;
+                c.active = false;
             }
-        }
-        if (!__any_sync(fullmask, active)) {
-            S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg);
-            if (lane == 0) *S.tile_done = 1;
+            bool fresh = false;
+            if (!c.active && !exhausted) {
+                const long long idx = (long long)atomicAdd(a.counter, 1ull);
+                if (idx < a.n_seg) {
+                    c.seg = idx; c.ia = lto_node_a(c.seg, a.npt);
+                    const long long it = lto_traj_of(c.seg, a.npt);
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) xbuf[(c.xi * ND + i) * TS] = a.x0[c.ia * ND + i];
+                    c.tcur = a.t0[c.ia]; c.tf = a.t1[c.ia];
+                    if (!(c.tcur < c.tf)) c.tf = c.tcur;
+                    c.span = c.tf - c.tcur;
+                    const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
+                    const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
+                    c.tk = tl * a.c.kthr;
+                    c.rho_inv = 1.0 / rho;
+                    c.rq = 0.25 / rho;
+                    c.na = 0; c.nt = 0; c.status = 0; c.lastrej = false;
+                    c.active = true; fresh = true; flags |= F_RESET;
+                } else {
+                    exhausted = true;
+                }
+            }
+            if (!__any_sync(fullmask, c.active)) {
+                S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg);
+                if (lane == 0) *S.tile_done = 1;
+                mbar_arrive(S.bar_full);
+                alive &= ~(1u << t);
+                ctl[t] = c;
+                continue;
+            }
+            LawConst lw; lw.tk = c.tk; lw.rho_inv = c.rho_inv; lw.rho_inv_quarter = c.rq;
+            KStore K;
+            const double* xs = xbuf + c.xi * ND * TS;
+            state_stage_s<0>(K, xs, 0.0, 0.0, a.c, lw, rec);
+            if (__any_sync(fullmask, fresh)) {
+                double x[ND];
+#pragma unroll
+                for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
+                const double h1 = initial_step(K, x, c.span, a.c, lw, atol, rtol);
+                if (fresh) c.h = h1;
+            }
+            c.last = false;
+            if (c.tcur + c.h >= c.tf) { c.h = c.tf - c.tcur; c.last = true; }
+            if (c.active) ++c.nt;
+            const double h = c.h;
+            S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (c.active ? F_ACTIVE : 0), store_seg);
+            const double h2 = h * h;
+            state_stage_s<1>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<2>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<3>(K, xs, h, h2, a.c, lw, rec);
+            state_stage_s<4>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<5>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<6>(K, xs, h, h2, a.c, lw, rec);
+            state_stage_s<7>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<8>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<9>(K, xs, h, h2, a.c, lw, rec);
+            state_stage_s<10>(K, xs, h, h2, a.c, lw, rec); state_stage_s<11>(K, xs, h, h2, a.c, lw, rec); state_stage_s<12>(K, xs, h, h2, a.c, lw, rec);
+            {
+                double x[ND], xn[ND];
+#pragma unroll
+                for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
+                c.esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+                double* xc = xbuf + (c.xi ^ 1) * ND * TS;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
+            }
             mbar_arrive(S.bar_full);
-            break;
+            c.have = true; ++c.visit;
+            ctl[t] = c;
         }
-        KStore K;
-        const double* xs = xbuf + xi * ND * TS;
-        state_stage_s<0>(K, xs, 0.0, 0.0, a.c, lw, rec);
-        if (__any_sync(fullmask, fresh)) {
-            double x[ND];
-#pragma unroll
-            for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-            const double h1 = initial_step(K, x, span, a.c, lw, atol, rtol);
-            if (fresh) h = h1;
-        }
-        last = false;
-        if (tcur + h >= tf) { h = tf - tcur; last = true; }
-        if (active) ++nt;
-        S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0), store_seg);
-        const double h2 = h * h;
-        state_stage_s<1>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<2>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<3>(K, xs, h, h2, a.c, lw, rec);
-        state_stage_s<4>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<5>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<6>(K, xs, h, h2, a.c, lw, rec);
-        state_stage_s<7>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<8>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<9>(K, xs, h, h2, a.c, lw, rec);
-        state_stage_s<10>(K, xs, h, h2, a.c, lw, rec); state_stage_s<11>(K, xs, h, h2, a.c, lw, rec); state_stage_s<12>(K, xs, h, h2, a.c, lw, rec);
-        {
-            double x[ND], xn[ND];
-#pragma unroll
-            for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-            esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
-            double* xc = xbuf + (xi ^ 1) * ND * TS;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
-        }
-        mbar_arrive(S.bar_full);
-        have = true; ++visit;
     }
 }
 
@@ -585,8 +611,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw14(IndirectArgs a) {
         *S.tile_done = 0;
     }
     __syncthreads();
-    // warps 0..6: column warps (sub-partitions 0,1,2,3,0,1,2); warps 7, 8: state warps (sub-partitions 3, 0)
-    if (warp >= NCW) state_warp<JOINT>(a, warp - NCW, lane, smem_raw);
+    // warps 0..6: column warps (sub-partitions 0,1,2,3,0,1,2); warp 7: the state warp (sub-partition 3, next to one column warp)
+    if (warp == NCW) state_warp<JOINT>(a, lane, smem_raw);
     else column_warp<JOINT>(a, warp, lane, smem_raw);
 }
 

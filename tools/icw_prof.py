@@ -8,14 +8,30 @@ norm = capi.LTO_NORM_STATE if (len(sys.argv) > 1 and sys.argv[1] == "state") els
 h = capi.Handle(0)
 b = S.indirect_batch(131072, ndim=12, seed=20180002)
 p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05, err_norm=norm)
+import torch
+dev = torch.device("cuda", 0)
+n = 131072
+dx0 = torch.from_numpy(b["x0"]).to(dev); dt0 = torch.from_numpy(b["t0"]).to(dev); dt1 = torch.from_numpy(b["t1"]).to(dev)
+d_def = torch.empty((n, 12), dtype=torch.float64, device=dev); d_ns = torch.empty((n, 2), dtype=torch.int32, device=dev)
+d_phi = torch.empty((n, 12, 12), dtype=torch.float64, device=dev)
+st = torch.cuda.ExternalStream(h.stream, device=dev)
 for _ in range(2):
-    r = h.indirect(b["x0"], b["t0"], b["t1"], params=p)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        e0.record()
+        h.indirect_dev(p, n, 0, 12, dx0.data_ptr(), dt0.data_ptr(), dt1.data_ptr(), None, None, None, d_def.data_ptr(), None, d_ns.data_ptr(), d_phi.data_ptr())
+        e1.record()
+    h.sync()
+r = {"nsteps": d_ns.cpu().numpy()}
+kms = e0.elapsed_time(e1)
 w = h.debug_profile().astype(np.float64)
 grid, NW, NT = 148, 8, 2
 c = w[:grid * NW * 4].reshape(grid, NW, 4)
 pre = w[grid * NW * 4: grid * NW * 4 + grid * NT].reshape(grid, NT)
 st, co = c[:, :NT], c[:, NT:]
-print("kernel ms %.3f  attempts/seg %.2f" % (h.last_kernel_ms, r["nsteps"][:, 1].mean()))
+print("kernel ms %.3f  attempts/seg %.2f" % (kms, r["nsteps"][:, 1].mean()))
+load = w[grid * NW * 4 + grid * NT: grid * NW * 4 + grid * NT + grid * 6].reshape(grid, 6)
+print("column L2 load cycles per half-phase %.0f" % (load / co[..., 2]).mean())
 print("state : alive %.0f  work/attempt %.0f  wait/attempt %.0f  pre/attempt %.0f  attempts %.0f" % (
     st[..., 3].mean(), (st[..., 0] / st[..., 2]).mean(), (st[..., 1] / st[..., 2]).mean(), (pre / st[..., 2]).mean(), st[..., 2].mean()))
 print("column: alive %.0f  work/half-phase %.0f  wait/visit %.0f  half-phases %.0f  busy %.1f%%" % (
