@@ -60,7 +60,9 @@ constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h,
 constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);        // current columns, both halves
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
 constexpr size_t XN_BYTES = (size_t)2 * ND * TS * sizeof(double);          // the state x and its candidate (double buffer; keeps 24 registers free in the state warps)
-constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
+constexpr int NXW = ND + 6;                                                // next-segment stash: x0, t0, tf, aL, 1/rho, aL/(4 rho), h0
+constexpr size_t NXT_BYTES = (size_t)NXW * TS * sizeof(double);
+constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES + NXT_BYTES;
 constexpr size_t BAR_BYTES = 128;                                          // 13 stage barriers, done, tile_done
 constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
 // Stage-level hand-off (columns start a tile while its state warp is still producing the later
@@ -71,7 +73,7 @@ constexpr int START_STAGE = 4;
 constexpr size_t SCRATCH_BYTES_PER_CTA = (size_t)NTILE * 2 * ND * NCT * sizeof(double);   // candidate columns (global)
 
 struct TileSmem {
-    double2* rec; double* hval; int2* hctl; double* cur; double* errp; double* xn;
+    double2* rec; double* hval; int2* hctl; double* cur; double* errp; double* xn; double* nx;
     unsigned bar_full, bar_done; volatile int* tile_done;
 };
 
@@ -83,7 +85,8 @@ __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
     s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
     s.cur = reinterpret_cast<double*>(p); p += CUR_BYTES;
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
-    s.xn = reinterpret_cast<double*>(p);
+    s.xn = reinterpret_cast<double*>(p); p += XN_BYTES;
+    s.nx = reinterpret_cast<double*>(p);
     unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * BAR_BYTES;
     s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 13 * 8);         // bar_full + 8 j: stage j's record is published
     s.tile_done = reinterpret_cast<volatile int*>(b + 14 * 8);
@@ -440,6 +443,73 @@ __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)
     return sqrt(s * (1.0 / (double)ND));
 }
 
+__device__ __noinline__ Out9 sc_eval_state_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
+                                                double m0, double m1, double m2, double mu, double mu1, double omega, double pexp, double aL,
+                                                double rho_inv, double rq);
+
+// Off the critical path: while the column warps work on the attempt just published, every slot that has no successor yet claims
+// its NEXT segment from the work queue, loads it, and runs the Hairer-Norsett-Wanner initial-step estimate over the state
+// components (drive_rk8 in lto_prop_generic.cuh) -- queue atomic, scattered loads and two extra right-hand sides (~4-5 k cycles,
+// needed on nearly every visit because some slot of the 32 is always about to finish) used to sit in front of the next attempt.
+// The result waits in the tile's shared-memory stash until the slot's current segment finishes.  A slot claims just in time
+// (`soon`: it is idle, or the attempt just published reaches t1), so no segment is hoarded while other slots run dry.
+__device__ __forceinline__ void prepare_next(const IndirectArgs& a, const TileSmem& S, int slot, long long& nseg, bool& exhausted, bool soon) {
+    const unsigned fullmask = 0xffffffffu;
+    const bool want = soon && !exhausted && nseg < 0;
+    if (!__any_sync(fullmask, want)) return;
+    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
+    double x[ND];
+    double t0 = 0.0, tf = 0.0, aL = 0.0, rho_inv = 1.0, rq = 0.0;
+    bool got = false;
+    if (want) {
+        const long long idx = (long long)atomicAdd(a.counter, 1ull);
+        if (idx < a.n_seg) {
+            got = true; nseg = idx;
+            const long long ia = lto_node_a(idx, a.npt), it = lto_traj_of(idx, a.npt);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) x[i] = a.x0[ia * ND + i];
+            t0 = a.t0[ia]; tf = a.t1[ia];
+            if (!(t0 < tf)) tf = t0;                                      // empty span: one zero-length step, Phi = I
+            const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
+            const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
+            aL = tl * a.c.kthr / a.c.mass;                                // :33
+            rho_inv = 1.0 / rho;
+            rq = aL / (4.0 * rho);
+        } else {
+            exhausted = true;
+        }
+    }
+    if (!got) {
+#pragma unroll
+        for (int i = 0; i < ND; ++i) x[i] = 0.0;
+    }
+    const double span = tf - t0;
+    const Out9 o0 = sc_eval_state_call(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8], x[9], x[10], x[11], a.c.mu, a.c.m1, a.c.omega, a.c.p, aL,
+                                       rho_inv, rq);
+    double f0[ND], y1[ND];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { f0[q] = x[3 + q]; f0[3 + q] = o0.v[q]; f0[6 + q] = o0.v[3 + q]; f0[9 + q] = o0.v[6 + q]; }
+    const double d0 = rms12(x, x, atol, rtol), d1 = rms12(f0, x, atol, rtol);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+    h0 = fmin(h0, span);
+#pragma unroll
+    for (int i = 0; i < ND; ++i) y1[i] = fma(h0, f0[i], x[i]);
+    const Out9 o1 = sc_eval_state_call(y1[0], y1[1], y1[2], y1[3], y1[4], y1[5], y1[6], y1[7], y1[8], y1[9], y1[10], y1[11], a.c.mu, a.c.m1, a.c.omega, a.c.p,
+                                       aL, rho_inv, rq);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const double v1 = y1[3 + q]; y1[q] = v1 - f0[q]; y1[3 + q] = o1.v[q] - f0[3 + q]; y1[6 + q] = o1.v[3 + q] - f0[6 + q]; y1[9 + q] = o1.v[6 + q] - f0[9 + q]; }
+    const double d2 = rms12(y1, x, atol, rtol) / h0;
+    const double dm = fmax(d1, d2);
+    const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_eighth_root(dm / 0.01);
+    if (got) {
+        double* nx = S.nx + slot;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) nx[i * TS] = x[i];
+        nx[(ND + 0) * TS] = t0; nx[(ND + 1) * TS] = tf; nx[(ND + 2) * TS] = aL; nx[(ND + 3) * TS] = rho_inv; nx[(ND + 4) * TS] = rq;
+        nx[(ND + 5) * TS] = fmin(fmin(100.0 * h0, h1), span);
+    }
+}
+
 template <bool JOINT>
 __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
     const TileSmem S = tile_smem(smem, t);
@@ -456,10 +526,12 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     long long seg = -1, ia = 0;
     int na = 0, nt = 0, status = 0;
     bool active = false, lastrej = false, last = false, have = false, exhausted = false;
+    long long nseg = -1;                                                  // successor segment claimed and staged by prepare_next()
     unsigned visit = 0;
     double2* rec = S.rec + slot;
     long long c_wait = 0, c_work = 0, c_pre = 0;
     const long long c_begin = clock64();
+    prepare_next(a, S, slot, nseg, exhausted, true);
     while (true) {
         int flags = 0, store_seg = 0;
         bool finished = false;
@@ -512,27 +584,24 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             flags |= F_STORE; store_seg = (int)seg;
             active = false;
         }
-        bool fresh = false;
-        if (!active && !exhausted) {
-            const long long idx = (long long)atomicAdd(a.counter, 1ull);
-            if (idx < a.n_seg) {
-                seg = idx; ia = lto_node_a(seg, a.npt);
-                const long long it = lto_traj_of(seg, a.npt);
+        auto take_successor = [&]() {                                    // the successor prepared by prepare_next()
+            if (!active && nseg >= 0) {
+                seg = nseg; nseg = -1; ia = lto_node_a(seg, a.npt);
+                const double* nx = S.nx + slot;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) xbuf[(xi * ND + i) * TS] = a.x0[ia * ND + i];
-                tcur = a.t0[ia]; tf = a.t1[ia];
-                if (!(tcur < tf)) tf = tcur;                              // empty span: one zero-length step, Phi = I
+                for (int i = 0; i < ND; ++i) xbuf[(xi * ND + i) * TS] = nx[i * TS];
+                tcur = nx[(ND + 0) * TS]; tf = nx[(ND + 1) * TS];
                 span = tf - tcur;
-                const double tl = a.thrustLimit_arr ? a.thrustLimit_arr[it] : a.c.thrustLimit;
-                const double rho = a.rho_arr ? a.rho_arr[it] : a.c.rho;
-                lw.aL = tl * a.c.kthr / a.c.mass;                         // :33
-                lw.rho_inv = 1.0 / rho;
-                lw.rho_inv_quarter_aL = lw.aL / (4.0 * rho);
+                lw.aL = nx[(ND + 2) * TS]; lw.rho_inv = nx[(ND + 3) * TS]; lw.rho_inv_quarter_aL = nx[(ND + 4) * TS];
+                h = nx[(ND + 5) * TS];
                 na = 0; nt = 0; status = 0; lastrej = false;
-                active = true; fresh = true; flags |= F_RESET;
-            } else {
-                exhausted = true;
+                active = true; flags |= F_RESET;
             }
+        };
+        take_successor();
+        if (!__any_sync(fullmask, active)) {                             // nobody has work (only after segments ended in error): claim on demand
+            prepare_next(a, S, slot, nseg, exhausted, true);
+            take_successor();
         }
         if (!__any_sync(fullmask, active)) {
             S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg);
@@ -546,30 +615,6 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         KStore K;
         const double* xs = xbuf + xi * ND * TS;
         state_stage_s<0>(K, xs, 0.0, 0.0, a.c, lw, rec, S.bar_full);
-        if (__any_sync(fullmask, fresh)) {
-            // Hairer-Norsett-Wanner initial step over the state components (drive_rk8 in lto_prop_generic.cuh)
-            double f0[ND], y1[ND], x[ND];
-#pragma unroll
-            for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { f0[q] = x[3 + q]; f0[3 + q] = K.kv[0][q]; f0[6 + q] = K.kl[0][q]; f0[9 + q] = K.km[0][q]; }
-            const double d0 = rms12(x, x, atol, rtol), d1 = rms12(f0, x, atol, rtol);
-            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-            h0 = fmin(h0, span);
-#pragma unroll
-            for (int i = 0; i < ND; ++i) y1[i] = fma(h0, f0[i], x[i]);
-            {
-                const double R1[3] = {y1[0], y1[1], y1[2]}, V1[3] = {y1[3], y1[4], y1[5]}, L1[3] = {y1[6], y1[7], y1[8]}, M1[3] = {y1[9], y1[10], y1[11]};
-                double kv1[3], kl1[3], km1[3];
-                sc_eval<false>(R1, V1, L1, M1, a.c, lw, kv1, kl1, km1, nullptr);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) { y1[q] = V1[q] - f0[q]; y1[3 + q] = kv1[q] - f0[3 + q]; y1[6 + q] = kl1[q] - f0[6 + q]; y1[9 + q] = km1[q] - f0[9 + q]; }
-            }
-            const double d2 = rms12(y1, x, atol, rtol) / h0;
-            const double dm = fmax(d1, d2);
-            const double h1 = (dm <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : inv_eighth_root(dm / 0.01);
-            if (fresh) h = fmin(fmin(100.0 * h0, h1), span);
-        }
         last = false;
         if (tcur + h >= tf) { h = tf - tcur; last = true; }
         if (active) ++nt;
@@ -592,6 +637,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         if (!STAGE_PIPE) mbar_arrive(S.bar_full);                        // the whole attempt's record
         c_work += clock64() - c2;
         have = true; ++visit;
+        prepare_next(a, S, slot, nseg, exhausted, last || !active);      // while the column warps work on this attempt
     }
     if (a.prof && lane == 0) {
         unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + t) * 4;
@@ -648,7 +694,7 @@ __device__ __forceinline__ TileSmem tile_smem3(unsigned char* base, int t) {
     s.rec = reinterpret_cast<double2*>(p); p += REC_BYTES;
     s.hval = reinterpret_cast<double*>(p); p += TS * sizeof(double);
     s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
-    s.cur = nullptr;
+    s.cur = nullptr; s.nx = nullptr;
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
     s.xn = reinterpret_cast<double*>(p);
     unsigned char* b = base + (size_t)NT3 * TILE3_BYTES + (size_t)t * BAR3_BYTES;

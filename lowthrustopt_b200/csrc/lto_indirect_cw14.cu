@@ -239,12 +239,16 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
     unsigned alive = (1u << NTILE) - 1u;
     unsigned visit = 0;
     unsigned par = 0;                                                   // bit (2 t + hf): which of the two buffers holds the current column
+    long long c_wait = 0, n_work = 0;
+    const long long c_begin = clock64();
     while (alive) {
 #pragma unroll 1
         for (int t = 0; t < NTILE; ++t) {
             if (!(alive & (1u << t))) continue;
             const TileSmem S = tile_smem(smem, t);
+            const long long c0 = clock64();
             mbar_wait_parked(S.bar_full, visit & 1);
+            c_wait += clock64() - c0;
             const bool done = *S.tile_done != 0;
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
@@ -282,9 +286,14 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 if (JOINT) S.errp[col * TS + slot] = es;
             }
             if (done) alive &= ~(1u << t);
-            else mbar_arrive(S.bar_done);
+            else { mbar_arrive(S.bar_done); n_work += 2; }
         }
         ++visit;
+    }
+    if (a.prof && lane == 0) {                                          // [CTA][8 warps][work, wait, count, alive]: warp 0 = state, 1..7 = columns
+        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + 1 + cw) * 4;
+        const long long tot = clock64() - c_begin;
+        o[0] = tot - c_wait; o[1] = c_wait; o[2] = n_work; o[3] = tot;
     }
 }
 
@@ -479,6 +488,8 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
     }
     bool exhausted = false;
     unsigned alive = (1u << NTILE) - 1u;
+    long long c_wait = 0, c_work = 0, c_pre = 0, n_att = 0;
+    const long long c_begin = clock64();
     while (alive) {
 #pragma unroll 1
         for (int t = 0; t < NTILE; ++t) {
@@ -489,8 +500,12 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
             double2* const rec = S.rec + slot;
             int flags = 0, store_seg = 0;
             bool finished = false;
+            const long long c0 = clock64();
+            long long c1 = c0;
             if (c.have) {
                 mbar_wait_parked(S.bar_done, (c.visit - 1) & 1);
+                c1 = clock64();
+                c_wait += c1 - c0;
                 if (c.active) {
                     double s2 = c.esum;
                     if (JOINT) {
@@ -566,6 +581,8 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
             LawConst lw; lw.tk = c.tk; lw.rho_inv = c.rho_inv; lw.rho_inv_quarter = c.rq;
             KStore K;
             const double* xs = xbuf + c.xi * ND * TS;
+            const long long c2 = clock64();
+            c_pre += c2 - c1;
             state_stage_s<0>(K, xs, 0.0, 0.0, a.c, lw, rec);
             if (__any_sync(fullmask, fresh)) {
                 double x[ND];
@@ -594,9 +611,15 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
             }
             mbar_arrive(S.bar_full);
+            c_work += clock64() - c2; ++n_att;
             c.have = true; ++c.visit;
             ctl[t] = c;
         }
+    }
+    if (a.prof && lane == 0) {
+        unsigned long long* o = a.prof + (size_t)blockIdx.x * NW * 4;
+        o[0] = c_work; o[1] = c_wait; o[2] = n_att; o[3] = clock64() - c_begin;
+        a.prof[(size_t)gridDim.x * NW * 4 + blockIdx.x] = c_pre;
     }
 }
 
