@@ -80,4 +80,34 @@ function jacobianCalc_indirect(XC_all, t_TU, nstate, n_nodes, params)
     Jac_full[:, 1:nstate] .= 0.0; Jac_full[:, (end - 2 * nstate + 1):(end - nstate)] .= 0.0   # :141-142
     Jac_full
 end
+# ---- indirect: the linear step of optimizeTraj_OLS (multiShoot_CRTBP_indirect.jl:181-182, :207) on the device.
+# `phi` is what jacobianCalc_blocks returns (m x m x (n_nodes-1)); Jac_full is never formed.
+function jacobianCalc_blocks(XC_all, t_TU, nstate, n_nodes, params)
+    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1); phi = zeros(m, m, n_nodes - 1)
+    GC.@preserve XC_all t_TU defect status phi check(ccall((:lto_indirect_defect_jac_traj, lib), Cint,
+        (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL, phi))
+    phi
+end
+function newtonUpdate(phi::Array{Float64,3}, defect::Matrix{Float64}, n_nodes, flag_adjointsOnly::Bool)
+    xc_update = zeros(12, n_nodes); status = zeros(Int32, 1)              # == reshape(xc_update2, 2*nstate, n_nodes) (:185)
+    GC.@preserve phi defect xc_update status check(ccall((:lto_indirect_newton, lib), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        handle[], 1, n_nodes, flag_adjointsOnly ? 1 : 0, phi, defect, xc_update, status))
+    xc_update
+end
+
+# ---- indirect: multiShoot_CRTBP_indirect (:58-345) for a BATCH of trajectories, iterated on the device.
+# XC_batch: 12 x n_nodes x n_traj, t_batch: n_nodes x n_traj; thrustLimit / rho: per-trajectory vectors (continuation ladders).
+function multiShoot_CRTBP_indirect_batch(XC_batch::Array{Float64,3}, t_batch::Matrix{Float64}, MU, DU, TU, mass0, thrustLimit::Vector{Float64},
+                                         flag_adjointsOnly::Bool, maxIter, p, rho::Vector{Float64})
+    n_nodes = size(XC_batch, 2); n_traj = size(XC_batch, 3)
+    XC = copy(XC_batch); defect = zeros(12, n_nodes - 1, n_traj)
+    status_flag = zeros(Int32, n_traj); iters = zeros(Int32, n_traj); er = zeros(n_traj)
+    prm = iparams((MU, DU, TU, thrustLimit[1], mass0, 1.0, p, rho[1]))
+    GC.@preserve XC t_batch thrustLimit rho defect status_flag iters er check(ccall((:lto_indirect_solve_batch, lib), Cint,
+        (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        handle[], prm, n_traj, n_nodes, maxIter, flag_adjointsOnly ? 1 : 0, XC, t_batch, thrustLimit, rho, defect, status_flag, iters, er))
+    (XC, defect, status_flag)
+end
 end # module

@@ -37,29 +37,41 @@ constexpr int NTHREADS = 32 * NW;
 
 enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };
 
-constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);
-constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2));
+constexpr int NSS = 4;            // double2 per published stage STATE: (r0,r1) (r2,lv0) (lv1,lv2) (m,-)
+constexpr size_t SST_BYTES = (size_t)13 * NSS * TS * sizeof(double2);       // stage states of one tile (state warp -> column warps)
+constexpr size_t HDR_BYTES = (size_t)TS * (4 * sizeof(double) + sizeof(int2));   // h, tk, 1/rho, 1/(4 rho), {flags, segment}
+constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);          // candidate columns, both half-phases
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);
 constexpr size_t XN_BYTES = (size_t)2 * ND * TS * sizeof(double);
-constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + ERR_BYTES + XN_BYTES;
+constexpr size_t TILE_BYTES = SST_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
+constexpr size_t LIN_BYTES = (size_t)13 * NC2 * HS * sizeof(double2);        // stage linearisations of ONE half-phase (built by the column threads)
 constexpr size_t BAR_BYTES = 64;
-constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
-constexpr size_t SCRATCH_DOUBLES_PER_CTA = (size_t)NTILE * 2 * 2 * ND * NCT;   // [tile][half][parity][component][thread]
+constexpr size_t LIN_OFFSET = NTILE * TILE_BYTES;
+constexpr size_t BAR_OFFSET = LIN_OFFSET + LIN_BYTES;
+constexpr size_t SMEM = BAR_OFFSET + NTILE * BAR_BYTES;
+static_assert(SMEM <= 232448, "shared-memory plan exceeds 227 KB");
+constexpr size_t SCRATCH_DOUBLES_PER_CTA = (size_t)NTILE * 2 * ND * NCT;    // current columns: [tile][half][component][thread]
+constexpr int NLIN = 13 * HS;     // (stage, slot) linearisation items per half-phase: 208 <= 224 column threads
+static_assert(NLIN <= NCT, "one linearisation item per column thread");
 
 struct TileSmem {
-    double2* rec; double* hval; int2* hctl; double* errp; double* xn;
+    double2* sst; double* hval; double* tk; double* rho_inv; double* rq; int2* hctl; double* cur; double* errp; double* xn;
     unsigned bar_full, bar_done; volatile int* tile_done;
 };
 
 __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
     unsigned char* p = base + (size_t)t * TILE_BYTES;
     TileSmem s;
-    s.rec = reinterpret_cast<double2*>(p); p += REC_BYTES;
+    s.sst = reinterpret_cast<double2*>(p); p += SST_BYTES;
     s.hval = reinterpret_cast<double*>(p); p += TS * sizeof(double);
+    s.tk = reinterpret_cast<double*>(p); p += TS * sizeof(double);
+    s.rho_inv = reinterpret_cast<double*>(p); p += TS * sizeof(double);
+    s.rq = reinterpret_cast<double*>(p); p += TS * sizeof(double);
     s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
+    s.cur = reinterpret_cast<double*>(p); p += CUR_BYTES;
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
     s.xn = reinterpret_cast<double*>(p);
-    unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * BAR_BYTES;
+    unsigned char* b = base + BAR_OFFSET + (size_t)t * BAR_BYTES;
     s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 8);
     s.tile_done = reinterpret_cast<volatile int*>(b + 16);
     return s;
@@ -184,11 +196,11 @@ template <int J>
 __device__ __forceinline__ void col_stage(KStore& K, const double (&p)[ND], double h, double h2, double w2, const double2* __restrict__ rec) {
     double R[3], V[3], L[3], M[3], Q;
     stage_input<J>(K, p, h, h2, R, V, L, M, Q);
-    const double2* w = rec + J * NC2 * TS;
+    const double2* w = rec + J * NC2 * HS;
     double U[6], W[6];
-    { const double2 a = w[0 * TS], b = w[1 * TS], c = w[2 * TS]; U[0] = a.x; U[1] = a.y; U[2] = b.x; U[3] = b.y; U[4] = c.x; U[5] = c.y; }
-    { const double2 a = w[3 * TS], b = w[4 * TS], c = w[5 * TS]; W[0] = a.x; W[1] = a.y; W[2] = b.x; W[3] = b.y; W[4] = c.x; W[5] = c.y; }
-    const double2 g0 = w[6 * TS], g1 = w[7 * TS], g2 = w[8 * TS], g3 = w[9 * TS], g4 = w[10 * TS];
+    { const double2 a = w[0 * HS], b = w[1 * HS], c = w[2 * HS]; U[0] = a.x; U[1] = a.y; U[2] = b.x; U[3] = b.y; U[4] = c.x; U[5] = c.y; }
+    { const double2 a = w[3 * HS], b = w[4 * HS], c = w[5 * HS]; W[0] = a.x; W[1] = a.y; W[2] = b.x; W[3] = b.y; W[4] = c.x; W[5] = c.y; }
+    const double2 g0 = w[6 * HS], g1 = w[7 * HS], g2 = w[8 * HS], g3 = w[9 * HS], g4 = w[10 * HS];
     const double lh[3] = {g0.x, g0.y, g1.x};
     const double uon = g1.y, cd = g2.x, cgm = g2.y, cml = g3.x, clml = g3.y, mm = g4.x, lmm = g4.y;
     const double qd = fma(lh[0], M[0], fma(lh[1], M[1], lh[2] * M[2]));
@@ -230,72 +242,7 @@ __device__ __forceinline__ double col_attempt(const double (&p)[ND], double h, d
 }
 
 template <bool JOINT>
-__device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int lane, unsigned char* smem) {
-    const int col = 2 * cw + (lane >> 4);
-    const int ct = cw * 32 + lane;
-    const double w2 = 2.0 * a.c.omega;
-    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
-    double* const scr = a.scratch + (size_t)blockIdx.x * SCRATCH_DOUBLES_PER_CTA + ct;
-    unsigned alive = (1u << NTILE) - 1u;
-    unsigned visit = 0;
-    unsigned par = 0;                                                   // bit (2 t + hf): which of the two buffers holds the current column
-    long long c_wait = 0, n_work = 0;
-    const long long c_begin = clock64();
-    while (alive) {
-#pragma unroll 1
-        for (int t = 0; t < NTILE; ++t) {
-            if (!(alive & (1u << t))) continue;
-            const TileSmem S = tile_smem(smem, t);
-            const long long c0 = clock64();
-            mbar_wait_parked(S.bar_full, visit & 1);
-            c_wait += clock64() - c0;
-            const bool done = *S.tile_done != 0;
-#pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
-                const int slot = hf * HS + (lane & (HS - 1));
-                const int2 hc = S.hctl[slot];
-                const double h = S.hval[slot];
-                const unsigned bit = 1u << (2 * t + hf);
-                if (hc.x & F_ACCEPT) par ^= bit;                       // the candidate of the previous attempt is the column now
-                double* const b0 = scr + (size_t)((t * 2 + hf) * 2) * ND * NCT;
-                double* const cur = b0 + ((par & bit) ? (size_t)ND * NCT : 0);
-                double* const cand = b0 + ((par & bit) ? 0 : (size_t)ND * NCT);
-                double p[ND];
-                if ((hc.x & F_STORE) || ((hc.x & F_ACTIVE) && !(hc.x & F_RESET))) {
-#pragma unroll
-                    for (int i = 0; i < ND; ++i) p[i] = __ldcg(cur + i * NCT);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < ND; ++i) p[i] = 0.0;
-                }
-                if (hc.x & F_STORE) {                                  // column `col` of ForwardDiff.jacobian(f, x0) (:121)
-                    double* out = a.phi + (long long)hc.y * (ND * ND) + col * ND;
-#pragma unroll
-                    for (int i = 0; i < ND; i += 2)
-                        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(out + i), "d"(p[i]), "d"(p[i + 1]) : "memory");
-                }
-                if (hc.x & F_RESET) {
-#pragma unroll
-                    for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; __stcg(cur + i * NCT, p[i]); }
-                }
-                if (done) continue;
-                double pn[ND];
-                const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, atol, rtol, pn);
-#pragma unroll
-                for (int i = 0; i < ND; ++i) __stcg(cand + i * NCT, pn[i]);
-                if (JOINT) S.errp[col * TS + slot] = es;
-            }
-            if (done) alive &= ~(1u << t);
-            else { mbar_arrive(S.bar_done); n_work += 2; }
-        }
-        ++visit;
-    }
-    if (a.prof && lane == 0) {                                          // [CTA][8 warps][work, wait, count, alive]: warp 0 = state, 1..7 = columns
-        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + 1 + cw) * 4;
-        const long long tot = clock64() - c_begin;
-        o[0] = tot - c_wait; o[1] = c_wait; o[2] = n_work; o[3] = tot;
-    }
-}
+__device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int lane, unsigned char* smem);
 
 // ---------------------------------------------------------------------------
 // State warp: the 14-dim right-hand side and its linearisation (lto_math.cuh sc_stage<14> is the reference
@@ -368,33 +315,33 @@ __device__ __forceinline__ void sc_eval(const double (&R)[3], const double (&V)[
         const double ee = e1 + e2, hs = h1 + h2;
         const double hx = fma(h1, dx1, h2 * dx2);
         const double sM0 = s5 * M[0];
-        w[0 * TS] = make_double2(U[0], U[1]);
-        w[1 * TS] = make_double2(U[2], U[3]);
-        w[2 * TS] = make_double2(U[4], U[5]);
-        w[3 * TS] = make_double2(fma(h1 * dx1, dx1, fma(h2 * dx2, dx2, fma(2.0 * t, M[0], ee))),
+        w[0 * HS] = make_double2(U[0], U[1]);
+        w[1 * HS] = make_double2(U[2], U[3]);
+        w[2 * HS] = make_double2(U[4], U[5]);
+        w[3 * HS] = make_double2(fma(h1 * dx1, dx1, fma(h2 * dx2, dx2, fma(2.0 * t, M[0], ee))),
                                  fma(hs * R[1], R[1], fma(2.0 * s5 * R[1], M[1], ee)));
-        w[4 * TS] = make_double2(fma(hs * R[2], R[2], fma(2.0 * s5 * R[2], M[2], ee)),
+        w[4 * HS] = make_double2(fma(hs * R[2], R[2], fma(2.0 * s5 * R[2], M[2], ee)),
                                  fma(hx, R[1], fma(t, M[1], sM0 * R[1])));
-        w[5 * TS] = make_double2(fma(hx, R[2], fma(t, M[2], sM0 * R[2])),
+        w[5 * HS] = make_double2(fma(hx, R[2], fma(t, M[2], sM0 * R[2])),
                                  fma(hs * R[1], R[2], s5 * fma(R[1], M[2], M[1] * R[2])));
-        w[6 * TS] = make_double2(l0, l1);
-        w[7 * TS] = make_double2(l2, uon);
-        w[8 * TS] = make_double2(cd, -dm);                                              // cd, cgm
-        w[9 * TS] = make_double2(-c.cm * Q * dn, -fma(dn, n, umag) * im);               // cml, clml
-        w[10 * TS] = make_double2(-c.cm * fma(Q, dm, umag), fma(-n, dm, umag * n * im) * im);   // mm, lmm
+        w[6 * HS] = make_double2(l0, l1);
+        w[7 * HS] = make_double2(l2, uon);
+        w[8 * HS] = make_double2(cd, -dm);                                              // cd, cgm
+        w[9 * HS] = make_double2(-c.cm * Q * dn, -fma(dn, n, umag) * im);               // cml, clml
+        w[10 * HS] = make_double2(-c.cm * fma(Q, dm, umag), fma(-n, dm, umag * n * im) * im);   // mm, lmm
     }
 }
 
 struct Out11 { double v[11]; };
+// The state warp evaluates the right-hand side only; the linearisation is built by the column threads (sc_lin below).
 __device__ __noinline__ Out11 sc_eval_call(double r0, double r1, double r2, double v0, double v1, double v2, double l0, double l1, double l2,
                                            double m0, double m1, double m2, double q, double mu, double mu1, double omega, double pexp, double cm,
-                                           double tk, double rho_inv, double rq, double2* w) {
+                                           double tk, double rho_inv, double rq) {
     const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, v2}, L[3] = {l0, l1, l2}, M[3] = {m0, m1, m2};
     SCConst c; c.mu = mu; c.m1 = mu1; c.omega = omega; c.p = pexp; c.cm = cm;
     LawConst lw; lw.tk = tk; lw.rho_inv = rho_inv; lw.rho_inv_quarter = rq;
     double kv[3], kl[3], km[3], kq, klm;
-    if (w) sc_eval<true>(R, V, L, M, q, c, lw, kv, kl, km, kq, klm, w);
-    else sc_eval<false>(R, V, L, M, q, c, lw, kv, kl, km, kq, klm, nullptr);
+    sc_eval<false>(R, V, L, M, q, c, lw, kv, kl, km, kq, klm, nullptr);
     Out11 o;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { o.v[i] = kv[i]; o.v[3 + i] = kl[i]; o.v[6 + i] = km[i]; }
@@ -402,13 +349,102 @@ __device__ __noinline__ Out11 sc_eval_call(double r0, double r1, double r2, doub
     return o;
 }
 
+// One (stage, slot) item of the linearisation phase: stage state (r, lv, m) -> the 22-double record the column arithmetic uses.
+__device__ __forceinline__ void sc_lin(const double2* __restrict__ sst, const SCConst& c, const LawConst& lw, double2* __restrict__ w) {
+    const double2 a0 = sst[0 * TS], a1 = sst[1 * TS], a2 = sst[2 * TS], a3 = sst[3 * TS];
+    const double R[3] = {a0.x, a0.y, a1.x}, M[3] = {a1.y, a2.x, a2.y}, Z[3] = {0.0, 0.0, 0.0};
+    double kv[3], kl[3], km[3], kq, klm;                                // right-hand-side values: unused here, eliminated by the compiler
+    sc_eval<true>(R, Z, Z, M, a3.x, c, lw, kv, kl, km, kq, klm, w);
+}
+
+template <bool JOINT>
+__device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int lane, unsigned char* smem) {
+    const int col = 2 * cw + (lane >> 4);
+    const int ct = cw * 32 + lane;
+    const double w2 = 2.0 * a.c.omega;
+    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
+    double* const cur_base = a.scratch + (size_t)blockIdx.x * SCRATCH_DOUBLES_PER_CTA + ct;   // current (last accepted) columns, L2 resident
+    double2* const lin = reinterpret_cast<double2*>(smem + LIN_OFFSET);
+    const int lstage = ct >> 4, ls16 = ct & (HS - 1);                   // this thread's (stage, slot) item of the linearisation phase
+    unsigned alive = (1u << NTILE) - 1u;
+    unsigned visit = 0;
+    long long c_wait = 0, n_work = 0;
+    const long long c_begin = clock64();
+    while (alive) {
+#pragma unroll 1
+        for (int t = 0; t < NTILE; ++t) {
+            if (!(alive & (1u << t))) continue;
+            const TileSmem S = tile_smem(smem, t);
+            const long long c0 = clock64();
+            mbar_wait_parked(S.bar_full, visit & 1);
+            c_wait += clock64() - c0;
+            const bool done = *S.tile_done != 0;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                const int slot = hf * HS + (lane & (HS - 1));
+                const int2 hc = S.hctl[slot];
+                const double h = S.hval[slot];
+                double* sc = S.cur + (size_t)hf * ND * NCT + ct;       // candidate of the previous attempt (shared memory)
+                double* sn = cur_base + (size_t)(t * 2 + hf) * ND * NCT;
+                double p[ND];
+                if (hc.x & F_ACCEPT) {                                 // an accepted step reads shared memory and refreshes the L2 copy
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) { p[i] = sc[i * NCT]; __stcg(sn + i * NCT, p[i]); }
+                } else {                                               // a rejected one reloads the last accepted column
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) p[i] = __ldcg(sn + i * NCT);
+                }
+                if (hc.x & F_STORE) {                                  // column `col` of ForwardDiff.jacobian(f, x0) (:121)
+                    double* out = a.phi + (long long)hc.y * (ND * ND) + col * ND;
+#pragma unroll
+                    for (int i = 0; i < ND; i += 2)
+                        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(out + i), "d"(p[i]), "d"(p[i + 1]) : "memory");
+                }
+                if (hc.x & F_RESET) {
+#pragma unroll
+                    for (int i = 0; i < ND; ++i) { p[i] = (i == col) ? 1.0 : 0.0; __stcg(sn + i * NCT, p[i]); }
+                }
+                if (done) continue;
+                // ---- linearisation phase: one (stage, slot) record per thread, straight from the state warp's stage states
+                if (ct < NLIN) {
+                    const int lslot = hf * HS + ls16;
+                    LawConst lw; lw.tk = S.tk[lslot]; lw.rho_inv = S.rho_inv[lslot]; lw.rho_inv_quarter = S.rq[lslot];
+                    sc_lin(S.sst + lstage * NSS * TS + lslot, a.c, lw, lin + lstage * NC2 * HS + ls16);
+                }
+                LTO_ICW14_LOCKSTEP();                                  // the half-phase's records are complete
+                double pn[ND];
+                const double es = col_attempt<JOINT>(p, h, w2, lin + (lane & (HS - 1)), atol, rtol, pn);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) sc[i * NCT] = pn[i];
+                if (JOINT) S.errp[col * TS + slot] = es;
+                LTO_ICW14_LOCKSTEP();                                  // all reads of the records done before the next phase rewrites them
+            }
+            if (done) alive &= ~(1u << t);
+            else { mbar_arrive(S.bar_done); n_work += 2; }
+        }
+        ++visit;
+    }
+    if (a.prof && lane == 0) {                                          // [CTA][8 warps][work, wait, count, alive]: warp 0 = state, 1..7 = columns
+        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + 1 + cw) * 4;
+        const long long tot = clock64() - c_begin;
+        o[0] = tot - c_wait; o[1] = c_wait; o[2] = n_work; o[3] = tot;
+    }
+}
+
 template <int J>
 __device__ __forceinline__ void state_stage(KStore& K, const double (&x)[ND], double h, double h2, const SCConst& c, const LawConst& lw,
-                                            double2* __restrict__ rec) {
+                                            double2* __restrict__ sst) {
     double R[3], V[3], L[3], M[3], Q;
     stage_input<J>(K, x, h, h2, R, V, L, M, Q);
+    if (sst) {                                                         // stage state for the column warps' linearisation phase
+        double2* w = sst + J * NSS * TS;
+        w[0 * TS] = make_double2(R[0], R[1]);
+        w[1 * TS] = make_double2(R[2], M[0]);
+        w[2 * TS] = make_double2(M[1], M[2]);
+        w[3 * TS] = make_double2(Q, 0.0);
+    }
     const Out11 o = sc_eval_call(R[0], R[1], R[2], V[0], V[1], V[2], L[0], L[1], L[2], M[0], M[1], M[2], Q, c.mu, c.m1, c.omega, c.p, c.cm,
-                                 lw.tk, lw.rho_inv, lw.rho_inv_quarter, rec ? rec + J * NC2 * TS : nullptr);
+                                 lw.tk, lw.rho_inv, lw.rho_inv_quarter);
 #pragma unroll
     for (int q = 0; q < 3; ++q) { K.kv[J][q] = o.v[q]; K.kl[J][q] = o.v[3 + q]; K.km[J][q] = o.v[6 + q]; }
     K.kq[J] = o.v[9];
@@ -417,11 +453,11 @@ __device__ __forceinline__ void state_stage(KStore& K, const double (&x)[ND], do
 
 template <int J>
 __device__ __forceinline__ void state_stage_s(KStore& K, const double* __restrict__ xs, double h, double h2, const SCConst& c, const LawConst& lw,
-                                              double2* __restrict__ rec) {
+                                              double2* __restrict__ sst) {
     double x[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-    state_stage<J>(K, x, h, h2, c, lw, rec);
+    state_stage<J>(K, x, h, h2, c, lw, sst);
 }
 
 __device__ __forceinline__ double rms14(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
@@ -446,7 +482,7 @@ __device__ __forceinline__ double initial_step(const KStore& K, const double (&x
     {
         const double R1[3] = {y1[0], y1[1], y1[2]}, V1[3] = {y1[3], y1[4], y1[5]}, L1[3] = {y1[7], y1[8], y1[9]}, M1[3] = {y1[10], y1[11], y1[12]};
         const Out11 o = sc_eval_call(R1[0], R1[1], R1[2], V1[0], V1[1], V1[2], L1[0], L1[1], L1[2], M1[0], M1[1], M1[2], y1[6], c.mu, c.m1, c.omega,
-                                     c.p, c.cm, lw.tk, lw.rho_inv, lw.rho_inv_quarter, nullptr);
+                                     c.p, c.cm, lw.tk, lw.rho_inv, lw.rho_inv_quarter);
 #pragma unroll
         for (int q = 0; q < 3; ++q) { y1[q] = V1[q] - f0[q]; y1[3 + q] = o.v[q] - f0[3 + q]; y1[7 + q] = o.v[3 + q] - f0[7 + q]; y1[10 + q] = o.v[6 + q] - f0[10 + q]; }
         y1[6] = o.v[9] - f0[6]; y1[13] = o.v[10] - f0[13];
@@ -497,7 +533,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
             const TileSmem S = tile_smem(smem, t);
             SlotCtl c = ctl[t];
             double* const xbuf = S.xn + slot;
-            double2* const rec = S.rec + slot;
+            double2* const rec = S.sst + slot;
             int flags = 0, store_seg = 0;
             bool finished = false;
             const long long c0 = clock64();
@@ -596,6 +632,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
             if (c.active) ++c.nt;
             const double h = c.h;
             S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (c.active ? F_ACTIVE : 0), store_seg);
+            S.tk[slot] = c.tk; S.rho_inv[slot] = c.rho_inv; S.rq[slot] = c.rq;
             const double h2 = h * h;
             state_stage_s<1>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<2>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<3>(K, xs, h, h2, a.c, lw, rec);
             state_stage_s<4>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<5>(K, xs, h, h2, a.c, lw, rec);  state_stage_s<6>(K, xs, h, h2, a.c, lw, rec);
