@@ -29,7 +29,9 @@ sys.path.insert(0, ROOT)
 
 # Algorithmic FLOPs per unit (sparsity-exploiting minimal formulation; DESIGN.md "Measurement")
 FLOPS_PER_SEG = {"direct7": 284040.0, "direct6": 217836.0}
-FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 55000.0}
+# ndim 14: 13 stages x (240 state + 14 columns x 82) + RK combinations 2*75*210 + error 10*210, minus the
+# beta-combinations of the 15 lm components (pure quadratures: 15 x 134) = 18,044 + 31,590
+FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 49634.0}
 # Algorithmic HBM bytes per unit
 BYTES_PER_SEG = {"direct7": 1360.0, "direct6": (2 * 6 + 6 + 2 + 6 + 1 + 6 * 18) * 8.0, 12: 1360.0, 14: 1808.0}
 

@@ -100,22 +100,33 @@ __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
 // ---------------------------------------------------------------------------
 struct KStore { double kv[13][3], kl[13][3], km[13][3]; };
 
-template <int J>
+template <int J, bool SPLIT = false>
 __device__ __forceinline__ void stage_input(const KStore& K, const double (&y)[ND], double h, double h2,
                                             double (&R)[3], double (&V)[3], double (&L)[3], double (&M)[3]) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         if (J == 0) { R[q] = y[q]; V[q] = y[3 + q]; L[q] = y[6 + q]; M[q] = y[9 + q]; continue; }
-        double av = 0.0, ar = 0.0, al = 0.0, am = 0.0;
+        // SPLIT (state warps): two partial sums per combination (even / odd stage index) halve the dependent-FMA depth of the chain
+        double av = 0.0, ar = 0.0, al = 0.0, am = 0.0, bv = 0.0, br = 0.0, bl = 0.0, bm = 0.0;
 #pragma unroll
         for (int l = 0; l < J; ++l) {
-            if (lto_tab::Bf(J, l) != 0.0) {
-                av = fma(lto_tab::Bf(J, l), K.kv[l][q], av);
-                al = fma(lto_tab::Bf(J, l), K.kl[l][q], al);
-                am = fma(lto_tab::Bf(J, l), K.km[l][q], am);
+            if (SPLIT && (l & 1)) {
+                if (lto_tab::Bf(J, l) != 0.0) {
+                    bv = fma(lto_tab::Bf(J, l), K.kv[l][q], bv);
+                    bl = fma(lto_tab::Bf(J, l), K.kl[l][q], bl);
+                    bm = fma(lto_tab::Bf(J, l), K.km[l][q], bm);
+                }
+                if (lto_tab::Gf(J, l) != 0.0) br = fma(lto_tab::Gf(J, l), K.kv[l][q], br);
+            } else {
+                if (lto_tab::Bf(J, l) != 0.0) {
+                    av = fma(lto_tab::Bf(J, l), K.kv[l][q], av);
+                    al = fma(lto_tab::Bf(J, l), K.kl[l][q], al);
+                    am = fma(lto_tab::Bf(J, l), K.km[l][q], am);
+                }
+                if (lto_tab::Gf(J, l) != 0.0) ar = fma(lto_tab::Gf(J, l), K.kv[l][q], ar);
             }
-            if (lto_tab::Gf(J, l) != 0.0) ar = fma(lto_tab::Gf(J, l), K.kv[l][q], ar);
         }
+        if (SPLIT) { av += bv; ar += br; al += bl; am += bm; }
         V[q] = fma(h, av, y[3 + q]);
         R[q] = fma(h2, ar, fma(h * lto_tab::Cf(J), y[3 + q], y[q]));
         L[q] = fma(h, al, y[6 + q]);
