@@ -80,10 +80,12 @@ int lto_init(int device, lto_handle** out) {
     h->device = device; h->n_sm = prop.multiProcessorCount;
     CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     CK(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     CK(h, cudaEventCreate(&h->ev_t0));
     CK(h, cudaEventCreate(&h->ev_t1));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
     CK(h, cudaMalloc((void**)&h->d_ctr, 256));
     if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
     *out = h;
@@ -116,7 +118,7 @@ void lto_destroy(lto_handle* h) {
     if (!h) return;
     if (h->n_child > 0) { for (int i = 0; i < h->n_child; ++i) lto_destroy(h->child[i]); free(h); return; }
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy);
+    cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy); cudaStreamSynchronize(h->s_h2d);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ctr) cudaFree(h->d_ctr);
@@ -124,9 +126,9 @@ void lto_destroy(lto_handle* h) {
     if (h->d_prof) cudaFree(h->d_prof);
     if (h->d_nwt) cudaFree(h->d_nwt);
     if (h->d_slv) cudaFree(h->d_slv);
-    for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev_chunk[i]);
+    for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev_chunk[i]); cudaEventDestroy(h->ev_h2d[i]); }
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
-    cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy);
+    cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_h2d);
     free(h);
 }
 
@@ -307,26 +309,31 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
     char* dq = (char*)h->d_out;
     double* dD = (double*)dq; dq += bD; double* dE = (double*)dq; dq += bE; int32_t* dS = (int32_t*)dq; dq += bS;
     double* dJ = want_jac ? (double*)dq : nullptr;
-    // ---- H2D
-    CK(h, cudaMemcpyAsync(dXa, Xa, rows * NS * 8, cudaMemcpyHostToDevice, h->s_copy));
-    CK(h, cudaMemcpyAsync(dua, ua, rows * 3 * 8, cudaMemcpyHostToDevice, h->s_copy));
-    CK(h, cudaMemcpyAsync(dta, ta, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
-    if (npt == 0) {
-        CK(h, cudaMemcpyAsync(dXb, Xb, rows * NS * 8, cudaMemcpyHostToDevice, h->s_copy));
-        CK(h, cudaMemcpyAsync(dub, ub, rows * 3 * 8, cudaMemcpyHostToDevice, h->s_copy));
-        CK(h, cudaMemcpyAsync(dtb, tb, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
-    }
-    CK(h, cudaEventRecord(h->ev_in, h->s_copy));
-    CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_in, 0));
+    // ---- H2D goes chunk by chunk on its own stream (below): the first kernel starts after the first chunk's inputs have
+    // arrived, and host->device and device->host transfers run on different copy engines
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
     // ---- chunked compute + D2H pipeline
     const size_t per_seg = (size_t)NS * 8 + 8 + 4 + (want_jac ? (size_t)NS * NV * 8 : 0);
     long long chunk = pick_chunk(n_seg, per_seg);
     if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }   // whole trajectories
     int ci = 0;
-    for (long long s0 = 0; s0 < n_seg; s0 += chunk, ++ci) {
-        const long long ns = std::min(chunk, n_seg - s0);
+    long long ns = 0;
+    for (long long s0 = 0; s0 < n_seg; s0 += ns, ++ci) {
+        ns = std::min(chunk, n_seg - s0);
         const long long r0 = lto_node_a(s0, npt);
+        {   // this chunk's input rows (trajectory form: whole trajectories, n_nodes rows each)
+            const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+            CK(h, cudaMemcpyAsync(dXa + r0 * NS, Xa + r0 * NS, nr * NS * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpyAsync(dua + r0 * 3, ua + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpyAsync(dta + r0, ta + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            if (npt == 0) {
+                CK(h, cudaMemcpyAsync(dXb + r0 * NS, Xb + r0 * NS, nr * NS * 8, cudaMemcpyHostToDevice, h->s_h2d));
+                CK(h, cudaMemcpyAsync(dub + r0 * 3, ub + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
+                CK(h, cudaMemcpyAsync(dtb + r0, tb + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            }
+            CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
+            CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
+        }
         a.Xa = dXa + r0 * NS; a.Xb = dXb + r0 * NS; a.ua = dua + r0 * 3; a.ub = dub + r0 * 3; a.ta = dta + r0; a.tb = dtb + r0;
         a.defect = dD + s0 * NS; a.errors = dE + s0; a.status = dS + s0; a.jac = want_jac ? dJ + s0 * NS * NV : nullptr;
         a.n_seg = ns; a.npt = npt;
@@ -389,23 +396,28 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     double* dD = (double*)dq; dq += bD; int32_t* dS = (int32_t*)dq; dq += bS; int32_t* dN = (int32_t*)dq; dq += bN;
     double* dJ = want_jac ? (double*)dq : nullptr;
     if (want_jac) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, indirect_cw_scratch_bytes(h->n_sm)); if (rc) return rc; }
-    CK(h, cudaMemcpyAsync(dX, x0, rows * ND * 8, cudaMemcpyHostToDevice, h->s_copy));
-    CK(h, cudaMemcpyAsync(dT0, t0, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
-    if (npt == 0) CK(h, cudaMemcpyAsync(dT1, t1, rows * 8, cudaMemcpyHostToDevice, h->s_copy));
-    if (sep_target) CK(h, cudaMemcpyAsync(dXT, x_target, rows * ND * 8, cudaMemcpyHostToDevice, h->s_copy));
-    if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_copy));
-    if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_copy));
-    CK(h, cudaEventRecord(h->ev_in, h->s_copy));
-    CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_in, 0));
+    // per-trajectory / per-segment parameter arrays are small: up front; the node data goes chunk by chunk (below)
+    if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
+    if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
     const size_t per_seg = (size_t)ND * 8 + 12 + (want_jac ? (size_t)ND * ND * 8 : 0);
     long long chunk = pick_chunk(n_seg, per_seg);
     if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }
     int ci = 0;
-    for (long long s0 = 0; s0 < n_seg; s0 += chunk, ++ci) {
-        const long long ns = std::min(chunk, n_seg - s0);
+    long long ns = 0;
+    for (long long s0 = 0; s0 < n_seg; s0 += ns, ++ci) {
+        ns = std::min(chunk, n_seg - s0);
         const long long r0 = lto_node_a(s0, npt);
         const long long p0 = lto_traj_of(s0, npt);
+        {
+            const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+            CK(h, cudaMemcpyAsync(dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpyAsync(dT0 + r0, t0 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            if (npt == 0) CK(h, cudaMemcpyAsync(dT1 + r0, t1 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            if (sep_target) CK(h, cudaMemcpyAsync(dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
+            CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
+        }
         a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
         a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
         a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;

@@ -12,9 +12,9 @@ static const size_t LTO_PROF_WORDS = 8192;
 struct lto_handle {
     int device;
     int n_sm;
-    cudaStream_t s_compute, s_copy;
+    cudaStream_t s_compute, s_copy, s_h2d;          // kernels; device->host (and peer pushes); host->device
     cudaEvent_t ev_in, ev_t0, ev_t1;
-    cudaEvent_t ev_chunk[8];
+    cudaEvent_t ev_chunk[8], ev_h2d[8];
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
     unsigned long long* d_ctr;
