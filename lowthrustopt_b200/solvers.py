@@ -3,7 +3,7 @@
 
     multiShoot_CRTBP_direct      src/multiShoot_CRTBP_direct.jl:58-594
     multiShoot_CRTBP_indirect    src/multiShoot_CRTBP_indirect.jl:58-345
-    reduceFuel_indirect          src/HelperFunctions.jl:105-193
+    reduceFuel_indirect          src/HelperFunctions.jl:105-193   (+ reduceFuel_indirect_batch: many trajectories, one device call per round)
     trajectory_stack_guess       CRTBP_Multishoot_direct_demo.jl:117-157
 
 Same names, argument order and return values.  Arrays use the reference's shapes
@@ -387,26 +387,19 @@ def multiShoot_CRTBP_indirect_batch(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, th
     return r["XC_all"].transpose(0, 2, 1).copy(), r["defect"].transpose(0, 2, 1).copy(), r["status_flag"], r["iters"]
 
 
-def reduceFuel_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rho_current, rho_target, backend=None, rng=None,
-                        log=None):
-    """rho-continuation driver (HelperFunctions.jl:105-193).  `rng` supplies the rand() of the back-off (:182)."""
-    rng = rng or np.random.default_rng(0)
+def _reduceFuel_steps(XC_all, rho_current, rho_target, rng):
+    """The rho-continuation ladder of reduceFuel_indirect (HelperFunctions.jl:105-193) as a coroutine: yields (XC_start, rho) for
+    every call of multiShoot_CRTBP_indirect it wants (maxIter = 10, p = 1) and is sent back (XC_new, defect, status); returns the
+    function's result.  Shared by the one-trajectory mirror and the batched driver, so both follow the reference line by line."""
     if rho_target > rho_current:
         rho_target = rho_current
-    p = 1.0; rho_temp = rho_current; maxIter = 10
-
-    def run(XC, rho):
-        out = multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, False, False, maxIter, p, rho, backend=backend)
-        if log is not None:
-            log.append(dict(rho=rho, status=out[2], er=float(np.max(np.abs(out[1])))))
-        return out
-
-    XC_new, defect, status = run(XC_all, rho_temp)
+    rho_temp = rho_current
+    XC_new, defect, status = yield XC_all, rho_temp
     if status == 0 and rho_current == rho_target:
         return XC_new, defect, status
     while status != 0 and rho_temp < 1:                                                                   # :131-141
         rho_temp = min(rho_temp * 5, 1.0)
-        XC_new, defect, status = run(XC_all, rho_temp)
+        XC_new, defect, status = yield XC_all, rho_temp
     if rho_temp == 1 and status != 0:
         return XC_new, defect, status
     if status == 0:
@@ -420,9 +413,58 @@ def reduceFuel_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rh
             XC_all = XC_new.copy()
             rho_temp = max(rho_temp / 2, rho_target)
         else:
-            rho_temp *= 3 * (1 + rng.random())
-        XC_new, defect, status = run(XC_all, rho_temp)
+            rho_temp *= 3 * (1 + rng.random())                                                            # :182
+        XC_new, defect, status = yield XC_all, rho_temp
     return XC_new, defect, status
+
+
+def reduceFuel_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rho_current, rho_target, backend=None, rng=None,
+                        log=None):
+    """rho-continuation driver (HelperFunctions.jl:105-193).  `rng` supplies the rand() of the back-off (:182)."""
+    gen = _reduceFuel_steps(np.array(XC_all, dtype=np.float64), rho_current, rho_target, rng or np.random.default_rng(0))
+    req = next(gen)
+    while True:
+        XC, rho = req
+        out = multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, False, False, 10, 1.0, rho, backend=backend)
+        if log is not None:
+            log.append(dict(rho=rho, status=out[2], er=float(np.max(np.abs(out[1])))))
+        try:
+            req = gen.send(out)
+        except StopIteration as fin:
+            return fin.value
+
+
+def reduceFuel_indirect_batch(XC_all, t_TU, MU, DU, TU, n_nodes, mass, thrustLimit, rho_current, rho_target, backend=None, rngs=None,
+                              log=None):
+    """reduceFuel_indirect for a BATCH of independent trajectories: every trajectory walks its own rho ladder
+    (halving on success, x 3(1 + rand) back-off on failure, :155-187); each round, the solver calls all unfinished trajectories
+    ask for are issued as ONE lto_indirect_solve_batch call with per-trajectory rho / thrustLimit.
+    XC_all: (n_traj, 12, n_nodes); t_TU: (n_traj, n_nodes); thrustLimit, rho_current, rho_target: scalars or (n_traj,).
+    Returns (XC_new (n_traj, 12, n_nodes), defect (n_traj, 12, n_nodes-1), status (n_traj,), rounds)."""
+    be = backend or default_backend()
+    XC_all = np.asarray(XC_all, dtype=np.float64); t_TU = np.asarray(t_TU, dtype=np.float64)
+    T = XC_all.shape[0]
+    tl = np.broadcast_to(np.asarray(thrustLimit, dtype=np.float64), (T,)).copy()
+    r0 = np.broadcast_to(np.asarray(rho_current, dtype=np.float64), (T,)); r1 = np.broadcast_to(np.asarray(rho_target, dtype=np.float64), (T,))
+    rngs = rngs or [np.random.default_rng(j) for j in range(T)]
+    gens = [_reduceFuel_steps(XC_all[j].copy(), float(r0[j]), float(r1[j]), rngs[j]) for j in range(T)]
+    req = {j: next(gens[j]) for j in range(T)}
+    res = [None] * T
+    rounds = 0
+    while req:
+        rounds += 1
+        idx = sorted(req)
+        XC = np.stack([req[j][0] for j in idx]); rho = np.array([req[j][1] for j in idx])
+        Xn, dn, st, it = multiShoot_CRTBP_indirect_batch(XC, t_TU[idx], MU, DU, TU, n_nodes, mass, tl[idx], False, 10, 1.0, rho, backend=be)
+        if log is not None:
+            log.append(dict(round=rounds, n=len(idx), rho=rho.copy(), status=np.asarray(st).copy()))
+        for k, j in enumerate(idx):
+            try:
+                req[j] = gens[j].send((Xn[k], dn[k], int(st[k])))
+            except StopIteration as fin:
+                res[j] = fin.value
+                del req[j]
+    return (np.stack([r[0] for r in res]), np.stack([r[1] for r in res]), np.array([r[2] for r in res], dtype=np.int32), rounds)
 
 
 def demo_fixtures():

@@ -58,3 +58,16 @@ class OracleBackend:
     def propagate(self, x0, t0, t1, params):
         self.calls += 1
         return O.indirect_prop(x0, t0, t1, self._ip(params), nthreads=self.nt)[0]
+
+    def indirect_solve_batch(self, XC, t, params, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False):
+        """Stand-in for lto_indirect_solve_batch on a machine without a GPU: the host loop, one trajectory after the other."""
+        from lowthrustopt_b200 import solvers as S
+        MU, DU, TU, tl0, mass, td, p, rho0 = params
+        T, N, m = XC.shape
+        Xo = np.empty_like(XC); Do = np.empty((T, N - 1, m)); fl = np.empty(T, dtype=np.int32); it = np.empty(T, dtype=np.int32)
+        for j in range(T):
+            log = []
+            X, d, st = S.multiShoot_CRTBP_indirect(XC[j].T, t[j], MU, DU, TU, N, mass, tl0 if thrustLimit is None else float(thrustLimit[j]), False,
+                                                   flag_adjointsOnly, max_iter, p, rho0 if rho is None else float(rho[j]), backend=self, log=log)
+            Xo[j] = X.T; Do[j] = d.T; fl[j] = st; it[j] = len(log)
+        return dict(XC_all=Xo, defect=Do, status_flag=fl, iters=it)

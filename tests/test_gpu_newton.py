@@ -134,3 +134,20 @@ def test_solve_batch_continuation_slab(lto):
     assert ok.sum() >= 8
     assert np.all(r["er"][ok] <= 1e-10)
     assert np.all(r["XC_all"][:, 0, :6] == XC[:, 0, :6]) and np.all(r["XC_all"][:, -1, :6] == XC[:, -1, :6])   # pinned end states (:324-325)
+
+
+def test_continuation_batch_matches_per_trajectory_ladders(demo_p2):
+    """reduceFuel_indirect (HelperFunctions.jl:105-193): the batched driver (one lto_indirect_solve_batch call per round) against the
+    one-trajectory mirror run once per trajectory (host loop, dense least squares)."""
+    gpu, t_TU, starts, p2 = demo_p2
+    T = p2.shape[0]
+    p1 = np.stack([S.multiShoot_CRTBP_indirect(p2[j], t_TU, MU, DU, TU, 30, 1e3, 0.05, False, False, 30, 1.0, 1.0, backend=gpu)[0] for j in range(T)])
+    tt = np.broadcast_to(t_TU, (T, 30)).copy()
+    target = np.array([1e-2, 0.125, 0.05, 0.5])
+    Xb, db, sb, rounds = S.reduceFuel_indirect_batch(p1, tt, MU, DU, TU, 30, 1e3, 0.05, 1.0, target, backend=gpu)
+    assert np.all(sb == 0) and rounds == 8                                  # 1 -> 1e-2 by halving: 1 + 7 solver calls for the longest ladder
+    for j in range(T):
+        Xh, dh, sh = S.reduceFuel_indirect(p1[j], t_TU, MU, DU, TU, 30, 1e3, 0.05, 1.0, float(target[j]), backend=gpu)
+        assert sh == 0
+        assert np.abs(Xb[j] - Xh).max() < TOL_TRAJ, (j, np.abs(Xb[j] - Xh).max())
+        assert np.abs(db[j]).max() <= 1e-10

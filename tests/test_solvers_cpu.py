@@ -95,6 +95,35 @@ def test_indirect_demo_sequence(demo):
     clog = []
     XC2, d2, st2 = S.reduceFuel_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 0.05, 1.0, 0.125, backend=be, log=clog)
     assert st2 == 0 and [c["rho"] for c in clog] == [1.0, 0.5, 0.25, 0.125] and all(c["status"] == 0 for c in clog)
+    # the batched driver walks every trajectory's own ladder (different targets) and ends where the one-trajectory mirror ends
+    XC3, d3, st3 = S.reduceFuel_indirect(XC, demo["t"], MU, DU, TU, 30, 1e3, 0.05, 1.0, 0.5, backend=be)
+    blog = []
+    Xb, db, sb, rounds = S.reduceFuel_indirect_batch(np.stack([XC, XC]), np.stack([demo["t"]] * 2), MU, DU, TU, 30, 1e3, 0.05, 1.0,
+                                                     np.array([0.125, 0.5]), backend=be, log=blog)
+    assert rounds == 4 and [b["n"] for b in blog] == [2, 2, 1, 1] and np.all(sb == 0)
+    assert np.abs(Xb[0] - XC2).max() < 1e-12 and np.abs(Xb[1] - XC3).max() < 1e-12
+
+
+def test_continuation_ladder_backs_off_like_the_reference():
+    """The ladder logic alone (HelperFunctions.jl:155-187) with a scripted solver: success halves rho, failure multiplies it by
+    3 (1 + rand) and restarts from the last converged trajectory."""
+    class R:
+        def random(self):
+            return 0.5
+    g = S._reduceFuel_steps(np.zeros((12, 3)), 1.0, 0.1, R())
+    X, rho = next(g); seen = [rho]
+    script = [0, 0, 1, 0, 0, 0, 0, 0]                                          # the third call (rho 0.25) fails once
+    out = None
+    for k, st in enumerate(script):
+        try:
+            X, rho = g.send((np.full((12, 3), float(k + 1)), None, st))
+        except StopIteration as fin:
+            out = fin.value
+            break
+        seen.append(rho)
+        if st != 0:
+            assert np.all(X == float(k))                                       # restart from the last converged XC_all, not the failed one
+    assert seen[:6] == [1.0, 0.5, 0.25, 0.25 * 4.5, 0.5625, 0.28125] and seen[-1] == 0.1 and out[2] == 0
 
 
 def test_invalid_p_and_nan_status():
