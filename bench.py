@@ -503,8 +503,8 @@ def allgather_leg(args, h, dev, wl, n_seg, world, rank, batch, p):
 
 
 def solve_passes(it_max):
-    """Propagation passes of one lto_indirect_solve_batch call that ran it_max iterations (every trajectory of the batch is
-    propagated in every pass): first nominal run + per iteration STM, SOC, check (+ 20 line-search trials from iteration 4)."""
+    """Propagation passes a trajectory goes through in lto_indirect_solve_batch when it iterates it_max times: first nominal run
+    + per iteration STM, SOC, check (+ 20 line-search trials from iteration 4)."""
     return 1 + sum(3 + (20 if it > 3 else 0) for it in range(1, it_max + 1))
 
 
@@ -577,10 +577,13 @@ def run_solve(args):
     p = capi.indirect_params(p=2.0, thrustLimit=10.0, rho=1.0); p.max_attempts = 5000
     max_iter = 8
     pin = capi.PinnedBuffer(XC0.shape); pin_t = capi.PinnedBuffer(tt.shape); pin_t.array[...] = tt
+    pin_out = {"defect": capi.PinnedBuffer((T, spu, nd)), "status_flag": capi.PinnedBuffer((T,), np.int32), "iters": capi.PinnedBuffer((T,), np.int32),
+               "er": capi.PinnedBuffer((T,))}
+    outs = {k: b.array for k, b in pin_out.items()}
 
     def step():
-        pin.array[...] = XC0                                     # the solver works in place on the caller's XC_all
-        return h.indirect_solve_batch(pin.array, pin_t.array, params=p, max_iter=max_iter)
+        pin.array[...] = XC0                                     # the solver works in place on the caller's XC_all (pinned, like every output)
+        return h.indirect_solve_batch(pin.array, pin_t.array, params=p, max_iter=max_iter, inplace=True, out=outs)
 
     def barrier():
         if world > 1:
@@ -609,8 +612,9 @@ def run_solve(args):
     its = torch.tensor([it_max], dtype=torch.int64, device=dev); conv = torch.tensor([int((r["status_flag"] == 0).sum())], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(its, op=dist.ReduceOp.MAX); dist.all_reduce(conv)
-    passes = solve_passes(it_max)                                # this rank's; ranks may differ by an iteration: use the per-rank count below
-    segs = torch.tensor([T * spu * passes], dtype=torch.float64, device=dev)
+    passes = solve_passes(it_max)
+    # a trajectory is propagated only while it iterates (the solver compacts its work set): count what was actually propagated
+    segs = torch.tensor([float(spu * sum(solve_passes(int(k)) for k in r["iters"]))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(segs)
     total_props = float(segs.item())
@@ -650,10 +654,10 @@ def run_solve(args):
                        "description": "BASELINE configs[4]: 1,024 trajectories x 200 segments (L2_Anderson_2 ballistic stack, costates 0.1 N(0,1), p = 2, "
                                       "thrustLimit 10 N) SOLVED to the reference's 1e-10 defect threshold by lto_indirect_solve_batch: one step = the whole "
                                       "multiShoot_CRTBP_indirect loop for all trajectories, every array resident on the device (STM pass, banded-QR Newton "
-                                      "update, SOC, line search, checks); value counts every segment propagation of every pass",
+                                      "update, SOC, line search, checks; trajectories leave the work set when they stop iterating); value counts the segment propagations actually done",
                        "trajectories_total": n_traj_total, "segments_total": n_traj_total * spu, "l2": "not flushed: each pass streams more than the 126 MB L2 holds",
                        "parallelism": "whole trajectories split over %d GPU(s), independent solver instances, no collective" % world},
-            "clocks": clocks, "iterations_max": int(its.item()), "trajectories_converged": int(conv.item()), "passes_per_step": passes,
+            "clocks": clocks, "iterations_max": int(its.item()), "trajectories_converged": int(conv.item()), "passes_of_the_longest_trajectory": passes,
             "trajectories_per_s": n_traj_total / (wall_ms * 1e-3),
             "e2e": {"value": total_props / (wall_ms * 1e-3), "unit": "segment-propagations/s", "ms_per_step": wall_ms,
                     "h2d_bytes_per_step": int(XC0.nbytes + tt.nbytes), "d2h_bytes_per_step": int(XC0.nbytes + T * spu * nd * 8 + T * 16),

@@ -381,11 +381,20 @@ class Handle:
         self._ck(lib().lto_indirect_newton_dev(self._h, int(n_traj), int(n_nodes), int(bool(flag_adjointsOnly)), _ptr(phi), _ptr(defect),
                                                _ptr(xc_update), _ptr(status)))
 
-    def indirect_solve_batch(self, XC_all, t_TU, params=None, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False):
+    def indirect_solve_batch(self, XC_all, t_TU, params=None, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False, inplace=False,
+                             out=None):
         """multiShoot_CRTBP_indirect (:58-345) for n_traj trajectories at once, iterated on the device.
-        XC_all: (n_traj, n_nodes, 12); t_TU: (n_traj, n_nodes).  Returns dict(XC_all, defect, status_flag, iters, er)."""
+        XC_all: (n_traj, n_nodes, 12); t_TU: (n_traj, n_nodes).  Returns dict(XC_all, defect, status_flag, iters, er).
+        inplace: work directly on XC_all (must be a C-contiguous float64 array, e.g. pinned) as the C entry point does;
+        out: optional preallocated arrays under the keys defect / status_flag / iters / er."""
         p = params or indirect_params()
-        XC = np.array(XC_all, dtype=np.float64, order="C"); t_TU = _f64(t_TU)
+        if inplace:
+            XC = XC_all
+            if not (isinstance(XC, np.ndarray) and XC.dtype == np.float64 and XC.flags.c_contiguous):
+                raise ValueError("inplace needs a C-contiguous float64 array")
+        else:
+            XC = np.array(XC_all, dtype=np.float64, order="C")
+        t_TU = _f64(t_TU)
         if XC.ndim == 2:
             XC, t_TU = XC[None], t_TU[None]
         n_traj, n_nodes, nd = XC.shape
@@ -393,8 +402,19 @@ class Handle:
             raise ValueError("the reference's indirect solver is 12-dimensional (multiShoot_CRTBP_indirect.jl:258)")
         tl = None if thrustLimit is None else _f64(thrustLimit)
         rh = None if rho is None else _f64(rho)
-        defect = np.empty((n_traj, n_nodes - 1, nd)); flag = np.empty(n_traj, dtype=np.int32); iters = np.empty(n_traj, dtype=np.int32)
-        er = np.empty(n_traj)
+        o = out or {}
+        defect = o.get("defect", None)
+        if defect is None:
+            defect = np.empty((n_traj, n_nodes - 1, nd))
+        flag = o.get("status_flag", None)
+        if flag is None:
+            flag = np.empty(n_traj, dtype=np.int32)
+        iters = o.get("iters", None)
+        if iters is None:
+            iters = np.empty(n_traj, dtype=np.int32)
+        er = o.get("er", None)
+        if er is None:
+            er = np.empty(n_traj)
         self._ck(lib().lto_indirect_solve_batch(self._h, C.addressof(p), n_traj, n_nodes, int(max_iter), int(bool(flag_adjointsOnly)),
                                                 _ptr(XC), _ptr(t_TU), _ptr(tl), _ptr(rh), _ptr(defect), _ptr(flag), _ptr(iters), _ptr(er)))
         return dict(XC_all=XC, defect=defect, status_flag=flag, iters=iters, er=er)

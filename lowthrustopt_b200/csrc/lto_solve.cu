@@ -80,20 +80,70 @@ __global__ void k_tile(const double* __restrict__ src, double* __restrict__ dst,
     if (i < n * reps) dst[i] = src[i % n];
 }
 
-// end of an iteration (:328-341): er = norm(defect[:], Inf); iterCount += 1; abort above 1e3; loop condition er > 1e-10
+// end of an iteration (:328-341): er = norm(defect[:], Inf); iterCount += 1; abort above 1e3; loop condition er > 1e-10.
+// Rows are the WORK SET (trajectories still iterating); orig[row] is the trajectory's index in the caller's arrays.
 //   flag: 0 converged / still iterating, 1 gave up (maxIter or abort)
-__global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ active, int* __restrict__ iters, int* __restrict__ flag,
-                           unsigned long long* __restrict__ n_active, long long n, int it, int max_iter) {
+__global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ active, const int* __restrict__ orig, int* __restrict__ iters,
+                           int* __restrict__ flag, double* __restrict__ er_full, unsigned long long* __restrict__ n_active, long long n, int it,
+                           int max_iter) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    if (!active[j]) return;
+    const int o = orig[j];
     const double e = er[j];
-    if (it > 0) iters[j] = it;
+    er_full[o] = e;
+    if (it > 0) iters[o] = it;
     bool go = e > 1e-10;                                  // NaN -> false: the reference's while-condition ends the loop as well
-    if (go && !(e <= 1e3)) { go = false; flag[j] = 1; }   // "Not likely to converge. Aborting." (:333-336)
-    if (go && it >= max_iter) { go = false; flag[j] = 1; }   // "Reached max iteration count" (:282-286)
+    if (go && !(e <= 1e3)) { go = false; flag[o] = 1; }   // "Not likely to converge. Aborting." (:333-336)
+    if (go && it >= max_iter) { go = false; flag[o] = 1; }   // "Reached max iteration count" (:282-286)
     active[j] = go ? 1 : 0;
     if (go) atomicAdd(n_active, 1ull);
+}
+
+// exclusive prefix sum of the active flags (one block; the work set is at most a few 10^5 rows)
+__global__ void __launch_bounds__(1024) k_scan_active(const int* __restrict__ active, int* __restrict__ pos, long long n) {
+    __shared__ int part[1024];
+    const long long per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    int c = 0;
+    for (long long i = lo; i < hi; ++i) c += active[i] ? 1 : 0;
+    part[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < 1024; ++i) { const int v = part[i]; part[i] = acc; acc += v; } }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (long long i = lo; i < hi; ++i) { pos[i] = run; run += active[i] ? 1 : 0; }
+}
+
+// rows that stopped iterating leave the work set: their rows go to the caller-ordered result arrays
+__global__ void __launch_bounds__(256) k_retire_rows(const double* __restrict__ src, double* __restrict__ dst_full, const int* __restrict__ orig,
+                                                     const int* __restrict__ active, long long n_rows, long long len) {
+    const long long total = n_rows * len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i / len;
+        if (!active[j]) dst_full[(long long)orig[j] * len + (i - j * len)] = src[i];
+    }
+}
+// the rows still iterating move to the front (into `dst`, same order)
+template <class V>
+__global__ void __launch_bounds__(256) k_compact_rows(const V* __restrict__ src, V* __restrict__ dst, const int* __restrict__ pos,
+                                                      const int* __restrict__ active, long long n_rows, long long len) {
+    const long long total = n_rows * len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i / len;
+        if (active[j]) dst[(long long)pos[j] * len + (i - j * len)] = src[i];
+    }
+}
+// line-search scale table scale[a*n + j] = alpha_a, and initial bookkeeping
+__global__ void k_fill_ls(const double* __restrict__ alpha_all, double* __restrict__ table, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * NA) table[i] = alpha_all[i / n];
+}
+__global__ void k_set_int(int* __restrict__ v, int value, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = value;
+}
+__global__ void k_iota(int* __restrict__ orig, int* __restrict__ active, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { orig[i] = (int)i; active[i] = 1; }
 }
 
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -166,25 +216,30 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
     CK(h, cudaSetDevice(h->device));
     const int ND = 12, N = n_nodes, NA = slv::NA;
     const long long T = n_traj, ns = T * (N - 1), nn = T * N;
+    if (T > 0x7fffffffll) return fail(h, LTO_ERR_ARG, "too many trajectories");
+    const long long LX = (long long)N * ND, LD = (long long)(N - 1) * ND;      // row lengths: states / defects of one trajectory
     cudaStream_t st = h->s_compute;
-    // ---- device arrays
+    // ---- device arrays.  "work" arrays hold the trajectories still iterating (compacted to the front after every iteration);
+    // "out" arrays are in the caller's order and receive a trajectory's rows when it stops.
     const size_t bXC = al(nn * ND * 8), bT = al(nn * 8), bPar = al(T * 8), bDef = al(ns * ND * 8), bPhi = al(ns * ND * ND * 8);
     const size_t bTrX = al((size_t)NA * nn * ND * 8), bTrD = al((size_t)NA * ns * ND * 8), bTrT = al((size_t)NA * nn * 8), bTrP = al((size_t)NA * T * 8);
     const size_t bVec = al((size_t)NA * T * 8), bInt = al(T * 4);
-    size_t need = bXC * 3 + bT + bPar * 2 + bDef * 2 + bPhi + bTrX + bTrD + bTrT + bTrP * 2 + bVec * 7 + bInt * 3 + al(NA * 8) + 256;
+    size_t need = bXC * 4 + bT + bPar * 2 + bDef * 3 + bPhi + bTrX + bTrD + bTrT + bTrP * 2 + bVec * 8 + bInt * 6 + al(NA * 8) + 256;
     int rc = ensure(h, &h->d_slv, &h->d_slv_cap, need); if (rc) return rc;
     char* q = (char*)h->d_slv;
     auto take = [&](size_t b) { char* r = q; q += b; return r; };
     double* dXC = (double*)take(bXC); double* dXS = (double*)take(bXC); double* dUp = (double*)take(bXC); double* dUp2 = dXS;   // the SOC state buffer is free again when the SOC update is computed
+    double* dXCout = (double*)take(bXC);
     double* dT = (double*)take(bT);
     double* dTL = thrustLimit_traj ? (double*)take(bPar) : nullptr; double* dRH = rho_traj ? (double*)take(bPar) : nullptr;
-    double* dDef = (double*)take(bDef); double* dDs = (double*)take(bDef); double* dPhi = (double*)take(bPhi);
+    double* dDef = (double*)take(bDef); double* dDs = (double*)take(bDef); double* dDefOut = (double*)take(bDef); double* dPhi = (double*)take(bPhi);
     double* dTrX = (double*)take(bTrX); double* dTrD = (double*)take(bTrD); double* dTrT = (double*)take(bTrT);
     double* dTrTL = thrustLimit_traj ? (double*)take(bTrP) : nullptr; double* dTrRH = rho_traj ? (double*)take(bTrP) : nullptr;
     double* dEr = (double*)take(bVec); double* dUmax = (double*)take(bVec); double* dMask = (double*)take(bVec);
     double* dErs = (double*)take(bVec); double* dAlpha = (double*)take(bVec); double* dScale = (double*)take(bVec);
-    double* dLsTable = (double*)take(bVec);
+    double* dLsTable = (double*)take(bVec); double* dErOut = (double*)take(bVec);
     int* dActive = (int*)take(bInt); int* dIters = (int*)take(bInt); int* dFlag = (int*)take(bInt);
+    int* dOrig = (int*)take(bInt); int* dOrig2 = (int*)take(bInt); int* dPos = (int*)take(bInt);
     double* dAlphaAll = (double*)take(al(NA * 8));
     unsigned long long* dCount = (unsigned long long*)take(256);
     // ---- inputs
@@ -196,26 +251,14 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
     for (int a = 0; a < NA; ++a) alpha_all[a] = 0.1 + (double)a * ((1.0 - 0.1) / (double)(NA - 1));      // LinRange(0.1, 1, 20)
     alpha_all[NA - 1] = 1.0;
     CK(h, cudaMemcpyAsync(dAlphaAll, alpha_all, NA * 8, cudaMemcpyHostToDevice, st));
-    // line-search scale table: scale[a*T + j] = alpha_a; and the tiled per-trajectory inputs of the NA trial copies
-    {
-        std::vector<double> sc((size_t)NA * T);
-        for (int a = 0; a < NA; ++a) for (long long j = 0; j < T; ++j) sc[(size_t)a * T + j] = alpha_all[a];
-        CK(h, cudaMemcpyAsync(dLsTable, sc.data(), (size_t)NA * T * 8, cudaMemcpyHostToDevice, st));
-        CK(h, cudaStreamSynchronize(st));
-    }
-    slv::k_tile<<<slv::nblk((long long)NA * nn, 256), 256, 0, st>>>(dT, dTrT, nn, NA);
-    if (dTL) slv::k_tile<<<slv::nblk((long long)NA * T, 256), 256, 0, st>>>(dTL, dTrTL, T, NA);
-    if (dRH) slv::k_tile<<<slv::nblk((long long)NA * T, 256), 256, 0, st>>>(dRH, dTrRH, T, NA);
+    CK(h, cudaStreamSynchronize(st));                                     // alpha_all is a stack array
     CK(h, cudaMemsetAsync(dIters, 0, T * 4, st));
     CK(h, cudaMemsetAsync(dFlag, 0, T * 4, st));
-    {
-        std::vector<int> ones((size_t)T, 1);
-        CK(h, cudaMemcpyAsync(dActive, ones.data(), T * 4, cudaMemcpyHostToDevice, st));
-        CK(h, cudaStreamSynchronize(st));
-    }
-    h->launches += 1 + (dTL ? 1 : 0) + (dRH ? 1 : 0);
+    slv::k_iota<<<slv::nblk(T, 256), 256, 0, st>>>(dOrig, dActive, T);
+    h->launches += 1;
     CK(h, cudaEventRecord(h->ev_t0, st));
 
+    long long nc = T;                                                     // size of the work set
     auto defect_pass = [&](const double* X, const double* T_, const double* tl, const double* rh, long long ntr, double* D) -> int {
         return lto_indirect_dev(h, p, ntr * (N - 1), N, ND, X, T_, nullptr, nullptr, tl, rh, D, nullptr, nullptr, nullptr);
     };
@@ -226,55 +269,86 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
         dim3 g(std::min<unsigned>(slv::nblk(rows * len, 256), 148u * 16u), (unsigned)reps);
         slv::k_axpy_rows<<<g, 256, 0, st>>>(x, u, scale, out, rows, len); h->launches += 1;
     };
-    auto iter_end = [&](int it) -> int {
+    auto grid_for = [&](long long n) { return std::min<unsigned>(slv::nblk(n, 256), 148u * 16u); };
+    // per-work-set tables for the batched line search: alpha table and the NA-fold tiled time / parameter arrays
+    auto prepare_trials = [&]() {
+        slv::k_fill_ls<<<slv::nblk(nc * NA, 256), 256, 0, st>>>(dAlphaAll, dLsTable, nc);
+        slv::k_tile<<<slv::nblk((long long)NA * nc * N, 256), 256, 0, st>>>(dT, dTrT, nc * N, NA);
+        if (dTL) slv::k_tile<<<slv::nblk((long long)NA * nc, 256), 256, 0, st>>>(dTL, dTrTL, nc, NA);
+        if (dRH) slv::k_tile<<<slv::nblk((long long)NA * nc, 256), 256, 0, st>>>(dRH, dTrRH, nc, NA);
+        h->launches += 2 + (dTL ? 1 : 0) + (dRH ? 1 : 0);
+    };
+    // end of an iteration: bookkeeping, retire the rows that stopped, compact the rest.  Returns the new work-set size.
+    auto iter_end = [&](int it, long long* n_next) -> int {
         CK(h, cudaMemsetAsync(dCount, 0, 8, st));
-        slv::k_iter_end<<<slv::nblk(T, 256), 256, 0, st>>>(dEr, dActive, dIters, dFlag, dCount, T, it, max_iter); h->launches += 1;
+        slv::k_iter_end<<<slv::nblk(nc, 256), 256, 0, st>>>(dEr, dActive, dOrig, dIters, dFlag, dErOut, dCount, nc, it, max_iter);
+        slv::k_retire_rows<<<grid_for(nc * LX), 256, 0, st>>>(dXC, dXCout, dOrig, dActive, nc, LX);
+        slv::k_retire_rows<<<grid_for(nc * LD), 256, 0, st>>>(dDef, dDefOut, dOrig, dActive, nc, LD);
+        h->launches += 3;
+        unsigned long long na = 0;
+        CK(h, cudaMemcpyAsync(&na, dCount, 8, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        if (na > 0 && (long long)na < nc) {
+            slv::k_scan_active<<<1, 1024, 0, st>>>(dActive, dPos, nc);
+            // XC, defects (through free buffers), times, parameters, original indices
+            slv::k_compact_rows<double><<<grid_for(nc * LX), 256, 0, st>>>(dXC, dXS, dPos, dActive, nc, LX);
+            CK(h, cudaMemcpyAsync(dXC, dXS, (size_t)na * LX * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<double><<<grid_for(nc * LD), 256, 0, st>>>(dDef, dDs, dPos, dActive, nc, LD);
+            CK(h, cudaMemcpyAsync(dDef, dDs, (size_t)na * LD * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<double><<<grid_for(nc * N), 256, 0, st>>>(dT, dUp, dPos, dActive, nc, N);
+            CK(h, cudaMemcpyAsync(dT, dUp, (size_t)na * N * 8, cudaMemcpyDeviceToDevice, st));
+            if (dTL) { slv::k_compact_rows<double><<<grid_for(nc), 256, 0, st>>>(dTL, dUmax, dPos, dActive, nc, 1); CK(h, cudaMemcpyAsync(dTL, dUmax, (size_t)na * 8, cudaMemcpyDeviceToDevice, st)); }
+            if (dRH) { slv::k_compact_rows<double><<<grid_for(nc), 256, 0, st>>>(dRH, dUmax, dPos, dActive, nc, 1); CK(h, cudaMemcpyAsync(dRH, dUmax, (size_t)na * 8, cudaMemcpyDeviceToDevice, st)); }
+            slv::k_compact_rows<int><<<grid_for(nc), 256, 0, st>>>(dOrig, dOrig2, dPos, dActive, nc, 1);
+            CK(h, cudaMemcpyAsync(dOrig, dOrig2, (size_t)na * 4, cudaMemcpyDeviceToDevice, st));
+            slv::k_set_int<<<slv::nblk((long long)na, 256), 256, 0, st>>>(dActive, 1, (long long)na);      // the compacted work set: all iterating
+            h->launches += 6 + (dTL ? 1 : 0) + (dRH ? 1 : 0);
+        }
+        *n_next = (long long)na;
         return 0;
     };
 
     // ---- first nominal run (:274)
-    rc = defect_pass(dXC, dT, dTL, dRH, T, dDef); if (rc) return rc;
-    rowmax(dDef, T, (long long)(N - 1) * ND, dEr);
-    rc = iter_end(0); if (rc) return rc;
-    unsigned long long n_active = 0;
-    CK(h, cudaMemcpyAsync(&n_active, dCount, 8, cudaMemcpyDeviceToHost, st));
-    CK(h, cudaStreamSynchronize(st));
+    rc = defect_pass(dXC, dT, dTL, dRH, nc, dDef); if (rc) return rc;
+    rowmax(dDef, nc, LD, dEr);
+    long long n_next = 0;
+    rc = iter_end(0, &n_next); if (rc) return rc;
     int it = 0;
-    while (n_active > 0 && it < max_iter) {
+    while (n_next > 0 && it < max_iter) {
+        nc = n_next;                                                      // every row of the work set is iterating
         ++it;
-        // jacobianCalc (:290): one launch, Phi_i of every segment of every trajectory (and the defects, unchanged)
-        rc = lto_indirect_dev(h, p, ns, N, ND, dXC, dT, nullptr, nullptr, dTL, dRH, dDef, nullptr, nullptr, dPhi); if (rc) return rc;
+        // jacobianCalc (:290): one launch, Phi_i of every segment of every trajectory still iterating (and the defects, unchanged)
+        rc = lto_indirect_dev(h, p, nc * (N - 1), N, ND, dXC, dT, nullptr, nullptr, dTL, dRH, dDef, nullptr, nullptr, dPhi); if (rc) return rc;
         // optimizeTraj_OLS (:149-183)
-        rc = lto_indirect_newton_dev(h, T, N, flag_adjointsOnly, dPhi, dDef, dUp, nullptr); if (rc) return rc;
+        rc = lto_indirect_newton_dev(h, nc, N, flag_adjointsOnly, dPhi, dDef, dUp, nullptr); if (rc) return rc;
         // second-order correction (:187-214), only where norm(xc_update, Inf) < 1e-1
-        rowmax(dUp, T, (long long)N * ND, dUmax);
-        slv::k_soc_mask<<<slv::nblk(T, 256), 256, 0, st>>>(dUmax, dActive, dMask, T); h->launches += 1;
-        axpy(dXC, dUp, dMask, dXS, T, (long long)N * ND, 1);                                   // XC_all_soc (:194)
-        rc = defect_pass(dXS, dT, dTL, dRH, T, dDs); if (rc) return rc;                        // :197
-        rc = lto_indirect_newton_dev(h, T, N, flag_adjointsOnly, dPhi, dDs, dUp2, nullptr); if (rc) return rc;   // :207 (same Jacobian)
-        axpy(dUp, dUp2, dMask, dUp, T, (long long)N * ND, 1);                                  // xc_update += xc_update_soc (:213)
+        rowmax(dUp, nc, LX, dUmax);
+        slv::k_soc_mask<<<slv::nblk(nc, 256), 256, 0, st>>>(dUmax, dActive, dMask, nc); h->launches += 1;
+        axpy(dXC, dUp, dMask, dXS, nc, LX, 1);                                                 // XC_all_soc (:194)
+        rc = defect_pass(dXS, dT, dTL, dRH, nc, dDs); if (rc) return rc;                       // :197
+        rc = lto_indirect_newton_dev(h, nc, N, flag_adjointsOnly, dPhi, dDs, dUp2, nullptr); if (rc) return rc;   // :207 (same Jacobian)
+        axpy(dUp, dUp2, dMask, dUp, nc, LX, 1);                                                // xc_update += xc_update_soc (:213)
         // line search (:298-302)
         const int use_ls = it > 3;
         if (use_ls) {
-            axpy(dXC, dUp, dLsTable, dTrX, T, (long long)N * ND, NA);                          // XC_all + xc_update*alpha (:235)
-            rc = defect_pass(dTrX, dTrT, dTrTL, dTrRH, (long long)NA * T, dTrD); if (rc) return rc;   // :238, all 20 x n_traj trials in one launch
-            rc = lto_sumsq_dev(h, dTrD, (long long)NA * T, (long long)(N - 1) * ND, dErs); if (rc) return rc;   // er[ind] = sum(defect[:].^2) (:241)
+            prepare_trials();
+            axpy(dXC, dUp, dLsTable, dTrX, nc, LX, NA);                                        // XC_all + xc_update*alpha (:235)
+            rc = defect_pass(dTrX, dTrT, dTrTL, dTrRH, (long long)NA * nc, dTrD); if (rc) return rc;   // :238, all 20 x n trial trajectories in one launch
+            rc = lto_sumsq_dev(h, dTrD, (long long)NA * nc, LD, dErs); if (rc) return rc;      // er[ind] = sum(defect[:].^2) (:241)
         }
-        slv::k_pick_alpha<<<slv::nblk(T, 256), 256, 0, st>>>(dErs, dAlphaAll, dActive, dAlpha, dScale, T, use_ls); h->launches += 1;
-        axpy(dXC, dUp, dScale, dXC, T, (long long)N * ND, 1);                                  // XC_all = XC_all + xc_update*alpha (:304)
+        slv::k_pick_alpha<<<slv::nblk(nc, 256), 256, 0, st>>>(dErs, dAlphaAll, dActive, dAlpha, dScale, nc, use_ls); h->launches += 1;
+        axpy(dXC, dUp, dScale, dXC, nc, LX, 1);                                                // XC_all = XC_all + xc_update*alpha (:304)
         // the end states cannot have moved (:324-325): their update entries are exact zeros (lto_newton.cu)
-        rc = defect_pass(dXC, dT, dTL, dRH, T, dDef); if (rc) return rc;                       // :328
-        rowmax(dDef, T, (long long)(N - 1) * ND, dEr);                                         // :332
-        rc = iter_end(it); if (rc) return rc;
-        CK(h, cudaMemcpyAsync(&n_active, dCount, 8, cudaMemcpyDeviceToHost, st));
-        CK(h, cudaStreamSynchronize(st));
+        rc = defect_pass(dXC, dT, dTL, dRH, nc, dDef); if (rc) return rc;                      // :328
+        rowmax(dDef, nc, LD, dEr);                                                             // :332
+        rc = iter_end(it, &n_next); if (rc) return rc;
     }
     CK(h, cudaEventRecord(h->ev_t1, st));
-    // ---- outputs
-    CK(h, cudaMemcpyAsync(XC_all, dXC, nn * ND * 8, cudaMemcpyDeviceToHost, st));
-    if (defect) CK(h, cudaMemcpyAsync(defect, dDef, ns * ND * 8, cudaMemcpyDeviceToHost, st));
+    // ---- outputs (every trajectory has been retired into the caller-ordered arrays by now)
+    CK(h, cudaMemcpyAsync(XC_all, dXCout, nn * ND * 8, cudaMemcpyDeviceToHost, st));
+    if (defect) CK(h, cudaMemcpyAsync(defect, dDefOut, ns * ND * 8, cudaMemcpyDeviceToHost, st));
     if (iters) CK(h, cudaMemcpyAsync(iters, dIters, T * 4, cudaMemcpyDeviceToHost, st));
-    if (er_out) CK(h, cudaMemcpyAsync(er_out, dEr, T * 8, cudaMemcpyDeviceToHost, st));
+    if (er_out) CK(h, cudaMemcpyAsync(er_out, dErOut, T * 8, cudaMemcpyDeviceToHost, st));
     std::vector<int32_t> flag((size_t)T);
     CK(h, cudaMemcpyAsync(flag.data(), dFlag, T * 4, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
