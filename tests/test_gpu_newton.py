@@ -151,3 +151,21 @@ def test_continuation_batch_matches_per_trajectory_ladders(demo_p2):
         assert sh == 0
         assert np.abs(Xb[j] - Xh).max() < TOL_TRAJ, (j, np.abs(Xb[j] - Xh).max())
         assert np.abs(db[j]).max() <= 1e-10
+
+
+def test_solve_batch_edge_cases(lto):
+    p = capi.indirect_params(p=2.0, thrustLimit=10.0)
+    c = synthetic.continuation_batch(n_traj=3, n_seg_per_traj=200, ndim=12)
+    c = dict(XC_all=c["XC_all"][:, :2].copy(), t_TU=c["t_TU"][:, :2].copy())         # two nodes: one (short) segment per trajectory
+    r = lto.indirect_solve_batch(c["XC_all"], c["t_TU"], params=p, max_iter=0)      # maxIter = 0: "Reached max iteration count" at once (:282-286)
+    assert np.all(r["status_flag"] == 1) and np.all(r["iters"] == 0) and np.array_equal(r["XC_all"], c["XC_all"])
+    r = lto.indirect_solve_batch(c["XC_all"], c["t_TU"], params=p, max_iter=20)
+    assert np.all(r["status_flag"] == 0) and np.all(r["er"] <= 1e-10)
+    assert np.array_equal(r["XC_all"][:, :, :6], c["XC_all"][:, :, :6])             # both nodes' states are pinned: only costates move
+    r = lto.indirect_solve_batch(np.zeros((0, 5, 12)), np.zeros((0, 5)), params=p)  # empty batch
+    assert r["XC_all"].shape == (0, 5, 12) and r["status_flag"].shape == (0,)
+    with pytest.raises(capi.LtoError):
+        lto.indirect_solve_batch(np.zeros((1, 1, 12)), np.zeros((1, 1)), params=p)  # n_nodes < 2
+    bad = c["XC_all"].copy(); bad[1, 0, 0] = np.nan
+    r = lto.indirect_solve_batch(bad, c["t_TU"], params=p, max_iter=5)
+    assert r["status_flag"][1] == 2 and r["status_flag"][0] == 0 and r["status_flag"][2] == 0   # isnan(XC_all[1]) -> 2 (:339-341)
