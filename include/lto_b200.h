@@ -94,7 +94,8 @@ int lto_init(int device, lto_handle** h);      /* LTO_ERR_NODEVICE when no sm_10
 /* One handle over several GPUs of the box, for a single host process (the Julia drop-in): every
  * host-buffer entry point splits its segments (trajectory forms: whole trajectories) into equal
  * contiguous ranges, one per device, runs them concurrently (one worker thread per device) and
- * each device copies its slab of the outputs into the caller's arrays.  The device-pointer entry
+ * each device copies its slab of the outputs into the caller's arrays (lto_indirect_newton and lto_indirect_solve_batch
+ * included: whole trajectories per device, independent solver instances).  The device-pointer entry
  * points (lto_*_dev, lto_stream) need a single-device handle. */
 int lto_init_devices(int n_devices, const int* devices, lto_handle** h);
 int lto_n_devices(const lto_handle* h);

@@ -14,6 +14,7 @@
 #include "lto_handle.h"
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace lto {
@@ -153,6 +154,24 @@ static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) 
 
 using namespace lto;
 
+// Multi-device handles (lto_init_devices): whole trajectories in equal contiguous ranges, one host worker thread per device;
+// every device copies its slab of the results straight into the caller's arrays.
+template <class F>
+static int split_trajectories(lto_handle* h, long long n_traj, F&& call) {
+    const int nc = h->n_child;
+    std::vector<int> rcs(nc, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < nc; ++i) {
+        const long long u0 = n_traj * i / nc, u1 = n_traj * (i + 1) / nc;
+        if (u1 <= u0) continue;
+        th.emplace_back([&, i, u0, u1] { rcs[i] = call(h->child[i], u0, u1 - u0); });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < nc; ++i)
+        if (rcs[i]) return fail(h, rcs[i], "device %d: %s", h->child[i]->device, h->child[i]->err);
+    return LTO_SUCCESS;
+}
+
 extern "C" {
 
 int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
@@ -175,11 +194,17 @@ int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag
 int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
                         const double* defect, double* xc_update, int32_t* status) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
-    if (h->n_child > 0) return lto_indirect_newton(h->child[0], n_traj, n_nodes, flag_adjointsOnly, phi, defect, xc_update, status);
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     if (n_traj == 0) return LTO_SUCCESS;
     if (!phi || !defect || !xc_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    if (h->n_child > 0) {
+        const long long N = n_nodes;
+        return split_trajectories(h, n_traj, [&](lto_handle* c, long long u0, long long nu) {
+            return lto_indirect_newton(c, nu, n_nodes, flag_adjointsOnly, phi + u0 * (N - 1) * 144, defect + u0 * (N - 1) * 12, xc_update + u0 * N * 12,
+                                       status ? status + u0 : nullptr);
+        });
+    }
     CK(h, cudaSetDevice(h->device));
     const long long ns = n_traj * (long long)(n_nodes - 1), nn = n_traj * (long long)n_nodes;
     const size_t bP = al(ns * 144 * 8), bD = al(ns * 12 * 8), bU = al(nn * 12 * 8), bS = al(n_traj * 4);
@@ -202,17 +227,21 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
                              int flag_adjointsOnly, double* XC_all, const double* t_TU, const double* thrustLimit_traj,
                              const double* rho_traj, double* defect, int32_t* status_flag, int32_t* iters, double* er_out) {
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
-    if (h->n_child > 0) {
-        // whole trajectories per device, one worker per device would be the natural split; kept simple: device 0
-        return lto_indirect_solve_batch(h->child[0], p, n_traj, n_nodes, max_iter, flag_adjointsOnly, XC_all, t_TU, thrustLimit_traj,
-                                        rho_traj, defect, status_flag, iters, er_out);
-    }
     if (!p) return fail(h, LTO_ERR_ARG, "null params");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     if (max_iter < 0) return fail(h, LTO_ERR_ARG, "negative max_iter");
     if (n_traj == 0) return LTO_SUCCESS;
     if (!XC_all || !t_TU) return fail(h, LTO_ERR_ARG, "null array argument");
+    if (h->n_child > 0) {                                                 // independent solver instances: no communication between the devices
+        const long long N = n_nodes;
+        return split_trajectories(h, n_traj, [&](lto_handle* c, long long u0, long long nu) {
+            return lto_indirect_solve_batch(c, p, nu, n_nodes, max_iter, flag_adjointsOnly, XC_all + u0 * N * 12, t_TU + u0 * N,
+                                            thrustLimit_traj ? thrustLimit_traj + u0 : nullptr, rho_traj ? rho_traj + u0 : nullptr,
+                                            defect ? defect + u0 * (N - 1) * 12 : nullptr, status_flag ? status_flag + u0 : nullptr,
+                                            iters ? iters + u0 : nullptr, er_out ? er_out + u0 : nullptr);
+        });
+    }
     CK(h, cudaSetDevice(h->device));
     const int ND = 12, N = n_nodes, NA = slv::NA;
     const long long T = n_traj, ns = T * (N - 1), nn = T * N;

@@ -252,6 +252,18 @@ def test_multi_device_handle_equals_single_device(lto):
     assert np.array_equal(d1["defect"], dm["defect"])
     with pytest.raises(capi.LtoError):
         hm.direct_dev(capi.direct_params(), 1, 0, 7, 10, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)   # device-pointer calls need a single-device handle
+    # Newton update and batched solver: whole trajectories per device, same results as one device
+    c2 = S.continuation_batch(n_traj=11, n_seg_per_traj=200, ndim=12)
+    XC = c2["XC_all"].copy(); XC[:, :, 6:] *= 0.1
+    p2 = capi.indirect_params(p=2.0, thrustLimit=10.0)
+    s1 = lto.indirect_solve_batch(XC, c2["t_TU"], params=p2, max_iter=8)
+    sm = hm.indirect_solve_batch(XC, c2["t_TU"], params=p2, max_iter=8)
+    assert np.array_equal(s1["status_flag"], sm["status_flag"]) and np.array_equal(s1["iters"], sm["iters"])
+    assert np.abs(s1["XC_all"] - sm["XC_all"]).max() < 1e-11
+    tt1 = lto.indirect_traj(XC, c2["t_TU"], params=p2)
+    u1, st1 = lto.indirect_newton(tt1["phi"].reshape(11, 200, 12, 12), tt1["defect"].reshape(11, 200, 12))
+    um, stm = hm.indirect_newton(tt1["phi"].reshape(11, 200, 12, 12), tt1["defect"].reshape(11, 200, 12))
+    assert np.array_equal(u1, um) and np.array_equal(st1, stm)
     assert hm.launches > 0
     hm.close()
 
