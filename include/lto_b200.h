@@ -196,6 +196,11 @@ int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adj
                         const double* phi, const double* defect, double* xc_update, int32_t* status);
 int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly,
                             const double* phi, const double* defect, double* xc_update, int32_t* status);
+/* The second solve of optimizeTraj_OLS -- the second-order correction xc_update_soc = -Jac_sparse \ defect_vec with the SAME Jac_sparse
+ * (:207) -- without factorising again: the handle keeps the factorisation of the last lto_indirect_newton_dev call (same n_traj,
+ * n_nodes, flag_adjointsOnly required) and this call only transforms the new defects and back-substitutes.  `defect` 16-byte aligned. */
+int lto_indirect_newton_resolve_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly,
+                                    const double* defect, double* xc_update, int32_t* status);
 /* lto_indirect_solve_batch: multiShoot_CRTBP_indirect (src/multiShoot_CRTBP_indirect.jl:58-345) for n_traj independent
  * trajectories at once, all arrays resident on the device between iterations: first nominal run (:274), then per
  * iteration jacobianCalc (:290), optimizeTraj_OLS with the second-order correction (:149-218; applied per trajectory where

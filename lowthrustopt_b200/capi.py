@@ -30,7 +30,7 @@ EXPORTS = [
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
     "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_dev_alloc", "lto_dev_free", "lto_ipc_export", "lto_ipc_open", "lto_ipc_close",
     "lto_push_async", "lto_sync_copies", "lto_signal_dev", "lto_wait_dev", "lto_fp64_peak_probe", "lto_debug_profile",
-    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_solve_batch",
+    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_newton_resolve_dev", "lto_indirect_solve_batch",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
         L.lto_debug_profile.argtypes = [vp, vp, ci]
         L.lto_indirect_newton.argtypes = [vp, i64, ci, ci] + [vp] * 4
         L.lto_indirect_newton_dev.argtypes = [vp, i64, ci, ci] + [vp] * 4
+        L.lto_indirect_newton_resolve_dev.argtypes = [vp, i64, ci, ci] + [vp] * 3
         L.lto_indirect_solve_batch.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 8
         _lib = L
     return _lib
@@ -380,6 +381,11 @@ class Handle:
     def indirect_newton_dev(self, n_traj, n_nodes, flag_adjointsOnly, phi, defect, xc_update, status=None):
         self._ck(lib().lto_indirect_newton_dev(self._h, int(n_traj), int(n_nodes), int(bool(flag_adjointsOnly)), _ptr(phi), _ptr(defect),
                                                _ptr(xc_update), _ptr(status)))
+
+    def indirect_newton_resolve_dev(self, n_traj, n_nodes, flag_adjointsOnly, defect, xc_update, status=None):
+        """Same matrix as the preceding indirect_newton_dev call, new defects (the second-order correction, :207)."""
+        self._ck(lib().lto_indirect_newton_resolve_dev(self._h, int(n_traj), int(n_nodes), int(bool(flag_adjointsOnly)), _ptr(defect),
+                                                       _ptr(xc_update), _ptr(status)))
 
     def indirect_solve_batch(self, XC_all, t_TU, params=None, thrustLimit=None, rho=None, max_iter=50, flag_adjointsOnly=False, inplace=False,
                              out=None):

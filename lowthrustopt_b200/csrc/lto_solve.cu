@@ -21,6 +21,8 @@ namespace lto {
 size_t indirect_newton_workspace_bytes(long long n_traj, int n_nodes);
 cudaError_t launch_indirect_newton(const double* phi, const double* defect, double* work, double* update, int32_t* status,
                                    long long n_traj, int n_nodes, bool adjoints_only, cudaStream_t st);
+cudaError_t launch_indirect_newton_resolve(const double* defect, double* work, double* update, int32_t* status, long long n_traj, int n_nodes,
+                                           bool adjoints_only, cudaStream_t st);
 
 namespace slv {
 
@@ -184,9 +186,27 @@ int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag
     if (!phi || !defect || !xc_update) return fail(h, LTO_ERR_ARG, "null array argument");
     if (((uintptr_t)phi & 15u) != 0) return fail(h, LTO_ERR_ARG, "phi must be 16-byte aligned");
     CK(h, cudaSetDevice(h->device));
+    h->nwt_traj = 0;
     int rc = ensure(h, &h->d_nwt, &h->d_nwt_cap, indirect_newton_workspace_bytes(n_traj, n_nodes)); if (rc) return rc;
     cudaError_t e = launch_indirect_newton(phi, defect, (double*)h->d_nwt, xc_update, status, n_traj, n_nodes, flag_adjointsOnly != 0, h->s_compute);
     if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "newton kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    h->nwt_traj = n_traj; h->nwt_nodes = n_nodes; h->nwt_adj = flag_adjointsOnly != 0;
+    return LTO_SUCCESS;
+}
+
+int lto_indirect_newton_resolve_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* defect,
+                                    double* xc_update, int32_t* status) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!defect || !xc_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    if (h->nwt_traj != n_traj || h->nwt_nodes != n_nodes || h->nwt_adj != (flag_adjointsOnly != 0) || !h->d_nwt)
+        return fail(h, LTO_ERR_ARG, "lto_indirect_newton_resolve_dev: no factorisation of this shape and mode is held (call lto_indirect_newton_dev first)");
+    if (((uintptr_t)defect & 15u) != 0) return fail(h, LTO_ERR_ARG, "defect must be 16-byte aligned");
+    CK(h, cudaSetDevice(h->device));
+    cudaError_t e = launch_indirect_newton_resolve(defect, (double*)h->d_nwt, xc_update, status, n_traj, n_nodes, flag_adjointsOnly != 0, h->s_compute);
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "newton resolve kernel launch: %s", cudaGetErrorString(e));
     h->launches += 1;
     return LTO_SUCCESS;
 }
@@ -355,7 +375,7 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
         slv::k_soc_mask<<<slv::nblk(nc, 256), 256, 0, st>>>(dUmax, dActive, dMask, nc); h->launches += 1;
         axpy(dXC, dUp, dMask, dXS, nc, LX, 1);                                                 // XC_all_soc (:194)
         rc = defect_pass(dXS, dT, dTL, dRH, nc, dDs); if (rc) return rc;                       // :197
-        rc = lto_indirect_newton_dev(h, nc, N, flag_adjointsOnly, dPhi, dDs, dUp2, nullptr); if (rc) return rc;   // :207 (same Jacobian)
+        rc = lto_indirect_newton_resolve_dev(h, nc, N, flag_adjointsOnly, dDs, dUp2, nullptr); if (rc) return rc;   // :207 (same Jacobian: stored reflections replayed)
         axpy(dUp, dUp2, dMask, dUp, nc, LX, 1);                                                // xc_update += xc_update_soc (:213)
         // line search (:298-302)
         const int use_ls = it > 3;

@@ -54,6 +54,31 @@ def test_newton_update_vs_reference_least_squares(lto, n_traj, n_seg, adjoints_o
         assert np.all(upd[:, 0, :6] == 0.0) and np.all(upd[:, -1, :6] == 0.0)
 
 
+@pytest.mark.parametrize("adjoints_only", [False, True])
+def test_newton_resolve_reuses_the_factorisation(lto, adjoints_only):
+    """lto_indirect_newton_resolve_dev (the second-order correction's solve, :207): same matrix, new defects, no new factorisation."""
+    import torch
+    n_traj, n_seg = 7, 200
+    c = synthetic.continuation_batch(n_traj=n_traj, n_seg_per_traj=n_seg, ndim=12, seed=5)
+    r = lto.indirect_traj(c["XC_all"], c["t_TU"], params=capi.indirect_params(p=2.0, thrustLimit=10.0))
+    dev = torch.device("cuda", 0)
+    phi = torch.from_numpy(r["phi"]).to(dev); d1 = torch.from_numpy(r["defect"]).to(dev)
+    d2 = torch.from_numpy(np.random.default_rng(3).standard_normal(r["defect"].shape) * 1e-3).to(dev)
+    u1 = torch.empty((n_traj, n_seg + 1, 12), dtype=torch.float64, device=dev); u2 = torch.empty_like(u1); u2b = torch.empty_like(u1)
+    st = torch.zeros(n_traj, dtype=torch.int32, device=dev)
+    with pytest.raises(capi.LtoError):
+        lto.indirect_newton_resolve_dev(n_traj + 1, n_seg + 1, adjoints_only, d2.data_ptr(), u2.data_ptr())      # no such factorisation held
+    lto.indirect_newton_dev(n_traj, n_seg + 1, adjoints_only, phi.data_ptr(), d1.data_ptr(), u1.data_ptr())
+    lto.indirect_newton_resolve_dev(n_traj, n_seg + 1, adjoints_only, d2.data_ptr(), u2.data_ptr(), st.data_ptr())
+    lto.indirect_newton_dev(n_traj, n_seg + 1, adjoints_only, phi.data_ptr(), d2.data_ptr(), u2b.data_ptr())     # the same solve, factorised afresh
+    lto.sync()
+    assert int(st.abs().max()) == 0
+    a, b = u2.cpu().numpy(), u2b.cpu().numpy()
+    assert np.abs(a - b).max() < 1e-11 * max(1.0, np.abs(b).max())
+    ref = _lstsq_update(r["phi"].reshape(n_traj, n_seg, 12, 12)[0].transpose(0, 2, 1), d2.cpu().numpy().reshape(n_traj, n_seg, 12)[0], adjoints_only)
+    assert np.abs(a[0] - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
 def test_newton_update_flags_singular_systems(lto):
     phi = np.zeros((2, 4, 12, 12)); d = np.ones((2, 4, 12))
     phi[1] = np.eye(12)                                                   # trajectory 0: Phi = 0 (singular)

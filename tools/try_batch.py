@@ -33,3 +33,11 @@ for mode in (0, 1):
         b.record()
     h.sync()
     print("newton kernel mode", mode, "%.3f ms for 1024 x 201 nodes" % (a.elapsed_time(b) / 10))
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(st):
+        a.record()
+        for i in range(10):
+            h.indirect_newton_resolve_dev(1024, 201, mode, d.data_ptr(), upd.data_ptr())
+        b.record()
+    h.sync()
+    print("newton resolve mode", mode, "%.3f ms" % (a.elapsed_time(b) / 10))
