@@ -69,5 +69,15 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(y, fma(e, e, e), y);
 }
 
+// u^(-1/16) for normal positive u, i.e. (sqrt u)^(-1/8): the step-size factor 0.9 * err^(-1/8) of the order-8 controller straight from
+// the SQUARED scaled error, as three square roots of 1/sqrt(u), each one multiply by a reciprocal square root -- no IEEE
+// sqrt / division subroutines on the state warp's chain.
+__device__ __forceinline__ double inv_sixteenth_root(double u) {
+    double z = fast_rsqrt(u);              // u^(-1/2)
+    z = z * fast_rsqrt(z);                 // u^(-1/4)
+    z = z * fast_rsqrt(z);                 // u^(-1/8)
+    return z * fast_rsqrt(z);              // u^(-1/16)
+}
+
 }  // namespace cwc
 }  // namespace lto

@@ -558,12 +558,12 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
 #pragma unroll
                     for (int c = 0; c < ND; ++c) s2 += S.errp[c * TS + slot];
                 }
-                const double eest = sqrt(s2 * inv_ne);
-                if (!(eest == eest)) { status = LTO_ST_NAN; finished = true; }
+                const double u = s2 * inv_ne;                           // eest^2: eest <= 1 <=> u <= 1, eest^(-1/8) = u^(-1/16)
+                if (!(u == u)) { status = LTO_ST_NAN; finished = true; }
                 else {
-                    double q = (eest == 0.0) ? 5.0 : 0.9 * inv_eighth_root(eest);
+                    double q = (u == 0.0) ? 5.0 : ((u < 1e300) ? 0.9 * inv_sixteenth_root(u) : 0.2);
                     q = fmin(5.0, fmax(0.2, q));
-                    if (eest <= 1.0) {
+                    if (u <= 1.0) {
                         ++na; flags |= F_ACCEPT;
                         xi ^= 1;                                          // the candidate becomes x
                         if (last) { tcur = tf; finished = true; }
