@@ -1,0 +1,26 @@
+"""Small invocations of every kernel added in this round, for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+from lowthrustopt_b200 import capi, synthetic as S
+h = capi.Handle(0)
+p1 = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
+p2 = capi.indirect_params(p=2.0, thrustLimit=10.0)
+for nd in (12, 14):
+    b = S.indirect_batch(300, ndim=nd, seed=1)
+    r = h.indirect(b["x0"], b["t0"], b["t1"], params=p1)
+    r0 = h.indirect(b["x0"], b["t0"], b["t1"], params=p1, jac=False)
+    assert np.all(r["status"] == 0) and np.all(r0["status"] == 0)
+d = S.direct_batch(200, nstate=7, seed=2)
+rd = h.direct(d["Xa"], d["Xb"], d["ua"], d["ub"], d["ta"], d["tb"])
+rda = h.direct(d["Xa"], d["Xb"], d["ua"], d["ub"], d["ta"], d["tb"], params=capi.direct_params(mode=capi.LTO_ADAPTIVE))
+c = S.continuation_batch(n_traj=6, n_seg_per_traj=29, ndim=12)
+rt = h.indirect_traj(c["XC_all"], c["t_TU"], params=p2)
+for adj in (False, True):
+    u, st = h.indirect_newton(rt["phi"].reshape(6, 29, 12, 12), rt["defect"].reshape(6, 29, 12), adj)
+    assert np.all(st == 0)
+XC = c["XC_all"].copy(); XC[:, :, 6:] *= 0.1
+s = h.indirect_solve_batch(XC, c["t_TU"], params=p2, max_iter=6)
+print("sanitize run ok: solve flags", s["status_flag"], "iters", s["iters"], "launches", h.launches)
+h.close()
