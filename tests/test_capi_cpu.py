@@ -59,3 +59,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(d, f)).read()
                 assert "oracle" not in txt.lower() or f == "__init__.py" and False, os.path.join(d, f)
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "capi_smoke")
+    libdir = os.path.join(ROOT, "lowthrustopt_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "native", "capi_smoke.c"),
+                           "-L", libdir, "-llto_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_links(capi, tmp_path):
+    """include/lto_b200.h from a C99 translation unit (what cgo / ccall / ctypes bind): compiles with -Wall -Werror, links, and on a
+    machine without a GPU the program gets LTO_ERR_NODEVICE from lto_init (no fallback)."""
+    import subprocess
+    import torch
+    exe = _build_c_smoke(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the compute path of the C program is the gpu-marked test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("nodevice:") and "no CPU fallback" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_through_the_abi(capi, tmp_path):
+    import subprocess
+    out = subprocess.run([_build_c_smoke(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "direct: status 0" in out.stdout and "newton status 0" in out.stdout
