@@ -13,7 +13,9 @@ __device__ __forceinline__ double fast_rcp(double x) {
 template <int OP>
 __global__ void k(double* out, long long* cyc, double seed, int busy_warps) {
     double x = seed + threadIdx.x * 1e-9, m = 1.0 + 1e-12, c = 1e-13;
-    if ((threadIdx.x >> 5) > 0) {                       // optional background warps saturating the FP64 pipe of the other sub-partitions
+    // busy_warps = bit mask of the background warps (warp w sits on SM sub-partition w % 4) that saturate their FP64 pipe
+    if ((threadIdx.x >> 5) > 0 && !((busy_warps >> (threadIdx.x >> 5)) & 1)) return;
+    if ((threadIdx.x >> 5) > 0) {
         double a0 = x, a1 = x + 1, a2 = x + 2, a3 = x + 3;
         for (int i = 0; i < 40000; ++i) { a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c); }
         if (a0 + a1 + a2 + a3 == 1.2345) out[1] = a0;
@@ -40,8 +42,12 @@ __global__ void k(double* out, long long* cyc, double seed, int busy_warps) {
 int main() {
     double* d; long long* c; cudaMalloc(&d, 4096); cudaMalloc(&c, 64);
     const char* names[] = {"DFMA", "DMUL", "DADD", "fast_rsqrt+add", "fast_rcp+add", "exp()*c", "IEEE sqrt+add", "IEEE div+add", "shfl.f64"};
-    for (int busy = 0; busy < 2; ++busy) {
-        printf(busy ? "--- with 7 background warps issuing DFMA on the same SM\n" : "--- one warp alone\n");
+    const int masks[4] = {0, 0xfe, 0x10, 0xee};
+    const char* what[4] = {"--- one warp alone", "--- with 7 background warps issuing DFMA on the same SM (all sub-partitions)",
+                           "--- with ONE background warp on the SAME sub-partition (warp 4)", "--- with 6 background warps on the OTHER three sub-partitions only"};
+    for (int bi = 0; bi < 4; ++bi) {
+        const int busy = masks[bi];
+        printf("%s\n", what[bi]);
         for (int op = 0; op < 9; ++op) {
             long long h = 0; int threads = busy ? 256 : 32;
             for (int rep = 0; rep < 2; ++rep) {
