@@ -29,9 +29,10 @@ sys.path.insert(0, ROOT)
 
 # Algorithmic FLOPs per unit (sparsity-exploiting minimal formulation; DESIGN.md "Measurement")
 FLOPS_PER_SEG = {"direct7": 284040.0, "direct6": 217836.0}
-# ndim 14: 13 stages x (240 state + 14 columns x 82) + RK combinations 2*75*210 + error 10*210, minus the
-# beta-combinations of the 15 lm components (pure quadratures: 15 x 134) = 18,044 + 31,590
-FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 49634.0}
+# ndim 14, minimal formulation: the STM column d/d(lm0) is the constant e_14 (lm enters no right-hand side), so 13
+# columns are integrated: 13 stages x (240 state + 13 columns x 82) = 16,978; RK combinations over 14 + 13*14 = 196 components
+# 2*75*196 + error 10*196 = 31,360, minus the beta-combinations of the 14 lm components (pure quadratures: 14 x 134) = 29,484
+FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 46462.0}
 # Algorithmic HBM bytes per unit
 BYTES_PER_SEG = {"direct7": 1360.0, "direct6": (2 * 6 + 6 + 2 + 6 + 1 + 6 * 18) * 8.0, 12: 1360.0, 14: 1808.0}
 
