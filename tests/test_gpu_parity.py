@@ -293,3 +293,25 @@ def test_sumsq_dev_and_sharded_line_search_single_rank(lto):
     j, _ = sh.run(p, jac=True)
     rj = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"], jac=True)
     assert np.abs(j["phi"].cpu().numpy().reshape(-1, 12, 12) - rj["phi"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("variant", ["v3", "q3"])
+def test_experimental_k3_layouts_stay_correct(variant, lto, tmp_path):
+    """LTO_K3=v3 (three tiles in flight) / q3 (three lanes per column) are kept as measured negative results (DESIGN.md section 4);
+    they must keep producing the default kernel's results (integration-tolerance level: the step sequences may differ)."""
+    import subprocess, sys, os
+    b = S.indirect_batch(700, ndim=12, seed=77)
+    ref = lto.indirect(b["x0"], b["t0"], b["t1"], params=capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05))
+    out = str(tmp_path / "k3.npz")
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+            "from lowthrustopt_b200 import capi, synthetic as S\n"
+            "h = capi.Handle(0); b = S.indirect_batch(700, ndim=12, seed=77)\n"
+            "r = h.indirect(b['x0'], b['t0'], b['t1'], params=capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05))\n"
+            "np.savez(%r, defect=r['defect'], phi=r['phi'], status=r['status'])\n") % (os.path.join(os.path.dirname(__file__), ".."), out)
+    env = dict(os.environ, LTO_K3=variant)
+    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    got = np.load(out)
+    assert np.all(got["status"] == 0)
+    assert rel(got["defect"], ref["defect"]) < TOL_STATE
+    assert rel(got["phi"], ref["phi"], np.abs(ref["phi"]).max(axis=(1, 2), keepdims=True)) < TOL_JAC
