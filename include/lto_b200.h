@@ -218,6 +218,24 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
                              const double* thrustLimit_traj, const double* rho_traj,
                              double* defect, int32_t* status_flag, int32_t* iters, double* er_out);
 
+/* ---- the linear subproblem of the direct solver (device-side) ------------------------
+ * lto_direct_qp: optimizeTraj of src/multiShoot_CRTBP_direct.jl:248-403 in the setting the demo runs (flagEnd = false,
+ * allowImpulsive = false): with tf_jump, p1_jump, p2_jump and the dV jumps pinned by their bounds (:288-302) the JuMP / Ipopt model is
+ * the equality-constrained convex QP   min sum_i w_i |u_i + du_i|^2  (:323-325, :367-368)   s.t.  defect + Jac_full [dX; du] = 0 (:337),
+ * dX_1[1:6] = b0, dX_N[1:6] = bf (:374-375), dX_1[7] = b0[7] when nstate = 7 (:270) -- solved exactly through its banded KKT system,
+ * one warp per trajectory, straight from the Jacobian blocks of lto_direct_defect_jac[_traj] (Jac_full is never assembled).
+ *   jac      per segment nstate x 2(nstate+3) column-major blocks, as lto_direct_defect_jac_traj returns them
+ *   defect   nstate x (n_nodes-1) per trajectory;  u_all 3 x n_nodes;  t_TU n_nodes (node weights w)
+ *   b0       per trajectory 6 (nstate 6) or 7 (nstate 7) doubles: state_0 - X_all[1:6,1] - [0,0,0,dV1] (:374) [, mass - X_all[7,1]]
+ *   bf       per trajectory 6 doubles: state_f - X_all[1:6,end] - [0,0,0,dV2] (:375)
+ *   x_update nstate x n_nodes, u_update 3 x n_nodes per trajectory (X_jump, u_jump :391-392);  status n_traj (LTO_ST_NAN: singular), may be NULL */
+int lto_direct_qp(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect,
+                  const double* u_all, const double* t_TU, const double* b0, const double* bf,
+                  double* x_update, double* u_update, int32_t* status);
+int lto_direct_qp_dev(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect,
+                      const double* u_all, const double* t_TU, const double* b0, const double* bf,
+                      double* x_update, double* u_update, int32_t* status);
+
 /* ---- peer memory: one process per GPU, results delivered to the solver rank without a collective --------
  * The rank that runs the Newton step allocates its full output arrays with lto_dev_alloc and exports them
  * (lto_ipc_export: a 64-byte cudaIpcMemHandle_t to send to the other processes by any means); every other rank

@@ -30,7 +30,7 @@ EXPORTS = [
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
     "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_dev_alloc", "lto_dev_free", "lto_ipc_export", "lto_ipc_open", "lto_ipc_close",
     "lto_push_async", "lto_sync_copies", "lto_signal_dev", "lto_wait_dev", "lto_fp64_peak_probe", "lto_debug_profile",
-    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_newton_resolve_dev", "lto_indirect_solve_batch",
+    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_newton_resolve_dev", "lto_indirect_solve_batch", "lto_direct_qp", "lto_direct_qp_dev",
 ]
 
 
@@ -106,6 +106,8 @@ def lib():
         L.lto_indirect_newton_dev.argtypes = [vp, i64, ci, ci] + [vp] * 4
         L.lto_indirect_newton_resolve_dev.argtypes = [vp, i64, ci, ci] + [vp] * 3
         L.lto_indirect_solve_batch.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 8
+        L.lto_direct_qp.argtypes = [vp, i64, ci, ci] + [vp] * 9
+        L.lto_direct_qp_dev.argtypes = [vp, i64, ci, ci] + [vp] * 9
         _lib = L
     return _lib
 
@@ -424,3 +426,21 @@ class Handle:
         self._ck(lib().lto_indirect_solve_batch(self._h, C.addressof(p), n_traj, n_nodes, int(max_iter), int(bool(flag_adjointsOnly)),
                                                 _ptr(XC), _ptr(t_TU), _ptr(tl), _ptr(rh), _ptr(defect), _ptr(flag), _ptr(iters), _ptr(er)))
         return dict(XC_all=XC, defect=defect, status_flag=flag, iters=iters, er=er)
+
+    # ---- direct method: the QP of optimizeTraj on the device ----
+    def direct_qp(self, jac, defect, u_all, t_TU, b0, bf):
+        """optimizeTraj's linear subproblem (multiShoot_CRTBP_direct.jl:248-403, flagEnd = false, allowImpulsive = false) for a batch.
+        jac: (n_traj, n_nodes-1, 2(n+3), n) column-major blocks as direct_traj returns them; defect: (n_traj, n_nodes-1, n);
+        u_all: (n_traj, n_nodes, 3); t_TU: (n_traj, n_nodes); b0: (n_traj, 6 or 7); bf: (n_traj, 6).
+        Returns (x_update (n_traj, n_nodes, n), u_update (n_traj, n_nodes, 3), status (n_traj,))."""
+        jac, defect, u_all, t_TU, b0, bf = map(_f64, (jac, defect, u_all, t_TU, b0, bf))
+        n_traj, nseg, nv, n = jac.shape
+        N = nseg + 1
+        if nv != 2 * (n + 3) or defect.shape != (n_traj, nseg, n) or u_all.shape != (n_traj, N, 3) or t_TU.shape != (n_traj, N):
+            raise ValueError("inconsistent shapes")
+        if b0.shape != (n_traj, 6 + (n == 7)) or bf.shape != (n_traj, 6):
+            raise ValueError("b0 must be (n_traj, 6 or 7) and bf (n_traj, 6)")
+        xu = np.empty((n_traj, N, n)); uu = np.empty((n_traj, N, 3)); status = np.empty(n_traj, dtype=np.int32)
+        self._ck(lib().lto_direct_qp(self._h, n_traj, N, n, _ptr(jac), _ptr(defect), _ptr(u_all), _ptr(t_TU), _ptr(b0), _ptr(bf), _ptr(xu), _ptr(uu),
+                                     _ptr(status)))
+        return xu, uu, status

@@ -24,6 +24,11 @@ cudaError_t launch_indirect_newton(const double* phi, const double* defect, doub
 cudaError_t launch_indirect_newton_resolve(const double* defect, double* work, double* update, int32_t* status, long long n_traj, int n_nodes,
                                            bool adjoints_only, cudaStream_t st);
 
+size_t direct_qp_workspace_bytes(long long n_traj, int n_nodes, int nstate);
+cudaError_t launch_direct_qp(const double* jac, const double* defect, const double* X_all, const double* u_all, const double* t,
+                             const double* b0, const double* bf, double* work, double* x_update, double* u_update, int32_t* status,
+                             long long n_traj, int n_nodes, int nstate, cudaStream_t st);
+
 namespace slv {
 
 constexpr int NA = 20;      // line-search points: alpha_all = LinRange(0.1, 1, 20)  (multiShoot_CRTBP_indirect.jl:227)
@@ -239,6 +244,70 @@ int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adj
     CK(h, cudaMemcpyAsync(xc_update, dU, nn * 12 * 8, cudaMemcpyDeviceToHost, h->s_compute));
     if (status) CK(h, cudaMemcpyAsync(status, dS, n_traj * 4, cudaMemcpyDeviceToHost, h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_compute));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    return LTO_SUCCESS;
+}
+
+// ---- direct method: the QP of optimizeTraj (multiShoot_CRTBP_direct.jl:248-403, flagEnd = false, allowImpulsive = false) ----
+int lto_direct_qp_dev(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect,
+                      const double* u_all, const double* t_TU, const double* b0, const double* bf, double* x_update, double* u_update,
+                      int32_t* status) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (nstate != 6 && nstate != 7) return fail(h, LTO_ERR_ARG, "nstate must be 6 or 7 (got %d)", nstate);
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!jac || !defect || !u_all || !t_TU || !b0 || !bf || !x_update || !u_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    CK(h, cudaSetDevice(h->device));
+    h->nwt_traj = 0;                                                      // the workspace is shared with the indirect Newton update
+    int rc = ensure(h, &h->d_nwt, &h->d_nwt_cap, direct_qp_workspace_bytes(n_traj, n_nodes, nstate)); if (rc) return rc;
+    cudaError_t e = launch_direct_qp(jac, defect, nullptr, u_all, t_TU, b0, bf, (double*)h->d_nwt, x_update, u_update, status, n_traj, n_nodes,
+                                     nstate, h->s_compute);
+    if (e != cudaSuccess) return fail(h, LTO_ERR_CUDA, "direct QP kernel launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    return LTO_SUCCESS;
+}
+
+int lto_direct_qp(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect, const double* u_all,
+                  const double* t_TU, const double* b0, const double* bf, double* x_update, double* u_update, int32_t* status) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (nstate != 6 && nstate != 7) return fail(h, LTO_ERR_ARG, "nstate must be 6 or 7 (got %d)", nstate);
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!jac || !defect || !u_all || !t_TU || !b0 || !bf || !x_update || !u_update) return fail(h, LTO_ERR_ARG, "null array argument");
+    const long long N = n_nodes, NS = nstate, NV = 2 * (NS + 3), M0 = 6 + (nstate == 7 ? 1 : 0);
+    if (h->n_child > 0) {
+        return split_trajectories(h, n_traj, [&](lto_handle* c, long long u0, long long nu) {
+            return lto_direct_qp(c, nu, n_nodes, nstate, jac + u0 * (N - 1) * NS * NV, defect + u0 * (N - 1) * NS, u_all + u0 * N * 3, t_TU + u0 * N,
+                                 b0 + u0 * M0, bf + u0 * 6, x_update + u0 * N * NS, u_update + u0 * N * 3, status ? status + u0 : nullptr);
+        });
+    }
+    CK(h, cudaSetDevice(h->device));
+    const long long T = n_traj, ns = T * (N - 1), nn = T * N;
+    const size_t bJ = al(ns * NS * NV * 8), bD = al(ns * NS * 8), bU = al(nn * 3 * 8), bT = al(nn * 8), bB0 = al(T * M0 * 8), bBf = al(T * 6 * 8),
+                 bXo = al(nn * NS * 8), bS = al(T * 4);
+    int rc = ensure(h, &h->d_out, &h->d_out_cap, bJ + bD + bU * 2 + bT + bB0 + bBf + bXo + bS); if (rc) return rc;
+    char* q = (char*)h->d_out;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    double* dJ = (double*)take(bJ); double* dD = (double*)take(bD); double* dU = (double*)take(bU); double* dT = (double*)take(bT);
+    double* dB0 = (double*)take(bB0); double* dBf = (double*)take(bBf); double* dXo = (double*)take(bXo); double* dUo = (double*)take(bU);
+    int32_t* dS = (int32_t*)take(bS);
+    cudaStream_t st = h->s_compute;
+    CK(h, cudaMemcpyAsync(dJ, jac, ns * NS * NV * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dD, defect, ns * NS * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dU, u_all, nn * 3 * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dT, t_TU, nn * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dB0, b0, T * M0 * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dBf, bf, T * 6 * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaEventRecord(h->ev_t0, st));
+    rc = lto_direct_qp_dev(h, n_traj, n_nodes, nstate, dJ, dD, dU, dT, dB0, dBf, dXo, dUo, dS); if (rc) return rc;
+    CK(h, cudaEventRecord(h->ev_t1, st));
+    CK(h, cudaMemcpyAsync(x_update, dXo, nn * NS * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(u_update, dUo, nn * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (status) CK(h, cudaMemcpyAsync(status, dS, T * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
     float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
     return LTO_SUCCESS;
 }

@@ -72,6 +72,11 @@ class GpuBackend:
         self.calls += 1
         return self.h.indirect(x0, t0, t1, params=self._ip(params), jac=False)["defect"]
 
+    def direct_qp(self, blocks_cm, defect, u_all, t, b0, bf):
+        """optimizeTraj's QP on the device (lto_direct_qp): blocks_cm (B, N-1, 2(n+3), n) column-major Jacobian blocks."""
+        self.calls += 1
+        return self.h.direct_qp(blocks_cm, defect, u_all, t, b0, bf)
+
     def indirect_newton(self, phi, defect, flag_adjointsOnly):
         """-sparse(Jac_full) \\ defect_vec on the device (lto_indirect_newton); phi (B, N-1, m, m) [.., row, col] -> (B, N, m)."""
         self.calls += 1
@@ -237,9 +242,10 @@ def _qp_direct(X_all, u_all, dV1, dV2, defect, Jac_full, n, N, state_0, state_f,
 
 def multiShoot_CRTBP_direct(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, MU, DU, TU, n_nodes, nsteps, mass, Isp, X0_times, X0_states,
                             Xf_times, Xf_states, plot_yn=False, flagEnd=False, beta=0.0, allowImpulsive=False, maxIter=100,
-                            backend=None, log=None):
+                            backend=None, log=None, device_qp=False):
     """(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, defect) = multiShoot_CRTBP_direct(...)   (:58-60, :593).
-    `log`, if a list, receives one dict per SQP iteration (iter, er, cost, alpha)."""
+    `log`, if a list, receives one dict per SQP iteration (iter, er, cost, alpha).
+    device_qp: solve the QP on the GPU (lto_direct_qp, banded KKT) instead of the dense host KKT solve (allowImpulsive = false only)."""
     if flagEnd:
         raise NotImplementedError("flagEnd = true makes the subproblem a bound-constrained NLP (Ipopt, :286-298); only the "
                                   "demo's flagEnd = false equality-constrained QP is mirrored")
@@ -269,8 +275,19 @@ def multiShoot_CRTBP_direct(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, MU, DU, TU
         ddefect_dt = (dm[0] - dm[1]) / (2 * pert_tf)
         Jac_full = np.hstack([Jac_full, ddefect_dt.ravel()[:, None]])                                     # :516
         state_0, state_f = interpEndStates(tau1, tau2, X0_times, X0_states, Xf_times, Xf_states, MU)
-        x_update, u_update, dV1_update, dV2_update, cost = _qp_direct(X_all, u_all, dV1, dV2, defect, Jac_full, n, N, state_0, state_f,
-                                                                      mass, tau, t0_TU, tf_TU, DU, TU, allowImpulsive)
+        if device_qp and not allowImpulsive:
+            b0 = state_0 - X_all[:6, 0] - np.concatenate([np.zeros(3), dV1]); bf = state_f - X_all[:6, -1] - np.concatenate([np.zeros(3), dV2])
+            if n == 7:
+                b0 = np.concatenate([b0, [mass - X_all[6, 0]]])
+            t_fixed = t0_TU + (tau + 1) / 2 * (tf_TU - t0_TU)
+            xu, uu, st = be.direct_qp(np.ascontiguousarray(blocks.transpose(0, 1, 3, 2)), defect.T[None], u_all.T[None], t_fixed[None], b0[None], bf[None])
+            x_update, u_update = xu[0].T, uu[0].T
+            dV1_update = np.zeros(3); dV2_update = np.zeros(3)
+            dt_ = np.diff(t_fixed); w_ = np.repeat(np.concatenate([dt_ / 2, [dt_[-1] / 2]]) + np.concatenate([[0.0], dt_[:-1] / 2, [0.0]]), 3)
+            cost = float(np.sum((u_all.T.ravel() + u_update.T.ravel()) ** 2 * w_) + (DU / TU) ** 2 * (np.sum(dV1 ** 2) + np.sum(dV2 ** 2)))
+        else:
+            x_update, u_update, dV1_update, dV2_update, cost = _qp_direct(X_all, u_all, dV1, dV2, defect, Jac_full, n, N, state_0, state_f,
+                                                                          mass, tau, t0_TU, tf_TU, DU, TU, allowImpulsive)
         alpha = 1.0
         if iterCount > 10:                                                                                # :559-561, lineSearch :405-430
             alpha_all = np.linspace(0.1, 1.0, 10)
