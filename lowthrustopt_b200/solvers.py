@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's two outer solvers, for running BASELINE configs 1-2
 (the demo scripts) end to end without Julia / Ipopt / SuiteSparse.
 
-    multiShoot_CRTBP_direct      src/multiShoot_CRTBP_direct.jl:58-594
+    multiShoot_CRTBP_direct      src/multiShoot_CRTBP_direct.jl:58-594   (+ multiShoot_CRTBP_direct_batch: many trajectories, QP on the device)
     multiShoot_CRTBP_indirect    src/multiShoot_CRTBP_indirect.jl:58-345
     reduceFuel_indirect          src/HelperFunctions.jl:105-193   (+ reduceFuel_indirect_batch: many trajectories, one device call per round)
     trajectory_stack_guess       CRTBP_Multishoot_direct_demo.jl:117-157
@@ -303,6 +303,54 @@ def multiShoot_CRTBP_direct(X_all, u_all, tau1, tau2, t_TU, dV1, dV2, MU, DU, TU
         if log is not None:
             log.append(dict(iter=iterCount, er=er, cost=cost, alpha=alpha))
     return X_all, u_all, tau1, tau2, t_TU, dV1, dV2, defect
+
+
+def multiShoot_CRTBP_direct_batch(X_all, u_all, tau1, tau2, t_TU, MU, DU, TU, n_nodes, nsteps, mass, Isp, X0_times, X0_states, Xf_times, Xf_states,
+                                  maxIter=100, backend=None, log=None):
+    """multiShoot_CRTBP_direct (:465-594; flagEnd = false, allowImpulsive = false, dV = 0: the demo's setting) for a BATCH of independent
+    trajectories with every heavy step on the device: per SQP iteration ONE launch for all defects + Jacobian blocks
+    (lto_direct_defect_jac_traj), ONE launch for all QPs (lto_direct_qp), one launch for the 10-point line searches of all
+    trajectories (from iteration 11 on, :559-561), one launch for the defect check (:585).  A trajectory stops when its
+    max defect <= 1e-6 (:491) or after maxIter iterations; the others go on.
+    X_all: (T, n, N), u_all: (T, 3, N), t_TU: (T, N), tau1 / tau2: scalars or (T,).
+    Returns (X_all, u_all, defect (T, n, N-1), iters (T,))."""
+    be = backend or default_backend()
+    X = np.array(X_all, dtype=np.float64).transpose(0, 2, 1).copy(); U = np.array(u_all, dtype=np.float64).transpose(0, 2, 1).copy()
+    t = np.array(t_TU, dtype=np.float64)
+    T, N, n = X.shape
+    t1 = np.broadcast_to(np.asarray(tau1, dtype=np.float64), (T,)); t2 = np.broadcast_to(np.asarray(tau2, dtype=np.float64), (T,))
+    ends = [interpEndStates(float(t1[j]), float(t2[j]), X0_times, X0_states, Xf_times, Xf_states, MU) for j in range(T)]
+    s0 = np.stack([e[0] for e in ends]); sf = np.stack([e[1] for e in ends])
+    defect, _ = be.direct_defect(X, U, t, nsteps, Isp, MU, DU, TU)                                          # :486
+    er = np.max(np.abs(defect), axis=(1, 2))
+    iters = np.zeros(T, dtype=np.int32)
+    active = er > 1e-6
+    it = 0
+    while active.any() and it < maxIter:
+        it += 1
+        idx = np.nonzero(active)[0]
+        Xa, Ua, ta = X[idx], U[idx], t[idx]
+        d, _, blocks = be.direct_blocks(Xa, Ua, ta, nsteps, Isp, MU, DU, TU)                                # :500 (blocks [.., row, col])
+        b0 = s0[idx] - Xa[:, 0, :6]; bf = sf[idx] - Xa[:, -1, :6]                                           # :374-375 (dV = 0)
+        if n == 7:
+            b0 = np.concatenate([b0, (mass - Xa[:, 0, 6])[:, None]], axis=1)                                # :270
+        xu, uu, st = be.direct_qp(np.ascontiguousarray(blocks.transpose(0, 1, 3, 2)), d, Ua, ta, b0, bf)    # optimizeTraj (:248-403)
+        alpha = np.ones(len(idx))
+        if it > 10:                                                                                         # lineSearch (:405-430), all trajectories at once
+            al = np.linspace(0.1, 1.0, 10)
+            Xt = (Xa[None] + al[:, None, None, None] * xu[None]).reshape(-1, N, n); Ut = (Ua[None] + al[:, None, None, None] * uu[None]).reshape(-1, N, 3)
+            dd, _ = be.direct_defect(Xt, Ut, np.tile(ta, (10, 1)), nsteps, Isp, MU, DU, TU)
+            ers = np.sum(dd.reshape(10, len(idx), -1) ** 2, axis=2)
+            alpha = al[np.argmin(ers, axis=0)]
+        X[idx] = Xa + alpha[:, None, None] * xu; U[idx] = Ua + alpha[:, None, None] * uu                    # :563-569
+        dn, _ = be.direct_defect(X[idx], U[idx], ta, nsteps, Isp, MU, DU, TU)                               # :585
+        defect[idx] = dn
+        er[idx] = np.max(np.abs(dn), axis=(1, 2))
+        iters[idx] = it
+        if log is not None:
+            log.append(dict(iter=it, n_active=len(idx), er=er.copy(), alpha=alpha.copy()))
+        active = er > 1e-6
+    return X.transpose(0, 2, 1).copy(), U.transpose(0, 2, 1).copy(), defect.transpose(0, 2, 1).copy(), iters
 
 
 # --------------------------------------------------------------------------- indirect method

@@ -71,3 +71,23 @@ class OracleBackend:
                                                    flag_adjointsOnly, max_iter, p, rho0 if rho is None else float(rho[j]), backend=self, log=log)
             Xo[j] = X.T; Do[j] = d.T; fl[j] = st; it[j] = len(log)
         return dict(XC_all=Xo, defect=Do, status_flag=fl, iters=it)
+
+    def direct_qp(self, blocks_cm, defect, u_all, t, b0, bf):
+        """Stand-in for lto_direct_qp without a GPU: the host KKT mirror (solvers._qp_direct), one trajectory after the other."""
+        from lowthrustopt_b200 import solvers as S
+        T, Nm1, nv, n = blocks_cm.shape
+        N = Nm1 + 1
+        xu = np.zeros((T, N, n)); uu = np.zeros((T, N, 3))
+        for j in range(T):
+            Jf = S._band_direct(blocks_cm[j].transpose(0, 2, 1), n, N)
+            Jf = np.hstack([Jf, np.zeros((Jf.shape[0], 1))])
+            tau = (t[j] - t[j, 0]) / (t[j, -1] - t[j, 0]) * 2 - 1
+            # b0 / bf are the right-hand sides of the end constraints: feed them through X_all = 0
+            mass = b0[j][6] if n == 7 else 1e3
+            xr, ur, *_ = S._qp_direct(np.zeros((n, N)), u_all[j].T, np.zeros(3), np.zeros(3), defect[j].T, Jf, n, N, b0[j][:6].copy(), bf[j].copy(), mass,
+                                      tau, t[j, 0], t[j, -1], capi_DU, capi_TU, False)
+            xu[j] = xr.T; uu[j] = ur.T
+        return xu, uu, np.zeros(T, dtype=np.int32)
+
+
+from lowthrustopt_b200.capi import DU as capi_DU, TU as capi_TU  # noqa: E402

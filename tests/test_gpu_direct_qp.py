@@ -67,3 +67,22 @@ def test_direct_qp_flags_singular_input(lto):
     jac = np.zeros((T, N - 1, 18, 6)); dfc = np.zeros((T, N - 1, 6)); U = np.zeros((T, N, 3)); t = np.tile(np.linspace(0, 1, N), (T, 1))
     xu, uu, st = lto.direct_qp(jac, dfc, U, t, np.zeros((T, 6)), np.zeros((T, 6)))
     assert np.all(st == 1)
+
+
+def test_direct_batch_matches_per_trajectory_solves(demo):
+    """multiShoot_CRTBP_direct_batch (every heavy step batched on the device) against the one-trajectory mirror with the host QP."""
+    gpu, fx, (XC, t_TU, tau1, tau2, s0, sf) = demo
+    rng = np.random.default_rng(12)
+    T = 4
+    for n in (6, 7):
+        Xs = np.stack([XC[:6] + (2e-4 * j) * rng.standard_normal((6, 30)) for j in range(T)])
+        if n == 7:
+            Xs = np.concatenate([Xs, 1000.0 * np.ones((T, 1, 30))], axis=1)
+        Us = np.zeros((T, 3, 30)); tb = np.broadcast_to(t_TU, (T, 30)).copy()
+        Xb, Ub, db, itb = S.multiShoot_CRTBP_direct_batch(Xs, Us, tau1, tau2, tb, MU, DU, TU, 30, 10, 1e3, 2000.0, *fx, backend=gpu)
+        for j in range(T):
+            log = []
+            out = S.multiShoot_CRTBP_direct(Xs[j], Us[j], tau1, tau2, t_TU, np.zeros(3), np.zeros(3), MU, DU, TU, 30, 10, 1e3, 2000.0, *fx, backend=gpu, log=log)
+            assert itb[j] == len(log), (n, j, itb[j], len(log))
+            assert np.abs(Xb[j] - out[0]).max() < 1e-8 and np.abs(Ub[j] - out[1]).max() < 1e-8, (n, j)
+            assert np.abs(db[j]).max() <= 1e-6

@@ -65,6 +65,20 @@ def test_direct_nstate7_mass_row(demo):
     assert m[0] == 1000.0 and np.all(np.diff(m) < 0) and 995 < m[-1] < 1000
 
 
+def test_direct_batch_driver_matches_the_one_trajectory_mirror(demo):
+    """multiShoot_CRTBP_direct_batch (batched calls, per-trajectory stopping) against multiShoot_CRTBP_direct, both oracle-backed."""
+    rng = np.random.default_rng(12)
+    Xs = np.stack([demo["XC"][:6] + (2e-4 * j) * rng.standard_normal((6, 30)) for j in range(2)])
+    Us = np.zeros((2, 3, 30)); tb = np.stack([demo["t"]] * 2)
+    Xb, Ub, db, itb = S.multiShoot_CRTBP_direct_batch(Xs, Us, demo["tau1"], demo["tau2"], tb, MU, DU, TU, 30, 10, 1e3, 2000.0, *demo["fx"], backend=demo["be"])
+    for j in range(2):
+        log = []
+        out = S.multiShoot_CRTBP_direct(Xs[j], Us[j], demo["tau1"], demo["tau2"], demo["t"], np.zeros(3), np.zeros(3), MU, DU, TU, 30, 10, 1e3, 2000.0,
+                                        *demo["fx"], backend=demo["be"], log=log)
+        assert itb[j] == len(log) and np.abs(Xb[j] - out[0]).max() < 1e-12 and np.abs(Ub[j] - out[1]).max() < 1e-12
+        assert np.abs(db[j]).max() <= 1e-6
+
+
 def test_direct_flagEnd_is_refused(demo):
     X0t, X0, Xft, Xf = demo["fx"]
     with pytest.raises(NotImplementedError):

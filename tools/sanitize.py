@@ -22,5 +22,16 @@ for adj in (False, True):
     assert np.all(st == 0)
 XC = c["XC_all"].copy(); XC[:, :, 6:] *= 0.1
 s = h.indirect_solve_batch(XC, c["t_TU"], params=p2, max_iter=6)
+from lowthrustopt_b200 import solvers as SV
+fx = SV.demo_fixtures()
+gpu = SV.GpuBackend(handle=h)
+XCg, tg, tau1, tau2, s0, sf = SV.trajectory_stack_guess(fx[1], fx[3], backend=gpu)
+for n in (6, 7):
+    Xs = np.stack([XCg[:6]] * 3)
+    if n == 7:
+        Xs = np.concatenate([Xs, 1000.0 * np.ones((3, 1, 30))], axis=1)
+    Xb, Ub, db, itb = SV.multiShoot_CRTBP_direct_batch(Xs, np.zeros((3, 3, 30)), tau1, tau2, np.stack([tg] * 3), capi.MU, capi.DU, capi.TU, 30, 10, 1e3, 2000.0,
+                                                       *fx, backend=gpu)
+    assert np.abs(db).max() <= 1e-6, (n, np.abs(db).max())
 print("sanitize run ok: solve flags", s["status_flag"], "iters", s["iters"], "launches", h.launches)
 h.close()
