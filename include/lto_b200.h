@@ -236,6 +236,19 @@ int lto_direct_qp_dev(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, co
                       const double* u_all, const double* t_TU, const double* b0, const double* bf,
                       double* x_update, double* u_update, int32_t* status);
 
+/* lto_direct_solve_batch: the SQP loop of multiShoot_CRTBP_direct (src/multiShoot_CRTBP_direct.jl:465-594) for n_traj independent
+ * trajectories, resident on the device, in the demo's setting (flagEnd = false, allowImpulsive = false, dV1 = dV2 = 0, FIXED grid): first
+ * nominal run (:486); per iteration jacobianCalc as one launch (:500), the QP of optimizeTraj (lto_direct_qp_dev), the 10-point line search
+ * from iteration 11 on (:559-561, :405-430; all 10 x n_traj trials in one launch), the update (:563-564) and the defect check (:585-588).
+ * As in the reference every trajectory does at least one iteration (er starts at 1.0, :490) and stops when its max defect <= 1e-6 (:491) or
+ * after max_iter iterations; tau1, tau2 and tf do not move in this setting, so the end states are constants of the call.
+ *   X_all (nstate x n_nodes), u_all (3 x n_nodes): in/out per trajectory;  t_TU: n_nodes per trajectory
+ *   state_0, state_f: 6 doubles per trajectory = interpEndStates(tau1, tau2, ...) (:483);  mass: mass0 of :270 (nstate 7)
+ *   defect: out, nstate x (n_nodes-1) per trajectory (may be NULL); iters, er_out: out, n_traj (may be NULL) */
+int lto_direct_solve_batch(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate, int nsteps, int max_iter,
+                           double* X_all, double* u_all, const double* t_TU, const double* state_0, const double* state_f, double mass,
+                           double* defect, int32_t* iters, double* er_out);
+
 /* ---- peer memory: one process per GPU, results delivered to the solver rank without a collective --------
  * The rank that runs the Newton step allocates its full output arrays with lto_dev_alloc and exports them
  * (lto_ipc_export: a 64-byte cudaIpcMemHandle_t to send to the other processes by any means); every other rank

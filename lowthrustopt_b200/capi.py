@@ -30,7 +30,7 @@ EXPORTS = [
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
     "lto_direct_dev", "lto_indirect_dev", "lto_sumsq_dev", "lto_dev_alloc", "lto_dev_free", "lto_ipc_export", "lto_ipc_open", "lto_ipc_close",
     "lto_push_async", "lto_sync_copies", "lto_signal_dev", "lto_wait_dev", "lto_fp64_peak_probe", "lto_debug_profile",
-    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_newton_resolve_dev", "lto_indirect_solve_batch", "lto_direct_qp", "lto_direct_qp_dev",
+    "lto_indirect_newton", "lto_indirect_newton_dev", "lto_indirect_newton_resolve_dev", "lto_indirect_solve_batch", "lto_direct_qp", "lto_direct_qp_dev", "lto_direct_solve_batch",
 ]
 
 
@@ -108,6 +108,7 @@ def lib():
         L.lto_indirect_solve_batch.argtypes = [vp, vp, i64, ci, ci, ci] + [vp] * 8
         L.lto_direct_qp.argtypes = [vp, i64, ci, ci] + [vp] * 9
         L.lto_direct_qp_dev.argtypes = [vp, i64, ci, ci] + [vp] * 9
+        L.lto_direct_solve_batch.argtypes = [vp, vp, i64, ci, ci, ci, ci] + [vp] * 5 + [C.c_double] + [vp] * 3
         _lib = L
     return _lib
 
@@ -444,3 +445,18 @@ class Handle:
         self._ck(lib().lto_direct_qp(self._h, n_traj, N, n, _ptr(jac), _ptr(defect), _ptr(u_all), _ptr(t_TU), _ptr(b0), _ptr(bf), _ptr(xu), _ptr(uu),
                                      _ptr(status)))
         return xu, uu, status
+
+    def direct_solve_batch(self, X_all, u_all, t_TU, state_0, state_f, mass=1000.0, nsteps=10, max_iter=100, params=None):
+        """multiShoot_CRTBP_direct (:465-594, the demo's setting) for n_traj trajectories at once, iterated on the device.
+        X_all: (n_traj, n_nodes, nstate); u_all: (n_traj, n_nodes, 3); t_TU: (n_traj, n_nodes); state_0, state_f: (n_traj, 6).
+        Returns dict(X_all, u_all, defect, iters, er)."""
+        p = params or direct_params()
+        X = np.array(X_all, dtype=np.float64, order="C"); U = np.array(u_all, dtype=np.float64, order="C")
+        t_TU, state_0, state_f = map(_f64, (t_TU, state_0, state_f))
+        n_traj, n_nodes, ns = X.shape
+        if U.shape != (n_traj, n_nodes, 3) or t_TU.shape != (n_traj, n_nodes) or state_0.shape != (n_traj, 6) or state_f.shape != (n_traj, 6):
+            raise ValueError("inconsistent shapes")
+        defect = np.empty((n_traj, n_nodes - 1, ns)); iters = np.empty(n_traj, dtype=np.int32); er = np.empty(n_traj)
+        self._ck(lib().lto_direct_solve_batch(self._h, C.addressof(p), n_traj, n_nodes, ns, int(nsteps), int(max_iter), _ptr(X), _ptr(U), _ptr(t_TU),
+                                              _ptr(state_0), _ptr(state_f), float(mass), _ptr(defect), _ptr(iters), _ptr(er)))
+        return dict(X_all=X, u_all=U, defect=defect, iters=iters, er=er)

@@ -67,7 +67,7 @@ __global__ void k_soc_mask(const double* __restrict__ umax, const int* __restric
 
 // line search (:243-245): alpha = alpha_all[er .== minimum(er)][1]; scale = alpha for iterating trajectories, 0 otherwise
 __global__ void k_pick_alpha(const double* __restrict__ ers, const double* __restrict__ alpha_all, const int* __restrict__ active,
-                             double* __restrict__ alpha, double* __restrict__ scale, long long n, int use_ls) {
+                             double* __restrict__ alpha, double* __restrict__ scale, long long n, int use_ls, int n_alpha = NA) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     double al = 1.0;
@@ -75,7 +75,7 @@ __global__ void k_pick_alpha(const double* __restrict__ ers, const double* __res
         // minimum() propagates NaN in Julia, and then no entry compares equal: the reference would throw.  Here a NaN merit
         // value never wins; if all are NaN the full step is taken and the NaN surfaces in the defect check.
         double best = INFINITY; int ib = -1;
-        for (int a = 0; a < NA; ++a) { const double e = ers[(long long)a * n + j]; if (e < best) { best = e; ib = a; } }
+        for (int a = 0; a < n_alpha; ++a) { const double e = ers[(long long)a * n + j]; if (e < best) { best = e; ib = a; } }
         al = ib >= 0 ? alpha_all[ib] : 1.0;
     }
     alpha[j] = al;
@@ -93,15 +93,15 @@ __global__ void k_tile(const double* __restrict__ src, double* __restrict__ dst,
 //   flag: 0 converged / still iterating, 1 gave up (maxIter or abort)
 __global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ active, const int* __restrict__ orig, int* __restrict__ iters,
                            int* __restrict__ flag, double* __restrict__ er_full, unsigned long long* __restrict__ n_active, long long n, int it,
-                           int max_iter) {
+                           int max_iter, double tol = 1e-10, double abort_above = 1e3, int force_first = 0) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int o = orig[j];
     const double e = er[j];
     er_full[o] = e;
     if (it > 0) iters[o] = it;
-    bool go = e > 1e-10;                                  // NaN -> false: the reference's while-condition ends the loop as well
-    if (go && !(e <= 1e3)) { go = false; flag[o] = 1; }   // "Not likely to converge. Aborting." (:333-336)
+    bool go = e > tol || (force_first && it == 0);        // NaN -> false: the reference's while-condition ends the loop as well
+    if (go && !(e <= abort_above) && !(force_first && it == 0)) { go = false; flag[o] = 1; }   // "Not likely to converge. Aborting." (:333-336)
     if (go && it >= max_iter) { go = false; flag[o] = 1; }   // "Reached max iteration count" (:282-286)
     active[j] = go ? 1 : 0;
     if (go) atomicAdd(n_active, 1ull);
@@ -141,9 +141,23 @@ __global__ void __launch_bounds__(256) k_compact_rows(const V* __restrict__ src,
     }
 }
 // line-search scale table scale[a*n + j] = alpha_a, and initial bookkeeping
-__global__ void k_fill_ls(const double* __restrict__ alpha_all, double* __restrict__ table, long long n) {
+__global__ void k_fill_ls(const double* __restrict__ alpha_all, double* __restrict__ table, long long n, int n_alpha = NA) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n * NA) table[i] = alpha_all[i / n];
+    if (i < n * n_alpha) table[i] = alpha_all[i / n];
+}
+// right-hand sides of the direct solver's end constraints (multiShoot_CRTBP_direct.jl:374-375, :270; dV = 0):
+//   b0 = state_0 - X_all[1:6, 1] (, mass - X_all[7, 1]),  bf = state_f - X_all[1:6, end]
+__global__ void k_direct_ends(const double* __restrict__ X, const double* __restrict__ s0, const double* __restrict__ sf, const int* __restrict__ orig,
+                              double mass, double* __restrict__ b0, double* __restrict__ bf, long long n, int N, int ns) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int m0 = 6 + (ns == 7 ? 1 : 0);
+    const long long o = orig[j];
+    for (int k = 0; k < 6; ++k) {
+        b0[j * m0 + k] = s0[o * 6 + k] - X[(j * N) * ns + k];
+        bf[j * 6 + k] = sf[o * 6 + k] - X[(j * N + N - 1) * ns + k];
+    }
+    if (ns == 7) b0[j * m0 + 6] = mass - X[(j * N) * ns + 6];
 }
 __global__ void k_set_int(int* __restrict__ v, int value, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,6 +321,152 @@ int lto_direct_qp(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const 
     CK(h, cudaMemcpyAsync(x_update, dXo, nn * NS * 8, cudaMemcpyDeviceToHost, st));
     CK(h, cudaMemcpyAsync(u_update, dUo, nn * 3 * 8, cudaMemcpyDeviceToHost, st));
     if (status) CK(h, cudaMemcpyAsync(status, dS, T * 4, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    return LTO_SUCCESS;
+}
+
+// multiShoot_CRTBP_direct's SQP loop (:465-594) resident on the device, for n_traj independent trajectories in the demo's setting
+// (flagEnd = false, allowImpulsive = false, dV1 = dV2 = 0: tau1, tau2, tf stay fixed, so state_0 / state_f are constants of the call).
+int lto_direct_solve_batch(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate, int nsteps, int max_iter,
+                           double* X_all, double* u_all, const double* t_TU, const double* state_0, const double* state_f, double mass,
+                           double* defect, int32_t* iters, double* er_out) {
+    if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
+    if (!p) return fail(h, LTO_ERR_ARG, "null params");
+    if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
+    if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
+    if (nstate != 6 && nstate != 7) return fail(h, LTO_ERR_ARG, "nstate must be 6 or 7 (got %d)", nstate);
+    if (max_iter < 0) return fail(h, LTO_ERR_ARG, "negative max_iter");
+    if (p->mode != LTO_FIXED) return fail(h, LTO_ERR_ARG, "lto_direct_solve_batch runs the reference's fixed-grid ode7_8 path (LTO_FIXED)");
+    if (n_traj == 0) return LTO_SUCCESS;
+    if (!X_all || !u_all || !t_TU || !state_0 || !state_f) return fail(h, LTO_ERR_ARG, "null array argument");
+    const long long N = n_nodes, NS = nstate, NV = 2 * (NS + 3), M0 = 6 + (nstate == 7 ? 1 : 0);
+    if (h->n_child > 0) {
+        return split_trajectories(h, n_traj, [&](lto_handle* c, long long u0, long long nu) {
+            return lto_direct_solve_batch(c, p, nu, n_nodes, nstate, nsteps, max_iter, X_all + u0 * N * NS, u_all + u0 * N * 3, t_TU + u0 * N,
+                                          state_0 + u0 * 6, state_f + u0 * 6, mass, defect ? defect + u0 * (N - 1) * NS : nullptr,
+                                          iters ? iters + u0 : nullptr, er_out ? er_out + u0 : nullptr);
+        });
+    }
+    if (n_traj > 0x7fffffffll) return fail(h, LTO_ERR_ARG, "too many trajectories");
+    CK(h, cudaSetDevice(h->device));
+    const int NA = 10;                                                    // alpha_all = LinRange(0.1, 1, 10)  (:411)
+    const long long T = n_traj, ns = T * (N - 1), nn = T * N;
+    const long long LX = N * NS, LU = N * 3, LD = (N - 1) * NS;
+    cudaStream_t st = h->s_compute;
+    const size_t bX = al(nn * NS * 8), bU = al(nn * 3 * 8), bT = al(nn * 8), bD = al(ns * NS * 8), bJ = al(ns * NS * NV * 8), bE = al(T * 6 * 8),
+                 bB0 = al(T * M0 * 8), bVec = al((size_t)NA * T * 8), bInt = al(T * 4), bErr = al((size_t)NA * ns * 8);
+    size_t need = bX * 3 + bU * 3 + bT + bD * 3 + bJ + bE * 2 + bB0 + bE + (size_t)NA * (bX + bU + bT + bD) + bVec * 6 + bInt * 6 + bErr + al(NA * 8) + 256;
+    int rc = ensure(h, &h->d_slv, &h->d_slv_cap, need); if (rc) return rc;
+    char* q = (char*)h->d_slv;
+    auto take = [&](size_t b) { char* r = q; q += b; return r; };
+    double* dX = (double*)take(bX); double* dXu = (double*)take(bX); double* dXout = (double*)take(bX);
+    double* dU = (double*)take(bU); double* dUu = (double*)take(bU); double* dUout = (double*)take(bU);
+    double* dT = (double*)take(bT);
+    double* dDef = (double*)take(bD); double* dDtmp = (double*)take(bD); double* dDefOut = (double*)take(bD);
+    double* dJ = (double*)take(bJ);
+    double* dS0 = (double*)take(bE); double* dSf = (double*)take(bE); double* dB0 = (double*)take(bB0); double* dBf = (double*)take(bE);
+    double* dTrX = (double*)take((size_t)NA * bX); double* dTrU = (double*)take((size_t)NA * bU); double* dTrT = (double*)take((size_t)NA * bT);
+    double* dTrD = (double*)take((size_t)NA * bD);
+    double* dEr = (double*)take(bVec); double* dErs = (double*)take(bVec); double* dAlpha = (double*)take(bVec); double* dScale = (double*)take(bVec);
+    double* dLsTable = (double*)take(bVec); double* dErOut = (double*)take(bVec);
+    int* dActive = (int*)take(bInt); int* dIters = (int*)take(bInt); int* dFlag = (int*)take(bInt);
+    int* dOrig = (int*)take(bInt); int* dOrig2 = (int*)take(bInt); int* dPos = (int*)take(bInt);
+    double* dErrs = (double*)take(bErr);
+    double* dAlphaAll = (double*)take(al(NA * 8));
+    unsigned long long* dCount = (unsigned long long*)take(256);
+    CK(h, cudaMemcpyAsync(dX, X_all, nn * NS * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dU, u_all, nn * 3 * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dT, t_TU, nn * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dS0, state_0, T * 6 * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaMemcpyAsync(dSf, state_f, T * 6 * 8, cudaMemcpyHostToDevice, st));
+    double alpha_all[10];
+    for (int a = 0; a < NA; ++a) alpha_all[a] = 0.1 + (double)a * ((1.0 - 0.1) / (double)(NA - 1));
+    alpha_all[NA - 1] = 1.0;
+    CK(h, cudaMemcpyAsync(dAlphaAll, alpha_all, NA * 8, cudaMemcpyHostToDevice, st));
+    CK(h, cudaStreamSynchronize(st));
+    CK(h, cudaMemsetAsync(dIters, 0, T * 4, st));
+    CK(h, cudaMemsetAsync(dFlag, 0, T * 4, st));
+    slv::k_iota<<<slv::nblk(T, 256), 256, 0, st>>>(dOrig, dActive, T);
+    h->launches += 1;
+    CK(h, cudaEventRecord(h->ev_t0, st));
+    long long nc = T;
+    auto grid_for = [&](long long n) { return std::min<unsigned>(slv::nblk(n, 256), 148u * 16u); };
+    auto defect_pass = [&](const double* X, const double* U, const double* T_, long long ntr, double* D, double* J) -> int {
+        return lto_direct_dev(h, p, ntr * (N - 1), n_nodes, nstate, nsteps, X, nullptr, U, nullptr, T_, nullptr, D, dErrs, nullptr, J);
+    };
+    auto rowmax = [&](const double* v, long long rows, long long len, double* out) {
+        slv::k_rowmaxabs<<<slv::nblk(rows * 32, 256), 256, 0, st>>>(v, rows, len, out); h->launches += 1;
+    };
+    auto axpy = [&](const double* x, const double* u, const double* scale, double* out, long long rows, long long len, int reps) {
+        dim3 g(std::min<unsigned>(slv::nblk(rows * len, 256), 148u * 16u), (unsigned)reps);
+        slv::k_axpy_rows<<<g, 256, 0, st>>>(x, u, scale, out, rows, len); h->launches += 1;
+    };
+    auto iter_end = [&](int it, long long* n_next) -> int {
+        CK(h, cudaMemsetAsync(dCount, 0, 8, st));
+        // `er = 1.0` before the loop (:490): every trajectory does one iteration whatever its first defect; no abort rule in the direct solver
+        slv::k_iter_end<<<slv::nblk(nc, 256), 256, 0, st>>>(dEr, dActive, dOrig, dIters, dFlag, dErOut, dCount, nc, it, max_iter, 1e-6, INFINITY, 1);
+        slv::k_retire_rows<<<grid_for(nc * LX), 256, 0, st>>>(dX, dXout, dOrig, dActive, nc, LX);
+        slv::k_retire_rows<<<grid_for(nc * LU), 256, 0, st>>>(dU, dUout, dOrig, dActive, nc, LU);
+        slv::k_retire_rows<<<grid_for(nc * LD), 256, 0, st>>>(dDef, dDefOut, dOrig, dActive, nc, LD);
+        h->launches += 4;
+        unsigned long long na = 0;
+        CK(h, cudaMemcpyAsync(&na, dCount, 8, cudaMemcpyDeviceToHost, st));
+        CK(h, cudaStreamSynchronize(st));
+        if (na > 0 && (long long)na < nc) {
+            slv::k_scan_active<<<1, 1024, 0, st>>>(dActive, dPos, nc);
+            slv::k_compact_rows<double><<<grid_for(nc * LX), 256, 0, st>>>(dX, dXu, dPos, dActive, nc, LX);
+            CK(h, cudaMemcpyAsync(dX, dXu, (size_t)na * LX * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<double><<<grid_for(nc * LU), 256, 0, st>>>(dU, dUu, dPos, dActive, nc, LU);
+            CK(h, cudaMemcpyAsync(dU, dUu, (size_t)na * LU * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<double><<<grid_for(nc * LD), 256, 0, st>>>(dDef, dDtmp, dPos, dActive, nc, LD);
+            CK(h, cudaMemcpyAsync(dDef, dDtmp, (size_t)na * LD * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<double><<<grid_for(nc * N), 256, 0, st>>>(dT, dTrT, dPos, dActive, nc, N);
+            CK(h, cudaMemcpyAsync(dT, dTrT, (size_t)na * N * 8, cudaMemcpyDeviceToDevice, st));
+            slv::k_compact_rows<int><<<grid_for(nc), 256, 0, st>>>(dOrig, dOrig2, dPos, dActive, nc, 1);
+            CK(h, cudaMemcpyAsync(dOrig, dOrig2, (size_t)na * 4, cudaMemcpyDeviceToDevice, st));
+            slv::k_set_int<<<slv::nblk((long long)na, 256), 256, 0, st>>>(dActive, 1, (long long)na);
+            h->launches += 7;
+        }
+        *n_next = (long long)na;
+        return 0;
+    };
+
+    // ---- first nominal run (:486); er starts at 1.0 (:490)
+    rc = defect_pass(dX, dU, dT, nc, dDef, nullptr); if (rc) return rc;
+    rowmax(dDef, nc, LD, dEr);
+    long long n_next = 0;
+    rc = iter_end(0, &n_next); if (rc) return rc;
+    int it = 0;
+    while (n_next > 0 && it < max_iter) {
+        nc = n_next;
+        ++it;
+        rc = defect_pass(dX, dU, dT, nc, dDef, dJ); if (rc) return rc;                          // jacobianCalc (:500): all blocks in one launch
+        slv::k_direct_ends<<<slv::nblk(nc, 256), 256, 0, st>>>(dX, dS0, dSf, dOrig, mass, dB0, dBf, nc, n_nodes, nstate); h->launches += 1;
+        rc = lto_direct_qp_dev(h, nc, n_nodes, nstate, dJ, dDef, dU, dT, dB0, dBf, dXu, dUu, nullptr); if (rc) return rc;   // optimizeTraj (:248-403)
+        const int use_ls = it > 10;                                                               // :559-561
+        if (use_ls) {
+            slv::k_fill_ls<<<slv::nblk(nc * NA, 256), 256, 0, st>>>(dAlphaAll, dLsTable, nc, NA);
+            slv::k_tile<<<slv::nblk((long long)NA * nc * N, 256), 256, 0, st>>>(dT, dTrT, nc * N, NA);
+            h->launches += 2;
+            axpy(dX, dXu, dLsTable, dTrX, nc, LX, NA);                                            // X_all + x_update*alpha (:418)
+            axpy(dU, dUu, dLsTable, dTrU, nc, LU, NA);                                            // u_all + u_update*alpha (:419)
+            rc = defect_pass(dTrX, dTrU, dTrT, (long long)NA * nc, dTrD, nullptr); if (rc) return rc;   // :422, all 10 x n trial trajectories in one launch
+            rc = lto_sumsq_dev(h, dTrD, (long long)NA * nc, LD, dErs); if (rc) return rc;         // er[ind] = sum(defect[:].^2) (:424)
+        }
+        slv::k_pick_alpha<<<slv::nblk(nc, 256), 256, 0, st>>>(dErs, dAlphaAll, dActive, dAlpha, dScale, nc, use_ls, NA); h->launches += 1;
+        axpy(dX, dXu, dScale, dX, nc, LX, 1);                                                     // :563
+        axpy(dU, dUu, dScale, dU, nc, LU, 1);                                                     // :564
+        rc = defect_pass(dX, dU, dT, nc, dDef, nullptr); if (rc) return rc;                       // :585
+        rowmax(dDef, nc, LD, dEr);                                                                // :588
+        rc = iter_end(it, &n_next); if (rc) return rc;
+    }
+    CK(h, cudaEventRecord(h->ev_t1, st));
+    CK(h, cudaMemcpyAsync(X_all, dXout, nn * NS * 8, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaMemcpyAsync(u_all, dUout, nn * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (defect) CK(h, cudaMemcpyAsync(defect, dDefOut, ns * NS * 8, cudaMemcpyDeviceToHost, st));
+    if (iters) CK(h, cudaMemcpyAsync(iters, dIters, T * 4, cudaMemcpyDeviceToHost, st));
+    if (er_out) CK(h, cudaMemcpyAsync(er_out, dErOut, T * 8, cudaMemcpyDeviceToHost, st));
     CK(h, cudaStreamSynchronize(st));
     float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
     return LTO_SUCCESS;

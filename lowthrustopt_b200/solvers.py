@@ -322,7 +322,7 @@ def multiShoot_CRTBP_direct_batch(X_all, u_all, tau1, tau2, t_TU, MU, DU, TU, n_
     ends = [interpEndStates(float(t1[j]), float(t2[j]), X0_times, X0_states, Xf_times, Xf_states, MU) for j in range(T)]
     s0 = np.stack([e[0] for e in ends]); sf = np.stack([e[1] for e in ends])
     defect, _ = be.direct_defect(X, U, t, nsteps, Isp, MU, DU, TU)                                          # :486
-    er = np.max(np.abs(defect), axis=(1, 2))
+    er = np.ones(T)                                                                                         # `er = 1.0` (:490): one iteration always runs
     iters = np.zeros(T, dtype=np.int32)
     active = er > 1e-6
     it = 0

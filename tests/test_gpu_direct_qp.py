@@ -86,3 +86,30 @@ def test_direct_batch_matches_per_trajectory_solves(demo):
             assert itb[j] == len(log), (n, j, itb[j], len(log))
             assert np.abs(Xb[j] - out[0]).max() < 1e-8 and np.abs(Ub[j] - out[1]).max() < 1e-8, (n, j)
             assert np.abs(db[j]).max() <= 1e-6
+
+
+def test_direct_solve_batch_resident_loop(demo, lto):
+    """lto_direct_solve_batch (the SQP loop resident on the device) against the one-trajectory mirror with the host QP."""
+    gpu, fx, (XC, t_TU, tau1, tau2, s0, sf) = demo
+    rng = np.random.default_rng(21)
+    T = 6
+    state_0, state_f = S.interpEndStates(tau1, tau2, *fx, MU)
+    for n in (6, 7):
+        Xs = np.stack([XC[:6] + (2e-4 * j) * rng.standard_normal((6, 30)) for j in range(T)])
+        if n == 7:
+            Xs = np.concatenate([Xs, 1000.0 * np.ones((T, 1, 30))], axis=1)
+        Us = np.zeros((T, 3, 30))
+        for max_iter in (100, 2):
+            r = lto.direct_solve_batch(Xs.transpose(0, 2, 1), Us.transpose(0, 2, 1), np.stack([t_TU] * T), np.stack([state_0] * T), np.stack([state_f] * T),
+                                       mass=1e3, nsteps=10, max_iter=max_iter, params=capi.direct_params(Isp=2000.0))
+            for j in range(T):
+                log = []
+                out = S.multiShoot_CRTBP_direct(Xs[j], Us[j], tau1, tau2, t_TU, np.zeros(3), np.zeros(3), MU, DU, TU, 30, 10, 1e3, 2000.0, *fx, False, False,
+                                                0.0, False, max_iter, backend=gpu, log=log)
+                assert r["iters"][j] == len(log), (n, max_iter, j, r["iters"][j], len(log))
+                assert np.abs(r["X_all"][j].T - out[0]).max() < 1e-8 and np.abs(r["u_all"][j].T - out[1]).max() < 1e-8, (n, max_iter, j)
+                assert np.abs(r["defect"][j].T - out[7]).max() < 1e-9
+            if max_iter == 100:
+                assert np.all(r["er"] <= 1e-6)
+    r = lto.direct_solve_batch(np.zeros((0, 5, 6)), np.zeros((0, 5, 3)), np.zeros((0, 5)), np.zeros((0, 6)), np.zeros((0, 6)))
+    assert r["X_all"].shape == (0, 5, 6)
