@@ -110,4 +110,17 @@ function multiShoot_CRTBP_indirect_batch(XC_batch::Array{Float64,3}, t_batch::Ma
         handle[], prm, n_traj, n_nodes, maxIter, flag_adjointsOnly ? 1 : 0, XC, t_batch, thrustLimit, rho, defect, status_flag, iters, er))
     (XC, defect, status_flag)
 end
+# ---- direct: multiShoot_CRTBP_direct (:465-594) for a BATCH of trajectories, iterated on the device (flagEnd = false, allowImpulsive = false).
+# X_batch: nstate x n_nodes x n_traj, u_batch: 3 x n_nodes x n_traj, t_batch: n_nodes x n_traj, state_0 / state_f: 6 x n_traj (interpEndStates, :483)
+function multiShoot_CRTBP_direct_batch(X_batch::Array{Float64,3}, u_batch::Array{Float64,3}, t_batch::Matrix{Float64}, state_0::Matrix{Float64},
+                                       state_f::Matrix{Float64}, MU, DU, TU, nsteps, mass, Isp, maxIter)
+    nstate = size(X_batch, 1); n_nodes = size(X_batch, 2); n_traj = size(X_batch, 3)
+    p = DirectParams(); p.MU, p.DU, p.TU, p.Isp = MU, DU, TU, Isp
+    X = copy(X_batch); u = copy(u_batch); defect = zeros(nstate, n_nodes - 1, n_traj); iters = zeros(Int32, n_traj); er = zeros(n_traj)
+    GC.@preserve X u t_batch state_0 state_f defect iters er check(ccall((:lto_direct_solve_batch, lib), Cint,
+        (Ptr{Cvoid}, Ref{DirectParams}, Int64, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble,
+         Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
+        handle[], p, n_traj, n_nodes, nstate, nsteps, maxIter, X, u, t_batch, state_0, state_f, mass, defect, iters, er))
+    (X, u, defect, iters)
+end
 end # module

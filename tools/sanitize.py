@@ -33,5 +33,8 @@ for n in (6, 7):
     Xb, Ub, db, itb = SV.multiShoot_CRTBP_direct_batch(Xs, np.zeros((3, 3, 30)), tau1, tau2, np.stack([tg] * 3), capi.MU, capi.DU, capi.TU, 30, 10, 1e3, 2000.0,
                                                        *fx, backend=gpu)
     assert np.abs(db).max() <= 1e-6, (n, np.abs(db).max())
+    st0, stf = SV.interpEndStates(tau1, tau2, *fx, capi.MU)
+    rr = h.direct_solve_batch(Xs.transpose(0, 2, 1), np.zeros((3, 30, 3)), np.stack([tg] * 3), np.stack([st0] * 3), np.stack([stf] * 3), max_iter=12)
+    assert np.all(rr["er"] <= 1e-6)
 print("sanitize run ok: solve flags", s["status_flag"], "iters", s["iters"], "launches", h.launches)
 h.close()

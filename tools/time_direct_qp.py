@@ -19,8 +19,16 @@ for n in (6, 7):
         t0 = time.perf_counter(); l0 = h.launches
         Xb, Ub, db, itb = SV.multiShoot_CRTBP_direct_batch(Xs, Us, tau1, tau2, tb, capi.MU, capi.DU, capi.TU, N, 10, 1e3, 2000.0, *fx, backend=gpu)
         dt = time.perf_counter() - t0
-    print("nstate %d: batched direct solve of %d trajectories x %d nodes: %.1f ms wall, iterations %s, max defect %.1e, launches %d"
+    print("nstate %d: batched direct solve (Python driver) of %d trajectories x %d nodes: %.1f ms wall, iterations %s, max defect %.1e, launches %d"
           % (n, T, N, dt * 1e3, np.bincount(itb), np.abs(db).max(), h.launches - l0))
+    st0, stf = SV.interpEndStates(tau1, tau2, *fx, capi.MU)
+    Xr = Xs.transpose(0, 2, 1).copy(); Ur = Us.transpose(0, 2, 1).copy()
+    for rep in range(3):
+        t0 = time.perf_counter(); l0 = h.launches
+        rr = h.direct_solve_batch(Xr, Ur, tb, np.stack([st0] * T), np.stack([stf] * T), mass=1e3, nsteps=10, max_iter=100)
+        dt = time.perf_counter() - t0
+    print("   lto_direct_solve_batch (resident loop): %.1f ms wall, %.2f ms on the device, iterations %s, max defect %.1e, launches %d, agreement with the Python driver %.1e"
+          % (dt * 1e3, h.last_kernel_ms, np.bincount(rr["iters"]), np.abs(rr["defect"]).max(), h.launches - l0, np.abs(rr["X_all"].transpose(0, 2, 1) - Xb).max()))
     # the QP kernel alone
     r = h.direct_traj(Xs.transpose(0, 2, 1).copy(), Us.transpose(0, 2, 1).copy(), tb, nsteps=10, jac=True)
     dev = torch.device("cuda", 0)
