@@ -24,7 +24,7 @@ LTO_KERNEL_AUTO, LTO_KERNEL_GENERIC, LTO_KERNEL_FAST = 0, 1, 2
 
 EXPORTS = [
     "lto_version", "lto_device_count", "lto_init", "lto_init_devices", "lto_n_devices", "lto_destroy", "lto_last_error", "lto_host_alloc", "lto_host_free",
-    "lto_kernel_launches", "lto_last_kernel_ms", "lto_stream", "lto_sync",
+    "lto_kernel_launches", "lto_last_kernel_ms", "lto_stream", "lto_sync", "lto_host_chunk_plan",
     "lto_direct_params_default", "lto_indirect_params_default",
     "lto_direct_defect", "lto_direct_defect_jac", "lto_direct_defect_traj", "lto_direct_defect_jac_traj",
     "lto_indirect_defect", "lto_indirect_defect_jac", "lto_indirect_defect_traj", "lto_indirect_defect_jac_traj",
@@ -78,6 +78,7 @@ def lib():
         L.lto_n_devices.argtypes = [C.c_void_p]
         L.lto_destroy.argtypes = [C.c_void_p]
         L.lto_sync.argtypes = [C.c_void_p]
+        L.lto_host_chunk_plan.argtypes = [C.c_int] * 2 + [C.c_int64] + [C.c_int] * 5 + [C.c_void_p, C.c_int]
         vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
         L.lto_direct_defect.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 3
         L.lto_direct_defect_jac.argtypes = [vp, vp, i64, ci, ci] + [vp] * 6 + [vp] * 4
@@ -130,6 +131,18 @@ def indirect_params(thrustLimit=0.05, mass=1000.0, time_direction=1.0, p=1.0, rh
     q.thrustLimit, q.mass, q.time_direction, q.p, q.rho, q.Isp = thrustLimit, mass, time_direction, p, rho, Isp
     q.reltol, q.abstol, q.controller, q.err_norm, q.kernel = reltol, abstol, controller, err_norm, kernel
     return q
+
+
+def host_chunk_plan(method, n_seg, n_nodes=0, nvar=None, nsteps=10, mode=LTO_FIXED, jac=True, n_sm=148):
+    """Chunk sizes (segments per launch) of the host-buffer entry points' H2D -> kernel -> D2H pipeline (lto_host_chunk_plan;
+    pure host logic, needs no GPU).  method: "direct" | "indirect"."""
+    m = {"direct": 0, "indirect": 1}[method]
+    nvar = nvar if nvar is not None else (7 if m == 0 else 12)
+    buf = (C.c_int64 * 4096)()
+    n = lib().lto_host_chunk_plan(m, n_sm, int(n_seg), int(n_nodes), int(nvar), int(nsteps), int(mode), int(bool(jac)), buf, 4096)
+    if n < 0:
+        raise LtoError("lto_host_chunk_plan: bad arguments (rc %d)" % n)
+    return [int(buf[i]) for i in range(min(n, 4096))]
 
 
 def _ptr(a):

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <algorithm>
 #include <cstdlib>
+#include <cmath>
 #include <thread>
 #include <vector>
 
@@ -223,13 +224,64 @@ static int dispatch_indirect(lto_handle* h, const IndirectArgs& a, int ndim, int
     return 0;
 }
 
-// Chunk size (segments) of the compute / D2H pipeline of the host entry points.
-static long long pick_chunk(long long n_seg, size_t out_bytes_per_seg) {
-    if (n_seg * (long long)out_bytes_per_seg <= (8ll << 20)) return n_seg;       // small: one shot
-    long long c = (long long)((16ll << 20) / (long long)out_bytes_per_seg);      // ~16 MiB of output per chunk
-    c = std::max<long long>(c, 2048);
-    c = (c + 2047) / 2048 * 2048;
-    return std::min(c, n_seg);
+// Chunk schedule (segments per launch) of the H2D -> kernel -> D2H pipeline of the host entry points.
+// Cost model, measured on a B200 behind PCIe 5 x16: the device->host copy engine moves
+// out_bytes_per_seg at ~50 GB/s (d ns per segment), a launch over c segments takes a_ns + c * r_ns (a_ns: launch + the
+// tail of the adaptive kernels' work queue, 0.25 ms for K3), and the call ends when the last chunk's copy does.
+//   * copy-bound with cheap launches (K1: r = 10 ns, d = 24 ns per segment): a geometric ramp. The first chunk is one
+//     wave of the persistent grid, so the copy engine starts after ~60 us, and every later chunk is as large as it can be
+//     while its kernel still finishes inside the previous chunk's copy -- the copy engine never waits again.
+//   * otherwise (K3 / K3-14: r ~ d, expensive tail): k equal chunks, k = sqrt(n * d / a) minimises k * a + n * d / k
+//     (the launch tails paid k times + the last chunk's exposed copy).
+// `quantum` keeps chunks on wave / whole-trajectory boundaries.
+static void plan_chunks(std::vector<long long>& plan, long long n_seg, size_t out_bytes_per_seg, double r_ns, double a_ns,
+                        long long wave, long long unit) {
+    plan.clear();
+    if (n_seg <= 0) return;
+    if (n_seg * (long long)out_bytes_per_seg <= (8ll << 20)) { plan.push_back(n_seg); return; }      // small: one shot
+    const double d_ns = (double)out_bytes_per_seg / 50.0;
+    auto up = [](long long x, long long q) { return (x + q - 1) / q * q; };
+    const long long q_wave = up(std::max(wave, unit), unit);
+    const double next_of_wave = ((double)q_wave * d_ns - a_ns) / r_ns;
+    if (next_of_wave >= (double)q_wave) {
+        // tk: when the kernels enqueued so far finish; tc: when the copies enqueued so far finish.  The next chunk is the largest
+        // number of waves whose kernel ends before the copy engine runs dry (slack carries over from chunk to chunk).
+        long long c = q_wave, left = n_seg;
+        double tk = 0.0, tc = 0.0;
+        while (left > 0) {
+            const long long take = (left - c < q_wave) ? left : c;      // no sliver at the end
+            plan.push_back(take); left -= take;
+            tk += a_ns + (double)take * r_ns;
+            tc = std::max(tc, tk) + (double)take * d_ns;
+            c = std::max(q_wave, (long long)((tc - tk - a_ns) / r_ns) / q_wave * q_wave);
+        }
+        return;
+    }
+    long long k = (long long)std::llround(std::sqrt((double)n_seg * d_ns / std::max(a_ns, 1.0)));
+    k = std::min<long long>(std::max<long long>(k, 1), 256);
+    const long long q = up(std::max<long long>(2048, unit), unit);
+    const long long c = up((n_seg + k - 1) / k, q);
+    for (long long left = n_seg; left > 0; left -= std::min(c, left)) plan.push_back(std::min(c, left));
+}
+
+// Per-kernel constants of the model (B200, 1965 MHz).  Direct: K1 0.68 ms per 65,536 segments of 2 x 9 steps (one wave of
+// n_sm x 32 segments: 49 us), K2 (ode78 controller) 0.50 ms + a tail of retried legs, K4 (defect only) 0.082 ms.
+static void plan_direct(std::vector<long long>& plan, int n_sm, long long n_seg, int npt, int nstate, int nsteps, int mode, bool want_jac) {
+    const size_t NS = (size_t)nstate, NV = 2 * (NS + 3);
+    const size_t per_seg = NS * 8 + 8 + 4 + (want_jac ? NS * NV * 8 : 0);
+    const bool fixed = mode == LTO_FIXED;
+    const double r_ns = !want_jac ? 1.3 : fixed ? (nstate == 7 ? 10.4 : 11.0) * (double)std::max(nsteps - 1, 1) / 9.0 : 7.7;
+    const double a_ns = (want_jac && !fixed) ? 60e3 : 10e3;
+    plan_chunks(plan, n_seg, per_seg, r_ns, a_ns, (long long)n_sm * 32, npt > 0 ? npt - 1 : 1);
+}
+// Indirect: K3 17.5 ns per segment + 0.25 ms per launch (the work queue's tail: about one segment lifetime at 64 slots per SM),
+// K3-14 26 ns + 0.33 ms, K4 (defect only) 2.5 ns + 50 us.
+static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_seg, int npt, int ndim, bool want_jac) {
+    const size_t ND = (size_t)ndim;
+    const size_t per_seg = ND * 8 + 12 + (want_jac ? ND * ND * 8 : 0);
+    const double r_ns = !want_jac ? 2.5 : ndim == 14 ? 26.0 : 17.5;
+    const double a_ns = !want_jac ? 50e3 : ndim == 14 ? 330e3 : 250e3;
+    plan_chunks(plan, n_seg, per_seg, r_ns, a_ns, (long long)n_sm * 64, npt > 0 ? npt - 1 : 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -313,13 +365,11 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
     // arrived, and host->device and device->host transfers run on different copy engines
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
     // ---- chunked compute + D2H pipeline
-    const size_t per_seg = (size_t)NS * 8 + 8 + 4 + (want_jac ? (size_t)NS * NV * 8 : 0);
-    long long chunk = pick_chunk(n_seg, per_seg);
-    if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }   // whole trajectories
-    int ci = 0;
-    long long ns = 0;
-    for (long long s0 = 0; s0 < n_seg; s0 += ns, ++ci) {
-        ns = std::min(chunk, n_seg - s0);
+    std::vector<long long> plan;
+    plan_direct(plan, h->n_sm, n_seg, npt, nstate, nsteps, p->mode, want_jac);
+    long long s0 = 0;
+    for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
+        const long long ns = plan[ci];
         const long long r0 = lto_node_a(s0, npt);
         {   // this chunk's input rows (trajectory form: whole trajectories, n_nodes rows each)
             const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
@@ -400,13 +450,11 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    const size_t per_seg = (size_t)ND * 8 + 12 + (want_jac ? (size_t)ND * ND * 8 : 0);
-    long long chunk = pick_chunk(n_seg, per_seg);
-    if (npt > 0) { const long long spt = npt - 1; chunk = std::max(spt, chunk / spt * spt); }
-    int ci = 0;
-    long long ns = 0;
-    for (long long s0 = 0; s0 < n_seg; s0 += ns, ++ci) {
-        ns = std::min(chunk, n_seg - s0);
+    std::vector<long long> plan;
+    plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac);
+    long long s0 = 0;
+    for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
+        const long long ns = plan[ci];
         const long long r0 = lto_node_a(s0, npt);
         const long long p0 = lto_traj_of(s0, npt);
         {
@@ -439,6 +487,22 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
 }
 
 extern "C" {
+
+int lto_host_chunk_plan(int method, int n_sm, int64_t n_seg, int n_nodes, int nvar, int nsteps, int mode, int want_jac,
+                        int64_t* chunks, int cap) {
+    if (n_sm <= 0 || n_seg < 0 || n_nodes == 1 || n_nodes < 0 || cap < 0 || (cap > 0 && !chunks)) return LTO_ERR_ARG;
+    if (n_nodes > 0 && n_seg % (n_nodes - 1) != 0) return LTO_ERR_ARG;
+    std::vector<long long> plan;
+    if (method == 0) {
+        if (nvar != 6 && nvar != 7) return LTO_ERR_ARG;
+        plan_direct(plan, n_sm, n_seg, n_nodes, nvar, nsteps, mode, want_jac != 0);
+    } else if (method == 1) {
+        if (nvar != 12 && nvar != 14) return LTO_ERR_ARG;
+        plan_indirect(plan, n_sm, n_seg, n_nodes, nvar, want_jac != 0);
+    } else return LTO_ERR_ARG;
+    for (int i = 0; i < (int)plan.size() && i < cap; ++i) chunks[i] = plan[i];
+    return (int)plan.size();
+}
 
 int lto_direct_defect(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps, const double* Xa,
                       const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,

@@ -88,3 +88,34 @@ def test_c_program_through_the_abi(capi, tmp_path):
     out = subprocess.run([_build_c_smoke(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "direct: status 0" in out.stdout and "newton status 0" in out.stdout
+
+
+def test_host_chunk_plan(capi):
+    """The chunk schedule of the host-buffer pipeline (pure host logic): every segment exactly once, whole trajectories, the
+    shapes the cost model asks for."""
+    # small calls: one shot
+    assert capi.host_chunk_plan("direct", 1000) == [1000]
+    assert capi.host_chunk_plan("indirect", 29, n_nodes=30) == [29]
+    assert capi.host_chunk_plan("direct", 0) == []
+    # config 3 (65,536 direct segments, 7 x 20 blocks): copy-bound -> first chunk one wave of the persistent grid, then growing
+    plan = capi.host_chunk_plan("direct", 65536, nvar=7)
+    assert sum(plan) == 65536 and plan[0] == 148 * 32 and len(plan) <= 6
+    assert all(b >= a for a, b in zip(plan[:-2], plan[1:-1])) and all(c % (148 * 32) == 0 for c in plan[:-1])
+    # config 4 per GPU (131,072 indirect segments): kernel tail ~ copy time -> a few equal chunks
+    plan = capi.host_chunk_plan("indirect", 131072, nvar=12)
+    assert sum(plan) == 131072 and 3 <= len(plan) <= 5 and len(set(plan[:-1])) == 1
+    plan = capi.host_chunk_plan("indirect", 1 << 20, nvar=12)
+    assert sum(plan) == 1 << 20 and 8 <= len(plan) <= 14
+    # trajectory forms: chunks are whole trajectories
+    for method, nvar, nn, nt in (("indirect", 12, 201, 1024), ("indirect", 14, 201, 777), ("direct", 7, 30, 5000), ("direct", 6, 30, 4097)):
+        plan = capi.host_chunk_plan(method, nt * (nn - 1), n_nodes=nn, nvar=nvar)
+        assert sum(plan) == nt * (nn - 1) and all(c > 0 and c % (nn - 1) == 0 for c in plan), (method, plan)
+    # ragged sizes, both methods, with and without Jacobian, adaptive direct
+    rng = np.random.default_rng(5)
+    for n in rng.integers(1, 3_000_000, 40):
+        for kw in (dict(method="direct", nvar=7), dict(method="direct", nvar=6, jac=False), dict(method="direct", nvar=7, mode=capi.LTO_ADAPTIVE),
+                   dict(method="indirect", nvar=12), dict(method="indirect", nvar=14), dict(method="indirect", nvar=12, jac=False)):
+            plan = capi.host_chunk_plan(n_seg=int(n), **kw)
+            assert sum(plan) == n and min(plan) > 0 and len(plan) <= 300, (n, kw, plan[:4])
+    with pytest.raises(capi.LtoError):
+        capi.host_chunk_plan("direct", 100, n_nodes=30)        # not a whole number of trajectories
