@@ -5,6 +5,7 @@
     multiShoot_CRTBP_indirect    src/multiShoot_CRTBP_indirect.jl:58-345
     reduceFuel_indirect          src/HelperFunctions.jl:105-193   (+ reduceFuel_indirect_batch: many trajectories, one device call per round)
     trajectory_stack_guess       CRTBP_Multishoot_direct_demo.jl:117-157
+    densify, jacobiConstant, interpInitialStates, find_tau   src/HelperFunctions.jl:10-101
 
 Same names, argument order and return values.  Arrays use the reference's shapes
 (nstate x n_nodes etc.).  What stays on the host is only the small dense linear algebra of
@@ -132,6 +133,34 @@ def find_tau(X_times, X_states, state, MU=None):
     tau_trial = np.linspace(0.0, 1.0, 1001)
     d = np.array([np.linalg.norm(f(tt) - state) for tt in tau_trial])
     return float(tau_trial[np.argmin(d)])
+
+
+def jacobiConstant(state, MU, DU=None):
+    """Jacobi constant of every column of `state` (6 x K) -- HelperFunctions.jl:10-15."""
+    state = np.asarray(state, dtype=np.float64).reshape(6, -1)
+    r1 = np.sqrt((state[0] + MU) ** 2 + state[1] ** 2 + state[2] ** 2)
+    r2 = np.sqrt((state[0] + MU - 1) ** 2 + state[1] ** 2 + state[2] ** 2)
+    v2 = np.sum(state[3:6] ** 2, axis=0)
+    return state[0] ** 2 + state[1] ** 2 + 2 * (1 - MU) / r1 + 2 * MU / r2 - v2
+
+
+def densify(XC_all, t_TU, params, n_desired, backend=None):
+    """densify (HelperFunctions.jl:51-101): the trajectory on LinRange(t_TU[1], t_TU[end], n_desired).  Every dense time t with
+    t_TU[i] <= t < t_TU[i+1] takes its column from segment i's solution (:64-75); after the last segment its end state -- the
+    propagated one, not the node -- is appended (:94-97).  Returns (XC_dense, t_dense) like the reference.
+
+    The reference evaluates each segment's Vern8 dense-output interpolant; here every dense point is its own segment
+    propagation (node i, t_TU[i]) -> t at the solver tolerance, all n_desired of them in ONE batched call of the propagation path."""
+    be = backend or default_backend()
+    XC_all = np.asarray(XC_all, dtype=np.float64); t_TU = np.asarray(t_TU, dtype=np.float64)
+    N = XC_all.shape[1]
+    t_dense = np.linspace(t_TU[0], t_TU[-1], int(n_desired))
+    seg = np.searchsorted(t_TU, t_dense, side="right") - 1
+    keep = (seg >= 0) & (seg <= N - 2)                                    # t < t_TU[end]; the end point is added below
+    seg = np.append(seg[keep], N - 2)
+    t1 = np.append(t_dense[keep], t_TU[-1])
+    x = be.propagate(np.ascontiguousarray(XC_all[:, seg].T), np.ascontiguousarray(t_TU[seg]), t1, params)
+    return np.ascontiguousarray(x.T), t_dense
 
 
 def controlLaw_cart(lambda_v, thrustLimit, p, rho, mass, DU=capi.DU, TU=capi.TU):

@@ -88,3 +88,17 @@ def test_line_search_batch_equals_sequential(backends):
     for j in (0, 7, 19):
         dj = gpu.indirect_defect(c["XC_all"][j:j + 1], c["t_TU"][j:j + 1], params)
         assert np.array_equal(dj[0], d_all[j])
+
+
+def test_densify_gpu_vs_oracle(backends):
+    """densify (HelperFunctions.jl:51-101) -- the demo's 1,000-point trajectory (CRTBP_Multishoot_indirect_demo.jl:201-205) as one
+    batched call of the propagation path -- against the oracle-backed run: 1e-10 (segment end states)."""
+    gpu, cpu = backends
+    c = __import__("lowthrustopt_b200.synthetic", fromlist=["x"]).continuation_batch(n_traj=1, n_seg_per_traj=29, ndim=12)
+    XC, t_TU = c["XC_all"][0].T.copy(), c["t_TU"][0]
+    for params in ((MU, DU, TU, 0.05, 1e3, 1.0, 1.0, 1e-2), (MU, DU, TU, 10.0, 1e3, 1.0, 2.0, 1.0)):
+        Dg, tg = S.densify(XC, t_TU, params, 1000, backend=gpu)
+        Dc, tc = S.densify(XC, t_TU, params, 1000, backend=cpu)
+        assert Dg.shape == (12, 1000) and np.array_equal(tg, tc)
+        assert (np.abs(Dg - Dc) / np.maximum(1.0, np.abs(Dc))).max() < 1e-10
+        assert np.array_equal(Dg[:, 0], XC[:, 0])                               # a dense time on a node is the node (zero-length span)

@@ -148,3 +148,29 @@ def test_invalid_p_and_nan_status():
     XC[:, 0] = np.nan
     out, d, st = S.multiShoot_CRTBP_indirect(XC, np.array([0.0, 0.1, 0.2]), MU, DU, TU, 3, 1e3, 0.05, False, False, 3, 1.0, 1.0, backend=be)
     assert st == 2                                                              # isnan(XC_all[1]) -> status_flag 2 (:339-341)
+
+
+def test_densify_and_jacobi_constant(demo):
+    """densify (HelperFunctions.jl:51-101) on a ballistic trajectory whose nodes lie on ONE solution: every dense column equals
+    the propagation from the first node (1e-10), there are exactly n_desired columns on LinRange(t_1, t_N, n_desired), node times
+    return the node itself, and the Jacobi constant (HelperFunctions.jl:10-15) is conserved along it."""
+    be = demo["be"]
+    X0 = S.demo_fixtures()[1]
+    params = (MU, DU, TU, 0.0, 1e3, 1.0, 2.0, 1.0)                         # thrustLimit 0: ballistic, costates ride along
+    N = 12
+    t_TU = np.linspace(0.0, 1.5, N)
+    x0 = np.concatenate([X0[:, 3], 0.1 * np.ones(6)])
+    XC = np.empty((12, N)); XC[:, 0] = x0
+    XC[:, 1:] = be.propagate(np.tile(x0, (N - 1, 1)), np.zeros(N - 1), t_TU[1:], params).T
+    XC_dense, t_dense = S.densify(XC, t_TU, params, 56, backend=be)         # 56 = 5 * 11 + 1: the nodes are dense times too
+    assert XC_dense.shape == (12, 56) and np.array_equal(t_dense, np.linspace(0.0, 1.5, 56))
+    want = be.propagate(np.tile(x0, (56, 1)), np.zeros(56), t_dense, params).T
+    assert np.abs(XC_dense - want).max() < 1e-10
+    assert np.array_equal(XC_dense[:, 0], XC[:, 0]) and np.abs(XC_dense[:, 5] - XC[:, 1]).max() < 1e-13
+    C = S.jacobiConstant(XC_dense[:6], MU, DU)
+    assert C.shape == (56,) and np.abs(C - C[0]).max() < 1e-11 and abs(C[0] - 3.0327) < 1e-3   # SURVEY 8(c): C = 3.0327000 on L2_Anderson_1
+    # nodes that do NOT lie on one solution: a dense point belongs to the segment that starts at or before it
+    XC2 = XC.copy(); XC2[0, 4] += 1e-3
+    D2, _ = S.densify(XC2, t_TU, params, 56, backend=be)
+    assert np.array_equal(D2[:, :20], XC_dense[:, :20]) and np.array_equal(D2[:, 20], XC2[:, 4]) and np.abs(D2[0, 21] - XC_dense[0, 21]) > 1e-4
+    assert np.array_equal(D2[:, 25:], XC_dense[:, 25:])                     # the end column comes from the last segment's propagation
