@@ -13,6 +13,9 @@ struct lto_handle {
     int device;
     int n_sm;
     cudaStream_t s_compute, s_copy, s_h2d;          // kernels; device->host (and peer pushes); host->device
+    cudaStream_t s_compute2;                        // second kernel stream of the host-buffer indirect pipeline (alternating chunks)
+    cudaEvent_t ev_join;
+    int host_streams;                               // 1 or 2 (LTO_HOST_STREAMS, default 1)
     cudaEvent_t ev_in, ev_t0, ev_t1;
     cudaEvent_t ev_chunk[8], ev_h2d[8];
     void* d_in; size_t d_in_cap;
