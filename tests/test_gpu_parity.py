@@ -203,7 +203,7 @@ def test_indirect_symplectic_property(lto):
 
 
 @pytest.mark.parametrize("streams", [1, 2])
-@pytest.mark.parametrize("nd,n", [(12, 40000), (14, 20000)])
+@pytest.mark.parametrize("nd,n", [(12, 40000), (14, 40000)])
 def test_indirect_multi_chunk_host_pipeline(nd, n, streams, lto, monkeypatch):
     """Host-buffer calls above 8 MiB of output are cut into chunks (lto_host_chunk_plan) whose H2D copies, kernels and D2H copies
     run on their own streams -- with LTO_HOST_STREAMS=2 the kernels alternate between two streams, each with its own work-queue
