@@ -31,6 +31,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden14():
+    """The 14-dim system derived symbolically from its Hamiltonian (tests/golden/make_golden14.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "golden14_v1.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def hostcheck():
     """Test-only host build of the kernels' __host__ __device__ arithmetic."""
     d = os.path.join(ROOT, "tests", "native")

@@ -161,6 +161,21 @@ def test_indirect_vs_golden(lto, golden):
             assert np.abs(r["phi"][0].T - np.array(g["phi_richardson"])).max() < 5e-8
 
 
+def test_indirect14_vs_golden(lto, golden14):
+    """K3-14 / K4-14 against the symbolically derived 14-dim system (tests/golden/make_golden14.py): end states 1e-10 relative
+    (north_star), STM against the Richardson differences of the DOP853 flow."""
+    for g in golden14["indirect14"]:
+        p = capi.indirect_params(thrustLimit=g["thrustLimit"], time_direction=g["td"], p=g["p"], rho=g["rho"], Isp=g["Isp"])
+        want = np.array(g["xend"]); sc = np.maximum(1.0, np.abs(want))
+        r = lto.indirect([g["x0"]], [g["t0"]], [g["t1"]], params=p)
+        assert r["status"][0] == 0 and (np.abs(r["defect"][0] - want) / sc).max() < TOL_STATE
+        r0 = lto.indirect([g["x0"]], [g["t0"]], [g["t1"]], params=p, jac=False)
+        assert (np.abs(r0["defect"][0] - want) / sc).max() < TOL_STATE
+        if "phi_richardson" in g:
+            P = np.array(g["phi_richardson"])
+            assert np.abs(r["phi"][0].T - P).max() < 5e-8 * max(1.0, np.abs(P).max() / 10)
+
+
 def test_indirect_ode78_controller_and_per_segment_params(lto, oracle):
     n = 64
     b = S.indirect_batch(n, ndim=12, seed=203)

@@ -79,3 +79,19 @@ def test_indirect_segment_matches_oracle(nd, ctl, oracle, hostcheck):
             assert np.all(np.abs(xe - xo[s]) / sc < 1e-11)
             assert np.abs(Phi.T - Po[s]).max() < 1e-10 * max(1.0, np.abs(Po[s]).max())
             assert abs(na.value - nao[s]) <= 1
+
+
+def test_kernel_arithmetic_14_matches_symbolic_golden(oracle, hostcheck, golden14):
+    """The kernels' own 14-dim arithmetic (lto_math.cuh sc_stage<14> / sc_col<14> through the generic driver, compiled for the
+    host) against the system derived from the Hamiltonian by sympy (tests/golden/make_golden14.py): every law of the golden
+    set, time_direction = -1 included."""
+    for g in golden14["indirect14"]:
+        ip = oracle.iparams(g["thrustLimit"], td=g["td"], p=g["p"], rho=g["rho"], Isp=g["Isp"])
+        x0 = np.array(g["x0"]); want = np.array(g["xend"])
+        xe = np.zeros(14); Phi = np.zeros((14, 14)); na = C.c_int(); nt = C.c_int()
+        st = hostcheck.hc_sc_seg(14, 1, ptr(x0), C.c_double(g["t0"]), C.c_double(g["t1"]), C.c_double(1e-13), C.c_double(1e-13), 0, 1,
+                                 ptr(ip), ptr(xe), ptr(Phi), C.byref(na), C.byref(nt))
+        assert st == 0 and (np.abs(xe - want) / np.maximum(1.0, np.abs(want))).max() < 1e-11
+        if "phi_richardson" in g:
+            P = np.array(g["phi_richardson"])
+            assert np.abs(Phi.T - P).max() < 5e-8 * max(1.0, np.abs(P).max() / 10)

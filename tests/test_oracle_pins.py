@@ -109,6 +109,25 @@ def test_oracle_matches_golden_indirect(oracle, golden):
         assert np.abs(xe3 - xe).max() < 1e-12 and np.abs(phi3 - phi).max() < 1e-10
 
 
+def test_oracle_matches_golden_indirect14(oracle, golden14):
+    """The 14-dim extension [r v m | lr lv lm] against equations DERIVED from the Hamiltonian by sympy
+    (x' = dH/dl, l' = -dH/dx at fixed thrust force, then the reference's control law substituted) and integrated with
+    DOP853 -- nothing in that chain shares code with oracle/: end states (mass and lm included) 1e-11 relative, the
+    14 x 14 STM against Richardson-extrapolated central differences of that flow (their own noise ~5e-9)."""
+    assert len(golden14["indirect14"]) == 10
+    for g in golden14["indirect14"]:
+        ip = oracle.iparams(g["thrustLimit"], td=g["td"], p=g["p"], rho=g["rho"], Isp=g["Isp"])
+        x0 = np.array([g["x0"]])
+        xe, phi, st, na, nt = oracle.indirect_prop_jac(x0, [g["t0"]], [g["t1"]], ip)
+        want = np.array(g["xend"])
+        assert st[0] == 0 and (np.abs(xe[0] - want) / np.maximum(1.0, np.abs(want))).max() < 1e-11
+        xe0, *_ = oracle.indirect_prop(x0, [g["t0"]], [g["t1"]], ip)
+        assert (np.abs(xe0[0] - want) / np.maximum(1.0, np.abs(want))).max() < 1e-11
+        if "phi_richardson" in g:
+            P = np.array(g["phi_richardson"])
+            assert np.abs(phi[0] - P).max() < 5e-8 * max(1.0, np.abs(P).max() / 10)
+
+
 def test_oracle_invalid_p(oracle):
     with pytest.raises(ValueError):
         oracle.sc_rhs(np.ones(12), oracle.iparams(0.05, p=0.5))
