@@ -80,6 +80,22 @@ function jacobianCalc_indirect(XC_all, t_TU, nstate, n_nodes, params)
     Jac_full[:, 1:nstate] .= 0.0; Jac_full[:, (end - 2 * nstate + 1):(end - nstate)] .= 0.0   # :141-142
     Jac_full
 end
+# ---- densify (HelperFunctions.jl:51-101): every dense time is its own propagation (node i, t_TU[i]) -> t, all of them in ONE call
+# (pairs form of lto_indirect_defect, x_target = NULL returns x(t1)); the reference evaluates Vern8's dense-output interpolant instead.
+function densify(XC_all::Matrix{Float64}, t_TU::Vector{Float64}, params, n_desired)
+    m = size(XC_all, 1); N = size(XC_all, 2)
+    t_dense = collect(LinRange(t_TU[1], t_TU[end], n_desired))
+    seg = [searchsortedlast(t_TU, t) for t in t_dense]
+    keep = seg .<= N - 1                                                                  # t < t_TU[end] (:64)
+    seg = vcat(seg[keep], N - 1); t1 = vcat(t_dense[keep], t_TU[end])                     # + the last segment's end state (:94-97)
+    x0 = XC_all[:, seg]; t0 = t_TU[seg]; n = length(seg)
+    xend = zeros(m, n); status = zeros(Int32, n)
+    GC.@preserve x0 t0 t1 xend status check(ccall((:lto_indirect_defect, lib), Cint,
+        (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+        handle[], iparams(params), n, m, x0, t0, t1, C_NULL, C_NULL, C_NULL, xend, status, C_NULL))
+    (xend, t_dense)
+end
+
 # ---- indirect: the linear step of optimizeTraj_OLS (multiShoot_CRTBP_indirect.jl:181-182, :207) on the device.
 # `phi` is what jacobianCalc_blocks returns (m x m x (n_nodes-1)); Jac_full is never formed.
 function jacobianCalc_blocks(XC_all, t_TU, nstate, n_nodes, params)
