@@ -140,11 +140,11 @@ def host_chunk_plan(method, n_seg, n_nodes=0, nvar=None, nsteps=10, mode=LTO_FIX
     if m == 1:
         mode = streams
     nvar = nvar if nvar is not None else (7 if m == 0 else 12)
-    buf = (C.c_int64 * 4096)()
-    n = lib().lto_host_chunk_plan(m, n_sm, int(n_seg), int(n_nodes), int(nvar), int(nsteps), int(mode), int(bool(jac)), buf, 4096)
+    buf = (C.c_int64 * 8192)()
+    n = lib().lto_host_chunk_plan(m, n_sm, int(n_seg), int(n_nodes), int(nvar), int(nsteps), int(mode), int(bool(jac)), buf, 8192)
     if n < 0:
         raise LtoError("lto_host_chunk_plan: bad arguments (rc %d)" % n)
-    return [int(buf[i]) for i in range(min(n, 4096))]
+    return [int(buf[i]) for i in range(min(n, 8192))]
 
 
 def _ptr(a):

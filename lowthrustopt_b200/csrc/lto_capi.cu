@@ -85,12 +85,13 @@ int lto_init(int device, lto_handle** out) {
     CK(h, cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking));
     CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     { const char* e = getenv("LTO_HOST_STREAMS"); h->host_streams = (e && atoi(e) == 2) ? 2 : 1; }
+    { const char* e = getenv("LTO_HOST_PROGRESS"); if (e && atoi(e) == 1) h->host_streams = 3; }
     CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     CK(h, cudaEventCreate(&h->ev_t0));
     CK(h, cudaEventCreate(&h->ev_t1));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-    CK(h, cudaMalloc((void**)&h->d_ctr, 256));
+    CK(h, cudaMalloc((void**)&h->d_ctr, 256 + LTO_PROG_WORDS * 8));      // work-queue counters + completion counters (d_ctr + 32)
     if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
     *out = h;
     return LTO_SUCCESS;
@@ -221,7 +222,7 @@ static int dispatch_indirect(lto_handle* h, const IndirectArgs& a, int ndim, int
     cudaError_t e = cudaErrorNotSupported;
     if (kernel != LTO_KERNEL_GENERIC) e = launch_indirect_fast(a, ndim, st, &nl);
     if (e == cudaErrorNotSupported) {
-        if (kernel == LTO_KERNEL_FAST) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
+        if (kernel == LTO_KERNEL_FAST || a.progress) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
         e = launch_indirect_generic(a, ndim, st, &nl);
     }
     h->launches += nl;
@@ -288,6 +289,22 @@ static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_se
     const size_t per_seg = ND * 8 + 12 + (want_jac ? ND * ND * 8 : 0);
     const double r_ns = !want_jac ? 2.5 : ndim == 14 ? 26.0 : 17.5;
     const double a_ns = (!want_jac ? 50e3 : ndim == 14 ? 330e3 : 250e3) * (streams == 2 ? 0.4 : 1.0);
+    if (streams == 3 && want_jac && n_seg * (long long)per_seg > (8ll << 20)) {
+        // completion counters (LTO_HOST_PROGRESS=1): a first launch of about one fill of the slots (so that the copy engine starts
+        // early and the rest of the inputs arrive behind it), then ONE launch over everything else whose finished ranges of `cs`
+        // segments are shipped as their counters fill up -- the work queue's tail is paid twice per call, not once per chunk
+        const long long unit = npt > 0 ? npt - 1 : 1;
+        auto up = [](long long x, long long q) { return (x + q - 1) / q * q; };
+        const long long q = up(std::max<long long>(2048, unit), unit);
+        const long long c0 = std::min(n_seg, up((long long)n_sm * 64, q));
+        plan.clear(); plan.push_back(c0);
+        const long long rest = n_seg - c0;
+        if (rest > 0) {
+            const long long cs = std::max(up(16384, q), up((rest + LTO_PROG_WORDS - 1) / LTO_PROG_WORDS, q));
+            for (long long left = rest; left > 0; left -= std::min(cs, left)) plan.push_back(std::min(cs, left));
+        }
+        return;
+    }
     plan_chunks(plan, n_seg, per_seg, r_ns, a_ns, (long long)n_sm * 64, npt > 0 ? npt - 1 : 1);
 }
 
@@ -410,6 +427,21 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
     return LTO_SUCCESS;
 }
 
+// stream memory operations (driver API through the runtime's entry-point query): completion flags / counters on streams
+typedef int (*lto_cu_stream_val_fn)(void* stream, unsigned long long addr, unsigned long long value, unsigned int flags);
+static lto_cu_stream_val_fn g_cu_write64 = nullptr, g_cu_wait64 = nullptr;
+static int resolve_stream_memops(lto_handle* h) {
+    if (g_cu_write64 && g_cu_wait64) return 0;
+    void* fw = nullptr; void* fq = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fw, cudaEnableDefault, &qr) != cudaSuccess || !fw ||
+        cudaGetDriverEntryPoint("cuStreamWaitValue64", &fq, cudaEnableDefault, &qr) != cudaSuccess || !fq) {
+        cudaGetLastError();
+        return fail(h, LTO_ERR_CUDA, "stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64) are not available");
+    }
+    g_cu_write64 = (lto_cu_stream_val_fn)fw; g_cu_wait64 = (lto_cu_stream_val_fn)fq;
+    return 0;
+}
 static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long n_seg, int npt, long long n_nodes_total,
                          long long n_traj, int ndim, const double* x0, const double* t0, const double* t1,
                          const double* x_target, const double* tl_arr, const double* rho_arr, double* defect,
@@ -463,32 +495,49 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    // LTO_HOST_PROGRESS=1: completion counters (plan_indirect, kind 3).  Only the throughput kernels count, so the mode needs them.
+    const bool prog = want_jac && h->host_streams == 3 && p->kernel != LTO_KERNEL_GENERIC && p->controller == 0 && n_seg <= 0x7fffffffll;
     std::vector<long long> plan;
-    plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac, n_str);
+    plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac, prog ? 3 : n_str);
+    const bool grouped = prog && plan.size() > 2;                        // chunks 1.. are ONE launch
+    unsigned long long* d_prog = h->d_ctr + 32;
+    if (grouped) {
+        rc = resolve_stream_memops(h); if (rc) return rc;
+        CK(h, cudaMemsetAsync(d_prog, 0, (plan.size() - 1) * 8, h->s_compute));
+        CK(h, cudaEventRecord(h->ev_join, h->s_compute));
+        CK(h, cudaStreamWaitEvent(h->s_copy, h->ev_join, 0));            // no counter is looked at before it has been cleared
+    }
     long long s0 = 0;
     for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
         const long long ns = plan[ci];
-        const long long r0 = lto_node_a(s0, npt);
-        const long long p0 = lto_traj_of(s0, npt);
         const int si = ci % n_str;
         cudaStream_t st = si ? h->s_compute2 : h->s_compute;
-        {
-            const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+        if (!grouped || ci <= 1) {                                       // a launch starts here: over this chunk, or over all the rest
+            const long long nl = (grouped && ci == 1) ? n_seg - s0 : ns;
+            const long long r0 = lto_node_a(s0, npt);
+            const long long p0 = lto_traj_of(s0, npt);
+            const long long nr = npt > 0 ? nl / (npt - 1) * npt : nl;
             CK(h, cudaMemcpyAsync(dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaMemcpyAsync(dT0 + r0, t0 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
             if (npt == 0) CK(h, cudaMemcpyAsync(dT1 + r0, t1 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
             if (sep_target) CK(h, cudaMemcpyAsync(dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
             CK(h, cudaStreamWaitEvent(st, h->ev_h2d[ci & 7], 0));
+            a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
+            a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
+            a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
+            a.n_seg = nl; a.npt = npt; a.counter = h->d_ctr + 8 * si; a.scratch = (double*)((char*)h->d_scr + scr_bytes * si); a.prof = h->d_prof;
+            a.progress = (grouped && ci == 1) ? d_prog : nullptr; a.prog_chunk = (grouped && ci == 1) ? plan[1] : 0;
+            rc = dispatch_indirect(h, a, ndim, p->kernel, st); if (rc) return rc;
         }
-        a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
-        a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
-        a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
-        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr + 8 * si; a.scratch = (double*)((char*)h->d_scr + scr_bytes * si); a.prof = h->d_prof;
-        rc = dispatch_indirect(h, a, ndim, p->kernel, st); if (rc) return rc;
-        cudaEvent_t ev = h->ev_chunk[ci & 7];
-        CK(h, cudaEventRecord(ev, st));
-        CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
+        if (grouped && ci >= 1) {                                        // this range of the big launch is complete when its counter is full
+            const int e = g_cu_wait64((void*)h->s_copy, (unsigned long long)(uintptr_t)(d_prog + (ci - 1)), (unsigned long long)ns, 0u /* GEQ */);
+            if (e != 0) return fail(h, LTO_ERR_CUDA, "cuStreamWaitValue64 -> CUresult %d", e);
+        } else {
+            cudaEvent_t ev = h->ev_chunk[ci & 7];
+            CK(h, cudaEventRecord(ev, st));
+            CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
+        }
         CK(h, cudaMemcpyAsync(defect + s0 * ND, dD + s0 * ND, ns * ND * 8, cudaMemcpyDeviceToHost, h->s_copy));
         if (status) CK(h, cudaMemcpyAsync(status + s0, dS + s0, ns * 4, cudaMemcpyDeviceToHost, h->s_copy));
         if (nsteps_out) CK(h, cudaMemcpyAsync(nsteps_out + 2 * s0, dN + 2 * s0, ns * 8, cudaMemcpyDeviceToHost, h->s_copy));
@@ -517,7 +566,7 @@ int lto_host_chunk_plan(int method, int n_sm, int64_t n_seg, int n_nodes, int nv
         plan_direct(plan, n_sm, n_seg, n_nodes, nvar, nsteps, mode, want_jac != 0);
     } else if (method == 1) {
         if (nvar != 12 && nvar != 14) return LTO_ERR_ARG;
-        plan_indirect(plan, n_sm, n_seg, n_nodes, nvar, want_jac != 0, (mode == 2 && want_jac) ? 2 : 1);
+        plan_indirect(plan, n_sm, n_seg, n_nodes, nvar, want_jac != 0, ((mode == 2 || mode == 3) && want_jac) ? mode : 1);
     } else return LTO_ERR_ARG;
     for (int i = 0; i < (int)plan.size() && i < cap; ++i) chunks[i] = plan[i];
     return (int)plan.size();
@@ -677,20 +726,6 @@ int lto_sync_copies(lto_handle* h) {
 
 // Stream-ordered 64-bit flags (driver stream memory operations, resolved at run time so that the library does not
 // link libcuda): "my slab is written" signals from every rank into the solver rank's memory, awaited on its stream.
-typedef int (*lto_cu_stream_val_fn)(void* stream, unsigned long long addr, unsigned long long value, unsigned int flags);
-static lto_cu_stream_val_fn g_cu_write64 = nullptr, g_cu_wait64 = nullptr;
-static int resolve_stream_memops(lto_handle* h) {
-    if (g_cu_write64 && g_cu_wait64) return 0;
-    void* fw = nullptr; void* fq = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fw, cudaEnableDefault, &qr) != cudaSuccess || !fw ||
-        cudaGetDriverEntryPoint("cuStreamWaitValue64", &fq, cudaEnableDefault, &qr) != cudaSuccess || !fq) {
-        cudaGetLastError();
-        return fail(h, LTO_ERR_CUDA, "stream memory operations (cuStreamWriteValue64 / cuStreamWaitValue64) are not available");
-    }
-    g_cu_write64 = (lto_cu_stream_val_fn)fw; g_cu_wait64 = (lto_cu_stream_val_fn)fq;
-    return 0;
-}
 int lto_signal_dev(lto_handle* h, void* flag, uint64_t value) {
     if (!h || h->n_child > 0 || !flag) return fail(h, LTO_ERR_ARG, "needs a single-device handle and a flag address");
     CK(h, cudaSetDevice(h->device));

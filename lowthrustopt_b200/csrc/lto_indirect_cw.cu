@@ -521,10 +521,20 @@ __device__ __forceinline__ void prepare_next(const IndirectArgs& a, const TileSm
     }
 }
 
-template <bool JOINT>
-__device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
+// PROG: completion counters (IndirectArgs::progress).  A segment's STM columns are stored by the column threads during the visit
+// that carries its F_STORE flag; the state warp knows they are done when it passes that visit's bar_done (or, for the tile's last
+// visit, the CTA-wide barrier at the end of the kernel), fences at system scope and counts the segment.  Returns the segment
+// that is still to be counted after the final visit (-1: none).
+__device__ __forceinline__ void progress_count(const IndirectArgs& a, long long seg) {
+    __threadfence_system();
+    atomicAdd(a.progress + seg / a.prog_chunk, 1ull);
+}
+
+template <bool JOINT, bool PROG>
+__device__ __forceinline__ long long state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
     const TileSmem S = tile_smem(smem, t);
     const int slot = lane;
+    long long pend = -1;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
@@ -552,6 +562,9 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             mbar_wait_parked(S.bar_done, (visit - 1) & 1);
             c1 = clock64();
             c_wait += c1 - c0;
+            if (PROG) {
+                if (pend >= 0) { progress_count(a, pend); pend = -1; }
+            }
             if (active) {
                 double s2 = esum;
                 if (JOINT) {
@@ -593,6 +606,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             if (a.status) a.status[seg] = status;
             if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
             flags |= F_STORE; store_seg = (int)seg;
+            if (PROG) pend = seg;
             active = false;
         }
         auto take_successor = [&]() {                                    // the successor prepared by prepare_next()
@@ -655,9 +669,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         o[0] = c_work; o[1] = c_wait; o[2] = visit; o[3] = clock64() - c_begin;
         a.prof[(size_t)gridDim.x * NW * 4 + (size_t)blockIdx.x * NTILE + t] = c_pre;
     }
+    return pend;
 }
 
-template <bool JOINT>
+template <bool JOINT, bool PROG = false>
 __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -670,8 +685,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     __syncthreads();
     // warps 3 and 7 (both on SM sub-partition 3) are the state warps; the other three sub-partitions
     // each host two column warps that run the same instruction stream side by side
-    if ((warp & 3) == 3) state_warp<JOINT>(a, warp >> 2, lane, smem_raw);
+    long long pend = -1;
+    if ((warp & 3) == 3) pend = state_warp<JOINT, PROG>(a, warp >> 2, lane, smem_raw);
     else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
+    if (PROG) {
+        __syncthreads();                                                 // the columns of the tiles' last visits are stored
+        if (pend >= 0) progress_count(a, pend);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1243,7 +1263,7 @@ static cudaError_t launch_icw3(const IndirectArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <bool JOINT>
+template <bool JOINT, bool PROG>
 static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
     // per device: a single process may drive several GPUs (lto_init_devices)
     static int n_sm_dev[64] = {0};
@@ -1253,7 +1273,7 @@ static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_dev[dev]) {
         cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(icw::k_indirect_cw<JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw::SMEM);
+        e = cudaFuncSetAttribute(icw::k_indirect_cw<JOINT, PROG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw::SMEM);
         if (e != cudaSuccess) return e;
         attr_dev[dev] = true;
     }
@@ -1262,7 +1282,7 @@ static cudaError_t launch_icw(const IndirectArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const long long per_cta = (long long)icw::NTILE * icw::TS;
     const int grid = (int)std::min<long long>((a.n_seg + per_cta - 1) / per_cta, (long long)n_sm);
-    icw::k_indirect_cw<JOINT><<<grid, icw::NTHREADS, icw::SMEM, st>>>(a);
+    icw::k_indirect_cw<JOINT, PROG><<<grid, icw::NTHREADS, icw::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1288,7 +1308,11 @@ cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st,
         a.n_seg > 0x7fffffffll)
         return cudaErrorNotSupported;
     cudaError_t e;
-    if (use_two_tiles()) e = (a.cfg.err_norm != 0) ? launch_icw<true>(a, st) : launch_icw<false>(a, st);
+    if (a.progress != nullptr) {                                         // completion counters: the default two-tile kernel only
+        if (!use_two_tiles() || a.prog_chunk <= 0) return cudaErrorNotSupported;
+        e = (a.cfg.err_norm != 0) ? launch_icw<true, true>(a, st) : launch_icw<false, true>(a, st);
+    }
+    else if (use_two_tiles()) e = (a.cfg.err_norm != 0) ? launch_icw<true, false>(a, st) : launch_icw<false, false>(a, st);
     else e = (a.cfg.err_norm != 0) ? launch_icw3<true>(a, st) : launch_icw3<false>(a, st);
     if (e == cudaSuccess) *n_launch = 1;
     return e;

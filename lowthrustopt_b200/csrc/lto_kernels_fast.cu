@@ -28,7 +28,7 @@ static bool use_q3() {
 
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
     if (ndim == 14) return launch_indirect_cw14(a, st, n_launch);
-    if (a.phi != nullptr && use_q3()) return launch_indirect_q3(a, ndim, st, n_launch);
+    if (a.phi != nullptr && use_q3()) return a.progress ? cudaErrorNotSupported : launch_indirect_q3(a, ndim, st, n_launch);   // no completion counters in the experiment
     return launch_indirect_cw(a, ndim, st, n_launch);
 }
 

@@ -217,19 +217,20 @@ def test_indirect_symplectic_property(lto):
     assert np.abs(det - 1.0).max() < 1e-8
 
 
-@pytest.mark.parametrize("streams", [1, 2])
+@pytest.mark.parametrize("streams", [1, 2, 3])
 @pytest.mark.parametrize("nd,n", [(12, 40000), (14, 40000)])
 def test_indirect_multi_chunk_host_pipeline(nd, n, streams, lto, monkeypatch):
     """Host-buffer calls above 8 MiB of output are cut into chunks (lto_host_chunk_plan) whose H2D copies, kernels and D2H copies
     run on their own streams -- with LTO_HOST_STREAMS=2 the kernels alternate between two streams, each with its own work-queue
-    counter and column scratch: every segment must come back exactly as the one-launch call of a small batch computes it
+    counter and column scratch; with LTO_HOST_PROGRESS=1 everything after the first chunk is ONE launch whose finished ranges are
+    shipped as their completion counters fill up: every segment must come back exactly as the one-launch call of a small batch computes it
     (bitwise -- a segment's arithmetic does not depend on its batch position)."""
     plan = capi.host_chunk_plan("indirect", n, nvar=nd, streams=streams)
     assert len(plan) >= 2 and sum(plan) == n
     b = S.indirect_batch(n, ndim=nd, seed=77)
     p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
-    if streams == 2:
-        monkeypatch.setenv("LTO_HOST_STREAMS", "2")                           # read by lto_init
+    if streams >= 2:                                                          # 2: two kernel streams; 3: completion counters (one big launch)
+        monkeypatch.setenv(*(("LTO_HOST_STREAMS", "2") if streams == 2 else ("LTO_HOST_PROGRESS", "1")))    # read by lto_init
         h2 = capi.Handle(0)
         r = h2.indirect(b["x0"], b["t0"], b["t1"], params=p)
         h2.close()
