@@ -523,18 +523,29 @@ __device__ __forceinline__ void prepare_next(const IndirectArgs& a, const TileSm
 
 // PROG: completion counters (IndirectArgs::progress).  A segment's STM columns are stored by the column threads during the visit
 // that carries its F_STORE flag; the state warp knows they are done when it passes that visit's bar_done (or, for the tile's last
-// visit, the CTA-wide barrier at the end of the kernel), fences at system scope and counts the segment.  Returns the segment
-// that is still to be counted after the final visit (-1: none).
-__device__ __forceinline__ void progress_count(const IndirectArgs& a, long long seg) {
-    __threadfence_system();
-    atomicAdd(a.progress + seg / a.prog_chunk, 1ull);
+// visit, the CTA-wide barrier at the end of the kernel).  Counting needs a system-scope fence, which must not sit on the state
+// warp's dependent chain every visit (measured: -15 % end to end), so a lane parks up to two finished segments (pend[1], pend[2])
+// and the warp counts them every 8th visit, or at once when some lane's second place fills up; pend[0] is the segment whose
+// F_STORE visit is still in flight.
+__device__ __forceinline__ void progress_flush(const IndirectArgs& a, long long (&pend)[3]) {
+    if (pend[1] >= 0) {
+        __threadfence_system();
+        atomicAdd(a.progress + pend[1] / a.prog_chunk, 1ull);
+        if (pend[2] >= 0) atomicAdd(a.progress + pend[2] / a.prog_chunk, 1ull);
+        pend[1] = -1; pend[2] = -1;
+    }
+}
+__device__ __forceinline__ void progress_park(long long (&pend)[3]) {
+    if (pend[0] >= 0) {
+        if (pend[1] < 0) pend[1] = pend[0]; else pend[2] = pend[0];
+        pend[0] = -1;
+    }
 }
 
 template <bool JOINT, bool PROG>
-__device__ __forceinline__ long long state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
+__device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem, long long (&pend)[3]) {
     const TileSmem S = tile_smem(smem, t);
     const int slot = lane;
-    long long pend = -1;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
@@ -563,7 +574,8 @@ __device__ __forceinline__ long long state_warp(const IndirectArgs& a, int t, in
             c1 = clock64();
             c_wait += c1 - c0;
             if (PROG) {
-                if (pend >= 0) { progress_count(a, pend); pend = -1; }
+                progress_park(pend);
+                if ((visit & 7u) == 0u || __any_sync(fullmask, pend[2] >= 0)) progress_flush(a, pend);
             }
             if (active) {
                 double s2 = esum;
@@ -606,7 +618,7 @@ __device__ __forceinline__ long long state_warp(const IndirectArgs& a, int t, in
             if (a.status) a.status[seg] = status;
             if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
             flags |= F_STORE; store_seg = (int)seg;
-            if (PROG) pend = seg;
+            if (PROG) pend[0] = seg;
             active = false;
         }
         auto take_successor = [&]() {                                    // the successor prepared by prepare_next()
@@ -669,7 +681,6 @@ __device__ __forceinline__ long long state_warp(const IndirectArgs& a, int t, in
         o[0] = c_work; o[1] = c_wait; o[2] = visit; o[3] = clock64() - c_begin;
         a.prof[(size_t)gridDim.x * NW * 4 + (size_t)blockIdx.x * NTILE + t] = c_pre;
     }
-    return pend;
 }
 
 template <bool JOINT, bool PROG = false>
@@ -685,12 +696,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw(IndirectArgs a) {
     __syncthreads();
     // warps 3 and 7 (both on SM sub-partition 3) are the state warps; the other three sub-partitions
     // each host two column warps that run the same instruction stream side by side
-    long long pend = -1;
-    if ((warp & 3) == 3) pend = state_warp<JOINT, PROG>(a, warp >> 2, lane, smem_raw);
+    long long pend[3] = {-1, -1, -1};
+    if ((warp & 3) == 3) state_warp<JOINT, PROG>(a, warp >> 2, lane, smem_raw, pend);
     else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
     if (PROG) {
         __syncthreads();                                                 // the columns of the tiles' last visits are stored
-        if (pend >= 0) progress_count(a, pend);
+        if (pend[2] >= 0) progress_flush(a, pend);                       // (both places taken: make room for the one in flight)
+        progress_park(pend);
+        progress_flush(a, pend);
     }
 }
 

@@ -516,15 +516,26 @@ struct SlotCtl {
     unsigned visit;
 };
 
-// PROG: completion counters (IndirectArgs::progress), as in lto_indirect_cw.cu: a segment is counted once the visit that carried
-// its F_STORE flag has passed bar_done (its columns are stored), or after the CTA-wide barrier at the end of the kernel.
-__device__ __forceinline__ void progress_count(const IndirectArgs& a, long long seg) {
-    __threadfence_system();
-    atomicAdd(a.progress + seg / a.prog_chunk, 1ull);
+// PROG: completion counters (IndirectArgs::progress), as in lto_indirect_cw.cu: a segment may be counted once the visit that
+// carried its F_STORE flag has passed bar_done (its columns are stored), or after the CTA-wide barrier at the end of the kernel;
+// per tile a lane parks up to two such segments and the warp counts them (one system-scope fence) every 8th visit of the tile.
+__device__ __forceinline__ void progress_flush(const IndirectArgs& a, long long (&pend)[3]) {
+    if (pend[1] >= 0) {
+        __threadfence_system();
+        atomicAdd(a.progress + pend[1] / a.prog_chunk, 1ull);
+        if (pend[2] >= 0) atomicAdd(a.progress + pend[2] / a.prog_chunk, 1ull);
+        pend[1] = -1; pend[2] = -1;
+    }
+}
+__device__ __forceinline__ void progress_park(long long (&pend)[3]) {
+    if (pend[0] >= 0) {
+        if (pend[1] < 0) pend[1] = pend[0]; else pend[2] = pend[0];
+        pend[0] = -1;
+    }
 }
 
 template <bool JOINT, bool PROG>
-__device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsigned char* smem, long long (&pend)[NTILE]) {
+__device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsigned char* smem, long long (&pend)[NTILE][3]) {
     const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
@@ -561,7 +572,8 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 c1 = clock64();
                 c_wait += c1 - c0;
                 if (PROG) {
-                    if (pend[t] >= 0) { progress_count(a, pend[t]); pend[t] = -1; }
+                    progress_park(pend[t]);
+                    if ((c.visit & 7u) == 0u || __any_sync(fullmask, pend[t][2] >= 0)) progress_flush(a, pend[t]);
                 }
                 if (c.active) {
                     double s2 = c.esum;
@@ -603,7 +615,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 if (a.status) a.status[c.seg] = c.status;
                 if (a.nsteps_out) { a.nsteps_out[2 * c.seg] = c.na; a.nsteps_out[2 * c.seg + 1] = c.nt; }
                 flags |= F_STORE; store_seg = (int)c.seg;
-                if (PROG) pend[t] = c.seg;
+                if (PROG) pend[t][0] = c.seg;
                 c.active = false;
             }
             bool fresh = false;
@@ -694,16 +706,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw14(IndirectArgs a) {
     }
     __syncthreads();
     // warps 0..6: column warps (sub-partitions 0,1,2,3,0,1,2); warp 7: the state warp (sub-partition 3, next to one column warp)
-    long long pend[NTILE];
+    long long pend[NTILE][3];
 #pragma unroll
-    for (int t = 0; t < NTILE; ++t) pend[t] = -1;
+    for (int t = 0; t < NTILE; ++t) { pend[t][0] = -1; pend[t][1] = -1; pend[t][2] = -1; }
     if (warp == NCW) state_warp<JOINT, PROG>(a, lane, smem_raw, pend);
     else column_warp<JOINT>(a, warp, lane, smem_raw);
     if (PROG) {
         __syncthreads();                                                 // the columns of the tiles' last visits are stored
 #pragma unroll
-        for (int t = 0; t < NTILE; ++t)
-            if (pend[t] >= 0) progress_count(a, pend[t]);
+        for (int t = 0; t < NTILE; ++t) {
+            if (pend[t][2] >= 0) progress_flush(a, pend[t]);
+            progress_park(pend[t]);
+            progress_flush(a, pend[t]);
+        }
     }
 }
 
