@@ -67,7 +67,8 @@ def test_direct_leg_matches_oracle(ns, mode, oracle, hostcheck):
 def test_indirect_segment_matches_oracle(nd, ctl, oracle, hostcheck):
     b = S.indirect_batch(4, ndim=nd, seed=9)
     b["x0"][:, (9 if nd == 12 else 10):(12 if nd == 12 else 13)] *= 8.0
-    for law in ((1.0, 1.0, 0.05), (2.0, 1.0, 10.0), (1.0, 1e-2, 0.05)):
+    # smooth switch, unclamped p = 2, sharp switch, constant thrust (p = 0), clamped p = 2 (umag' = 0, CRTBP_stateCostate_deriv.jl:48-50)
+    for law in ((1.0, 1.0, 0.05), (2.0, 1.0, 10.0), (1.0, 1e-2, 0.05), (0.0, 1.0, 0.05), (2.0, 1.0, 1e-3)):
         ip = oracle.iparams(law[2], p=law[0], rho=law[1])
         xo, Po, so, nao, nto = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip, controller=ctl)
         for s in range(4):
