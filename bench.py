@@ -103,6 +103,49 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------- NUMA placement of the pinned host buffers
+def _cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def numa_bind(device_index):
+    """Before the pinned host buffers of the e2e leg are allocated: move this thread onto the CPUs of the NUMA node the GPU hangs off, so
+    that cudaHostAlloc places the pages there (PCIe DMA into the other socket's memory crosses the inter-socket link).  Returns
+    (previous affinity or None, note for the JSON line); never raises -- on any doubt nothing is changed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, "no NUMA information for %s" % bdf
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _cpulist(f.read())
+        old = os.sched_getaffinity(0)
+        want = old & cpus
+        if not want:
+            return None, "GPU %s is on NUMA node %d, none of its CPUs is available to this process" % (bdf, node)
+        os.sched_setaffinity(0, want)
+        return old, "pinned host buffers allocated from a CPU of NUMA node %d (the node of GPU %s)" % (node, bdf)
+    except Exception as e:                                                   # noqa: BLE001
+        return None, "NUMA placement skipped (%s)" % type(e).__name__
+
+
+def numa_restore(old):
+    try:
+        if old:
+            os.sched_setaffinity(0, old)
+    except Exception:                                                        # noqa: BLE001
+        pass
+
+
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
 def cpu_reference_pass(workload, batch, n, nthreads):
     """One pass of the REFERENCE ALGORITHM on the host: direct = defectCalc + forward-FD jacobianCalc
@@ -717,6 +760,7 @@ def run_ours(args):
     n_seg = args.n_seg or (65536 if direct else 131072)
     batch = make_batch(wl, n_seg, rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    numa_old, numa_note = numa_bind(local)                                # until the pinned buffers below exist
 
     if direct:
         ns = 7 if wl.startswith("direct7") else 6
@@ -777,6 +821,7 @@ def run_ours(args):
         flops_unit = None
         bytes_unit = BYTES_PER_SEG[nd]
         attempted = None
+    numa_restore(numa_old)                                               # the CPU baseline below uses every host thread again
 
     def barrier():
         if world > 1:
@@ -842,7 +887,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "segment-propagations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "timing": "host wall clock around the blocking lto_*_defect_jac call, pinned host buffers, max over ranks"},
+                    "timing": "host wall clock around the blocking lto_*_defect_jac call, pinned host buffers, max over ranks",
+                    "host_buffers": numa_note},
             "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
     if world > 1:
         line["allgather"] = allgather_leg(args, h, dev, wl, n_seg, world, rank, batch, p)
