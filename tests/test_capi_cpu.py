@@ -129,3 +129,24 @@ def test_host_chunk_plan(capi):
             assert sum(plan) == n and min(plan) > 0 and len(plan) <= 300, (n, kw, plan[:4])
     with pytest.raises(capi.LtoError):
         capi.host_chunk_plan("direct", 100, n_nodes=30)        # not a whole number of trajectories
+
+
+def test_library_carries_sm100a_kernels_only(capi):
+    """The shared object holds native sm_100a code for every kernel of the path (no PTX-only JIT path, no other architecture),
+    and the FP64 throughput kernels really are DFMA code."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from lowthrustopt_b200 import build
+    so = build.build_lib()
+    elfs = subprocess.run([cuobjdump, "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", elfs))
+    assert archs == {"sm_100a"}, archs
+    usage = subprocess.run([cuobjdump, "-res-usage", so], capture_output=True, text=True).stdout
+    for kern in ("k_direct_cw", "k_direct_state", "k_indirect_cw", "k_indirect_state", "k_indirect_cw14", "k_indirect_state14",
+                 "k_indirect_newton", "k_direct_qp", "k_fp64_probe"):
+        assert kern in usage, kern
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN3lto3icw16k_indirect_stateENS_12IndirectArgsE", so], capture_output=True, text=True).stdout
+    assert sass.count("DFMA") > 500
