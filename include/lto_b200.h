@@ -109,9 +109,7 @@ double lto_last_kernel_ms(const lto_handle* h);
 void* lto_stream(lto_handle* h);               /* cudaStream_t the *_dev entry points launch on */
 /* Introspection (no device work): the chunk schedule the host-buffer entry points would use for their
  * H2D -> kernel -> D2H pipeline on a GPU with n_sm SMs.  method 0 = direct (nvar = nstate, nsteps and mode as in
- * lto_direct_*), 1 = indirect (nvar = ndim; nsteps ignored; mode = 2: the two-kernel-stream experiment LTO_HOST_STREAMS=2,
- * 3: completion counters LTO_HOST_PROGRESS=1 (first chunk = its own launch, all others = ranges of ONE launch), anything else the
- * default single stream); n_nodes = 0 pairs form, > 0 trajectory form (chunks are
+ * lto_direct_*), 1 = indirect (nvar = ndim; nsteps and mode ignored); n_nodes = 0 pairs form, > 0 trajectory form (chunks are
  * whole trajectories).  Writes up to cap chunk sizes (segments) to chunks and returns the number of chunks, < 0 on bad arguments. */
 int lto_host_chunk_plan(int method, int n_sm, int64_t n_seg, int n_nodes, int nvar, int nsteps, int mode, int want_jac,
                         int64_t* chunks, int cap);

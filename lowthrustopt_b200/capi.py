@@ -133,12 +133,10 @@ def indirect_params(thrustLimit=0.05, mass=1000.0, time_direction=1.0, p=1.0, rh
     return q
 
 
-def host_chunk_plan(method, n_seg, n_nodes=0, nvar=None, nsteps=10, mode=LTO_FIXED, jac=True, n_sm=148, streams=1):
+def host_chunk_plan(method, n_seg, n_nodes=0, nvar=None, nsteps=10, mode=LTO_FIXED, jac=True, n_sm=148):
     """Chunk sizes (segments per launch) of the host-buffer entry points' H2D -> kernel -> D2H pipeline (lto_host_chunk_plan;
-    pure host logic, needs no GPU).  method: "direct" | "indirect" (streams: kernel streams the indirect chunks alternate between)."""
+    pure host logic, needs no GPU).  method: "direct" | "indirect"."""
     m = {"direct": 0, "indirect": 1}[method]
-    if m == 1:
-        mode = streams
     nvar = nvar if nvar is not None else (7 if m == 0 else 12)
     buf = (C.c_int64 * 8192)()
     n = lib().lto_host_chunk_plan(m, n_sm, int(n_seg), int(n_nodes), int(nvar), int(nsteps), int(mode), int(bool(jac)), buf, 8192)

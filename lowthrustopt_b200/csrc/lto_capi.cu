@@ -82,16 +82,12 @@ int lto_init(int device, lto_handle** out) {
     CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
     CK(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_compute2, cudaStreamNonBlocking));
-    CK(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    { const char* e = getenv("LTO_HOST_STREAMS"); h->host_streams = (e && atoi(e) == 2) ? 2 : 1; }
-    { const char* e = getenv("LTO_HOST_PROGRESS"); if (e && atoi(e) == 1) h->host_streams = 3; }
     CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
     CK(h, cudaEventCreate(&h->ev_t0));
     CK(h, cudaEventCreate(&h->ev_t1));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-    CK(h, cudaMalloc((void**)&h->d_ctr, 256 + LTO_PROG_WORDS * 8));      // work-queue counters + completion counters (d_ctr + 32)
+    CK(h, cudaMalloc((void**)&h->d_ctr, 256));                             // work-queue counter of the throughput kernels
     if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
     *out = h;
     return LTO_SUCCESS;
@@ -123,7 +119,7 @@ void lto_destroy(lto_handle* h) {
     if (!h) return;
     if (h->n_child > 0) { for (int i = 0; i < h->n_child; ++i) lto_destroy(h->child[i]); free(h); return; }
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_compute2); cudaStreamSynchronize(h->s_copy); cudaStreamSynchronize(h->s_h2d);
+    cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy); cudaStreamSynchronize(h->s_h2d);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ctr) cudaFree(h->d_ctr);
@@ -133,8 +129,7 @@ void lto_destroy(lto_handle* h) {
     if (h->d_slv) cudaFree(h->d_slv);
     for (int i = 0; i < 8; ++i) { cudaEventDestroy(h->ev_chunk[i]); cudaEventDestroy(h->ev_h2d[i]); }
     cudaEventDestroy(h->ev_in); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
-    cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_compute2); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_h2d);
-    cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_h2d);
     free(h);
 }
 
@@ -222,7 +217,7 @@ static int dispatch_indirect(lto_handle* h, const IndirectArgs& a, int ndim, int
     cudaError_t e = cudaErrorNotSupported;
     if (kernel != LTO_KERNEL_GENERIC) e = launch_indirect_fast(a, ndim, st, &nl);
     if (e == cudaErrorNotSupported) {
-        if (kernel == LTO_KERNEL_FAST || a.progress) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
+        if (kernel == LTO_KERNEL_FAST) return fail(h, LTO_ERR_ARG, "LTO_KERNEL_FAST does not cover this configuration");
         e = launch_indirect_generic(a, ndim, st, &nl);
     }
     h->launches += nl;
@@ -282,29 +277,11 @@ static void plan_direct(std::vector<long long>& plan, int n_sm, long long n_seg,
 }
 // Indirect: K3 17.5 ns per segment + 0.25 ms per launch (the work queue's tail: about one segment lifetime at 64 slots per SM),
 // K3-14 26 ns + 0.33 ms, K4 (defect only) 2.5 ns + 50 us.
-// streams = 2 (LTO_HOST_STREAMS=2, see indirect_host): the model assumes 0.4 of a chunk's tail stays exposed -- measured slower than
-// one stream, kept selectable.
-static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_seg, int npt, int ndim, bool want_jac, int streams) {
+static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_seg, int npt, int ndim, bool want_jac) {
     const size_t ND = (size_t)ndim;
     const size_t per_seg = ND * 8 + 12 + (want_jac ? ND * ND * 8 : 0);
     const double r_ns = !want_jac ? 2.5 : ndim == 14 ? 26.0 : 17.5;
-    const double a_ns = (!want_jac ? 50e3 : ndim == 14 ? 330e3 : 250e3) * (streams == 2 ? 0.4 : 1.0);
-    if (streams == 3 && want_jac && n_seg * (long long)per_seg > (8ll << 20)) {
-        // completion counters (LTO_HOST_PROGRESS=1): a first launch of about one fill of the slots (so that the copy engine starts
-        // early and the rest of the inputs arrive behind it), then ONE launch over everything else whose finished ranges of `cs`
-        // segments are shipped as their counters fill up -- the work queue's tail is paid twice per call, not once per chunk
-        const long long unit = npt > 0 ? npt - 1 : 1;
-        auto up = [](long long x, long long q) { return (x + q - 1) / q * q; };
-        const long long q = up(std::max<long long>(2048, unit), unit);
-        const long long c0 = std::min(n_seg, up((long long)n_sm * 64, q));
-        plan.clear(); plan.push_back(c0);
-        const long long rest = n_seg - c0;
-        if (rest > 0) {
-            const long long cs = std::max(up(16384, q), up((rest + LTO_PROG_WORDS - 1) / LTO_PROG_WORDS, q));
-            for (long long left = rest; left > 0; left -= std::min(cs, left)) plan.push_back(std::min(cs, left));
-        }
-        return;
-    }
+    const double a_ns = !want_jac ? 50e3 : ndim == 14 ? 330e3 : 250e3;
     plan_chunks(plan, n_seg, per_seg, r_ns, a_ns, (long long)n_sm * 64, npt > 0 ? npt - 1 : 1);
 }
 
@@ -484,68 +461,38 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     char* dq = (char*)h->d_out;
     double* dD = (double*)dq; dq += bD; int32_t* dS = (int32_t*)dq; dq += bS; int32_t* dN = (int32_t*)dq; dq += bN;
     double* dJ = want_jac ? (double*)dq : nullptr;
-    // LTO_HOST_STREAMS=2 (experiment, off by default): chunks alternate between two kernel streams (each with its own work-queue
-    // counter and column scratch), so the CTAs of chunk c+1 can start on every SM whose CTA of chunk c has drained its slots instead
-    // of waiting for the slowest segment of chunk c.  Measured on a B200 (config 4 per GPU, e2e): 27.4 M seg/s against 29.3 M with one
-    // stream and fewer, larger chunks (K3-14: 22.1 vs 22.8) -- a CTA only leaves when its last slot does, so little of the tail is hidden.
-    const int n_str = (want_jac && h->host_streams == 2) ? 2 : 1;
     const size_t scr_bytes = want_jac ? al(indirect_cw_scratch_bytes(h->n_sm)) : 0;
-    if (want_jac) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, scr_bytes * n_str); if (rc) return rc; }
+    if (want_jac) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, scr_bytes); if (rc) return rc; }
     // per-trajectory / per-segment parameter arrays are small: up front; the node data goes chunk by chunk (below)
     if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    // LTO_HOST_PROGRESS=1: completion counters (plan_indirect, kind 3).  Only the throughput kernels count, so the mode needs them.
-    const bool prog = want_jac && h->host_streams == 3 && p->kernel != LTO_KERNEL_GENERIC && p->controller == 0 && n_seg <= 0x7fffffffll;
     std::vector<long long> plan;
-    plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac, prog ? 3 : n_str);
-    const bool grouped = prog && plan.size() > 2;                        // chunks 1.. are ONE launch
-    unsigned long long* d_prog = h->d_ctr + 32;
-    if (grouped) {
-        rc = resolve_stream_memops(h); if (rc) return rc;
-        CK(h, cudaMemsetAsync(d_prog, 0, (plan.size() - 1) * 8, h->s_compute));
-        CK(h, cudaEventRecord(h->ev_join, h->s_compute));
-        CK(h, cudaStreamWaitEvent(h->s_copy, h->ev_join, 0));            // no counter is looked at before it has been cleared
-    }
+    plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac);
     long long s0 = 0;
     for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
         const long long ns = plan[ci];
-        const int si = ci % n_str;
-        cudaStream_t st = si ? h->s_compute2 : h->s_compute;
-        if (!grouped || ci <= 1) {                                       // a launch starts here: over this chunk, or over all the rest
-            const long long nl = (grouped && ci == 1) ? n_seg - s0 : ns;
-            const long long r0 = lto_node_a(s0, npt);
-            const long long p0 = lto_traj_of(s0, npt);
-            const long long nr = npt > 0 ? nl / (npt - 1) * npt : nl;
-            CK(h, cudaMemcpyAsync(dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
-            CK(h, cudaMemcpyAsync(dT0 + r0, t0 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
-            if (npt == 0) CK(h, cudaMemcpyAsync(dT1 + r0, t1 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
-            if (sep_target) CK(h, cudaMemcpyAsync(dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
-            CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
-            CK(h, cudaStreamWaitEvent(st, h->ev_h2d[ci & 7], 0));
-            a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
-            a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
-            a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
-            a.n_seg = nl; a.npt = npt; a.counter = h->d_ctr + 8 * si; a.scratch = (double*)((char*)h->d_scr + scr_bytes * si); a.prof = h->d_prof;
-            a.progress = (grouped && ci == 1) ? d_prog : nullptr; a.prog_chunk = (grouped && ci == 1) ? plan[1] : 0;
-            rc = dispatch_indirect(h, a, ndim, p->kernel, st); if (rc) return rc;
-        }
-        if (grouped && ci >= 1) {                                        // this range of the big launch is complete when its counter is full
-            const int e = g_cu_wait64((void*)h->s_copy, (unsigned long long)(uintptr_t)(d_prog + (ci - 1)), (unsigned long long)ns, 0u /* GEQ */);
-            if (e != 0) return fail(h, LTO_ERR_CUDA, "cuStreamWaitValue64 -> CUresult %d", e);
-        } else {
-            cudaEvent_t ev = h->ev_chunk[ci & 7];
-            CK(h, cudaEventRecord(ev, st));
-            CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
-        }
+        const long long r0 = lto_node_a(s0, npt);
+        const long long p0 = lto_traj_of(s0, npt);
+        const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+        CK(h, cudaMemcpyAsync(dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(h, cudaMemcpyAsync(dT0 + r0, t0 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        if (npt == 0) CK(h, cudaMemcpyAsync(dT1 + r0, t1 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        if (sep_target) CK(h, cudaMemcpyAsync(dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
+        CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
+        a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;
+        a.thrustLimit_arr = dTL ? dTL + p0 : nullptr; a.rho_arr = dRH ? dRH + p0 : nullptr;
+        a.defect = dD + s0 * ND; a.status = dS + s0; a.nsteps_out = dN + 2 * s0; a.phi = want_jac ? dJ + s0 * ND * ND : nullptr;
+        a.n_seg = ns; a.npt = npt; a.counter = h->d_ctr; a.scratch = (double*)h->d_scr; a.prof = h->d_prof;
+        rc = dispatch_indirect(h, a, ndim, p->kernel); if (rc) return rc;
+        cudaEvent_t ev = h->ev_chunk[ci & 7];
+        CK(h, cudaEventRecord(ev, h->s_compute));
+        CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
         CK(h, cudaMemcpyAsync(defect + s0 * ND, dD + s0 * ND, ns * ND * 8, cudaMemcpyDeviceToHost, h->s_copy));
         if (status) CK(h, cudaMemcpyAsync(status + s0, dS + s0, ns * 4, cudaMemcpyDeviceToHost, h->s_copy));
         if (nsteps_out) CK(h, cudaMemcpyAsync(nsteps_out + 2 * s0, dN + 2 * s0, ns * 8, cudaMemcpyDeviceToHost, h->s_copy));
         if (want_jac) CK(h, cudaMemcpyAsync(phi + s0 * ND * ND, dJ + s0 * ND * ND, ns * ND * ND * 8, cudaMemcpyDeviceToHost, h->s_copy));
-    }
-    if (n_str == 2) {
-        CK(h, cudaEventRecord(h->ev_join, h->s_compute2));
-        CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_join, 0));
     }
     CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_copy));
@@ -566,7 +513,7 @@ int lto_host_chunk_plan(int method, int n_sm, int64_t n_seg, int n_nodes, int nv
         plan_direct(plan, n_sm, n_seg, n_nodes, nvar, nsteps, mode, want_jac != 0);
     } else if (method == 1) {
         if (nvar != 12 && nvar != 14) return LTO_ERR_ARG;
-        plan_indirect(plan, n_sm, n_seg, n_nodes, nvar, want_jac != 0, ((mode == 2 || mode == 3) && want_jac) ? mode : 1);
+        plan_indirect(plan, n_sm, n_seg, n_nodes, nvar, want_jac != 0);
     } else return LTO_ERR_ARG;
     for (int i = 0; i < (int)plan.size() && i < cap; ++i) chunks[i] = plan[i];
     return (int)plan.size();

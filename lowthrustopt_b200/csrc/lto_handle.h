@@ -7,16 +7,12 @@
 #include <stdint.h>
 
 static const size_t LTO_PROF_WORDS = 8192;
-static const long long LTO_PROG_WORDS = 4096;      // completion counters of the host-buffer indirect pipeline (behind d_ctr)
 #define LTO_MAX_DEVICES 16
 
 struct lto_handle {
     int device;
     int n_sm;
     cudaStream_t s_compute, s_copy, s_h2d;          // kernels; device->host (and peer pushes); host->device
-    cudaStream_t s_compute2;                        // second kernel stream of the host-buffer indirect pipeline (alternating chunks)
-    cudaEvent_t ev_join;
-    int host_streams;                               // 1 or 2 kernel streams (LTO_HOST_STREAMS, default 1); 3: completion counters (LTO_HOST_PROGRESS=1)
     cudaEvent_t ev_in, ev_t0, ev_t1;
     cudaEvent_t ev_chunk[8], ev_h2d[8];
     void* d_in; size_t d_in_cap;

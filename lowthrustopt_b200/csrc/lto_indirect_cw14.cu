@@ -516,26 +516,8 @@ struct SlotCtl {
     unsigned visit;
 };
 
-// PROG: completion counters (IndirectArgs::progress), as in lto_indirect_cw.cu: a segment may be counted once the visit that
-// carried its F_STORE flag has passed bar_done (its columns are stored), or after the CTA-wide barrier at the end of the kernel;
-// per tile a lane parks up to two such segments and the warp counts them (one system-scope fence) every 8th visit of the tile.
-__device__ __forceinline__ void progress_flush(const IndirectArgs& a, long long (&pend)[3]) {
-    if (pend[1] >= 0) {
-        __threadfence_system();
-        atomicAdd(a.progress + pend[1] / a.prog_chunk, 1ull);
-        if (pend[2] >= 0) atomicAdd(a.progress + pend[2] / a.prog_chunk, 1ull);
-        pend[1] = -1; pend[2] = -1;
-    }
-}
-__device__ __forceinline__ void progress_park(long long (&pend)[3]) {
-    if (pend[0] >= 0) {
-        if (pend[1] < 0) pend[1] = pend[0]; else pend[2] = pend[0];
-        pend[0] = -1;
-    }
-}
-
-template <bool JOINT, bool PROG>
-__device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsigned char* smem, long long (&pend)[NTILE][3]) {
+template <bool JOINT>
+__device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsigned char* smem) {
     const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
@@ -571,10 +553,6 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 mbar_wait_parked(S.bar_done, (c.visit - 1) & 1);
                 c1 = clock64();
                 c_wait += c1 - c0;
-                if (PROG) {
-                    progress_park(pend[t]);
-                    if ((c.visit & 7u) == 0u || __any_sync(fullmask, pend[t][2] >= 0)) progress_flush(a, pend[t]);
-                }
                 if (c.active) {
                     double s2 = c.esum;
                     if (JOINT) {
@@ -615,7 +593,6 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 if (a.status) a.status[c.seg] = c.status;
                 if (a.nsteps_out) { a.nsteps_out[2 * c.seg] = c.na; a.nsteps_out[2 * c.seg + 1] = c.nt; }
                 flags |= F_STORE; store_seg = (int)c.seg;
-                if (PROG) pend[t][0] = c.seg;
                 c.active = false;
             }
             bool fresh = false;
@@ -694,7 +671,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
     }
 }
 
-template <bool JOINT, bool PROG = false>
+template <bool JOINT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw14(IndirectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -706,20 +683,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_cw14(IndirectArgs a) {
     }
     __syncthreads();
     // warps 0..6: column warps (sub-partitions 0,1,2,3,0,1,2); warp 7: the state warp (sub-partition 3, next to one column warp)
-    long long pend[NTILE][3];
-#pragma unroll
-    for (int t = 0; t < NTILE; ++t) { pend[t][0] = -1; pend[t][1] = -1; pend[t][2] = -1; }
-    if (warp == NCW) state_warp<JOINT, PROG>(a, lane, smem_raw, pend);
+    if (warp == NCW) state_warp<JOINT>(a, lane, smem_raw);
     else column_warp<JOINT>(a, warp, lane, smem_raw);
-    if (PROG) {
-        __syncthreads();                                                 // the columns of the tiles' last visits are stored
-#pragma unroll
-        for (int t = 0; t < NTILE; ++t) {
-            if (pend[t][2] >= 0) progress_flush(a, pend[t]);
-            progress_park(pend[t]);
-            progress_flush(a, pend[t]);
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -819,7 +784,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) k_indirect_state14(IndirectArgs
 
 size_t indirect_cw14_scratch_bytes(int n_sm) { return (size_t)n_sm * icw14::SCRATCH_DOUBLES_PER_CTA * sizeof(double); }
 
-template <bool JOINT, bool PROG>
+template <bool JOINT>
 static cudaError_t launch_icw14(const IndirectArgs& a, cudaStream_t st) {
     static int n_sm_dev[64] = {0};
     static bool attr_dev[64] = {false};
@@ -828,7 +793,7 @@ static cudaError_t launch_icw14(const IndirectArgs& a, cudaStream_t st) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_dev[dev]) {
         cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(icw14::k_indirect_cw14<JOINT, PROG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw14::SMEM);
+        e = cudaFuncSetAttribute(icw14::k_indirect_cw14<JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)icw14::SMEM);
         if (e != cudaSuccess) return e;
         attr_dev[dev] = true;
     }
@@ -837,7 +802,7 @@ static cudaError_t launch_icw14(const IndirectArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     const long long per_cta = (long long)icw14::NTILE * icw14::TS;
     const int grid = (int)std::min<long long>((a.n_seg + per_cta - 1) / per_cta, (long long)n_sm);
-    icw14::k_indirect_cw14<JOINT, PROG><<<grid, icw14::NTHREADS, icw14::SMEM, st>>>(a);
+    icw14::k_indirect_cw14<JOINT><<<grid, icw14::NTHREADS, icw14::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -857,13 +822,7 @@ cudaError_t launch_indirect_cw14(const IndirectArgs& a, cudaStream_t st, int* n_
         return e;
     }
     if (a.scratch == nullptr) return cudaErrorNotSupported;
-    cudaError_t e;
-    if (a.progress != nullptr) {
-        if (a.prog_chunk <= 0) return cudaErrorNotSupported;
-        e = (a.cfg.err_norm != 0) ? launch_icw14<true, true>(a, st) : launch_icw14<false, true>(a, st);
-    } else {
-        e = (a.cfg.err_norm != 0) ? launch_icw14<true, false>(a, st) : launch_icw14<false, false>(a, st);
-    }
+    const cudaError_t e = (a.cfg.err_norm != 0) ? launch_icw14<true>(a, st) : launch_icw14<false>(a, st);
     if (e == cudaSuccess) *n_launch = 1;
     return e;
 }

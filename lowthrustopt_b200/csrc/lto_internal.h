@@ -32,11 +32,6 @@ struct IndirectArgs {
     int npt;
     IndirectCfg cfg;
     SCConst c;
-    // optional completion counters (K3 / K3-14 only): progress[seg / prog_chunk] is incremented once per segment after ALL of its
-    // outputs (defect, status, step counts, every STM column) have been written and fenced at system scope, so that a copy stream
-    // can ship a finished range of segments (cuStreamWaitValue64) while the launch is still running; NULL = off
-    unsigned long long* progress;
-    long long prog_chunk;
 };
 
 __host__ __device__ inline long long lto_node_a(long long s, int npt) { return npt > 0 ? s + s / (npt - 1) : s; }

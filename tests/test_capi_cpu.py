@@ -106,16 +106,6 @@ def test_host_chunk_plan(capi):
     assert sum(plan) == 131072 and 3 <= len(plan) <= 5 and len(set(plan[:-1])) == 1
     plan = capi.host_chunk_plan("indirect", 1 << 20, nvar=12)
     assert sum(plan) == 1 << 20 and 8 <= len(plan) <= 14
-    # the two-kernel-stream experiment (LTO_HOST_STREAMS=2) assumes most of a chunk's tail hidden -> more, smaller chunks
-    plan2 = capi.host_chunk_plan("indirect", 131072, nvar=12, streams=2)
-    assert sum(plan2) == 131072 and 5 <= len(plan2) <= 8 and len(set(plan2[:-1])) == 1
-    # completion counters (LTO_HOST_PROGRESS=1): one fill of the slots first, then ranges of one big launch
-    plan3 = capi.host_chunk_plan("indirect", 131072, nvar=12, streams=3)
-    assert sum(plan3) == 131072 and plan3[0] == 10240 and set(plan3[1:-1]) == {16384} and 0 < plan3[-1] <= 16384
-    plan3 = capi.host_chunk_plan("indirect", 1 << 27, nvar=12, streams=3)
-    assert sum(plan3) == 1 << 27 and len(plan3) - 1 <= 4096 and len(set(plan3[1:-1])) == 1
-    plan3 = capi.host_chunk_plan("indirect", 1024 * 200, n_nodes=201, nvar=12, streams=3)
-    assert sum(plan3) == 1024 * 200 and all(c % 200 == 0 for c in plan3) and len(set(plan3[1:-1])) == 1
     # trajectory forms: chunks are whole trajectories
     for method, nvar, nn, nt in (("indirect", 12, 201, 1024), ("indirect", 14, 201, 777), ("direct", 7, 30, 5000), ("direct", 6, 30, 4097)):
         plan = capi.host_chunk_plan(method, nt * (nn - 1), n_nodes=nn, nvar=nvar)

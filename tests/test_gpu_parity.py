@@ -217,25 +217,16 @@ def test_indirect_symplectic_property(lto):
     assert np.abs(det - 1.0).max() < 1e-8
 
 
-@pytest.mark.parametrize("streams", [1, 2, 3])
 @pytest.mark.parametrize("nd,n", [(12, 40000), (14, 40000)])
-def test_indirect_multi_chunk_host_pipeline(nd, n, streams, lto, monkeypatch):
+def test_indirect_multi_chunk_host_pipeline(nd, n, lto):
     """Host-buffer calls above 8 MiB of output are cut into chunks (lto_host_chunk_plan) whose H2D copies, kernels and D2H copies
-    run on their own streams -- with LTO_HOST_STREAMS=2 the kernels alternate between two streams, each with its own work-queue
-    counter and column scratch; with LTO_HOST_PROGRESS=1 everything after the first chunk is ONE launch whose finished ranges are
-    shipped as their completion counters fill up: every segment must come back exactly as the one-launch call of a small batch computes it
+    run on their own streams: every segment must come back exactly as the one-launch call of a small batch computes it
     (bitwise -- a segment's arithmetic does not depend on its batch position)."""
-    plan = capi.host_chunk_plan("indirect", n, nvar=nd, streams=streams)
+    plan = capi.host_chunk_plan("indirect", n, nvar=nd)
     assert len(plan) >= 2 and sum(plan) == n
     b = S.indirect_batch(n, ndim=nd, seed=77)
     p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
-    if streams >= 2:                                                          # 2: two kernel streams; 3: completion counters (one big launch)
-        monkeypatch.setenv(*(("LTO_HOST_STREAMS", "2") if streams == 2 else ("LTO_HOST_PROGRESS", "1")))    # read by lto_init
-        h2 = capi.Handle(0)
-        r = h2.indirect(b["x0"], b["t0"], b["t1"], params=p)
-        h2.close()
-    else:
-        r = lto.indirect(b["x0"], b["t0"], b["t1"], params=p)
+    r = lto.indirect(b["x0"], b["t0"], b["t1"], params=p)
     assert np.all(r["status"] == 0) and np.all(np.isfinite(r["phi"])) and np.all(r["nsteps"][:, 0] > 0)
     for lo in (0, plan[0] - 1500, n - 3000):                              # inside the first chunk, across a chunk boundary, the tail
         sl = slice(lo, lo + 3000)
@@ -341,25 +332,3 @@ def test_sumsq_dev_and_sharded_line_search_single_rank(lto):
     j, _ = sh.run(p, jac=True)
     rj = lto.indirect_traj(c["XC_all"], c["t_TU"], params=p, thrustLimit=c["thrustLimit"], jac=True)
     assert np.abs(j["phi"].cpu().numpy().reshape(-1, 12, 12) - rj["phi"]).max() < 1e-12
-
-
-@pytest.mark.parametrize("variant", ["v3", "q3"])
-def test_experimental_k3_layouts_stay_correct(variant, lto, tmp_path):
-    """LTO_K3=v3 (three tiles in flight) / q3 (three lanes per column) are kept as measured negative results (DESIGN.md section 4);
-    they must keep producing the default kernel's results (integration-tolerance level: the step sequences may differ)."""
-    import subprocess, sys, os
-    b = S.indirect_batch(700, ndim=12, seed=77)
-    ref = lto.indirect(b["x0"], b["t0"], b["t1"], params=capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05))
-    out = str(tmp_path / "k3.npz")
-    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
-            "from lowthrustopt_b200 import capi, synthetic as S\n"
-            "h = capi.Handle(0); b = S.indirect_batch(700, ndim=12, seed=77)\n"
-            "r = h.indirect(b['x0'], b['t0'], b['t1'], params=capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05))\n"
-            "np.savez(%r, defect=r['defect'], phi=r['phi'], status=r['status'])\n") % (os.path.join(os.path.dirname(__file__), ".."), out)
-    env = dict(os.environ, LTO_K3=variant)
-    res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stderr
-    got = np.load(out)
-    assert np.all(got["status"] == 0)
-    assert rel(got["defect"], ref["defect"]) < TOL_STATE
-    assert rel(got["phi"], ref["phi"], np.abs(ref["phi"]).max(axis=(1, 2), keepdims=True)) < TOL_JAC
