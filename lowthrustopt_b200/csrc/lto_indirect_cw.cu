@@ -134,9 +134,18 @@ __device__ __forceinline__ void stage_input(const KStore& K, const double (&y)[N
     }
 }
 
+
+// State-only step control (LTO_NORM_STATE: K4, and K3 when the columns are not in the norm): the embedded estimate e = ga + gb is the
+// sum of the differences ga ~ (k1 - k12) and gb ~ (k11 - k13), which can cancel; the controller then takes max(|e|, |ga|, |gb|)
+// per component (lto_prop_generic.cuh drive_rk8 `robust`).  A NaN estimate stays NaN.
+__device__ __forceinline__ double rob_est(double e, double ga) {
+    const double m = fmax(fabs(e), fmax(fabs(ga), fabs(e - ga)));
+    return (e == e) ? m : e;
+}
+
 // 8th-order update (ode.jl:937) and, if ERR, the scaled squared error of the embedded
 // estimate (ode.jl:940 with the controller's scaling atol + rtol*max(|y|, |ynew|)).
-template <bool ERR>
+template <bool ERR, bool ROB = false>
 __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)[ND], double h, double h2, double atol, double rtol,
                                               double (&yn)[ND]) {
     double esum = 0.0;
@@ -163,6 +172,16 @@ __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)
             e[1] = ce * ((K.kv[0][q] + K.kv[10][q]) - (K.kv[11][q] + K.kv[12][q]));
             e[2] = ce * ((K.kl[0][q] + K.kl[10][q]) - (K.kl[11][q] + K.kl[12][q]));
             e[3] = ce * ((K.km[0][q] + K.km[10][q]) - (K.km[11][q] + K.km[12][q]));
+            if (ROB) {
+                double gr = 0.0;                                                              // (k1 - k12) of r' = v: -h B[11] . kv
+#pragma unroll
+                for (int l = 0; l < 11; ++l)
+                    if (lto_tab::Bf(11, l) != 0.0) gr = fma(lto_tab::Bf(11, l), K.kv[l][q], gr);
+                e[0] = rob_est(e[0], -ce2 * gr);
+                e[1] = rob_est(e[1], ce * (K.kv[0][q] - K.kv[11][q]));
+                e[2] = rob_est(e[2], ce * (K.kl[0][q] - K.kl[11][q]));
+                e[3] = rob_est(e[3], ce * (K.km[0][q] - K.km[11][q]));
+            }
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const double sc = fma(rtol, fmax(fabs(y[3 * b + q]), fabs(yn[3 * b + q])), atol);
@@ -640,7 +659,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             double x[ND], xn[ND];
 #pragma unroll
             for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-            esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+            esum = step_finish<true, !JOINT>(K, x, h, h2, atol, rtol, xn);
             double* xc = xbuf + (xi ^ 1) * ND * TS;
 #pragma unroll
             for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
@@ -718,7 +737,7 @@ constexpr int K4I_THREADS = 128;
 
 __global__ void __launch_bounds__(K4I_THREADS, 2) k_indirect_state(IndirectArgs a) {
     const unsigned fullmask = 0xffffffffu;
-    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
+    double atol = a.cfg.atol, rtol = a.cfg.rtol;                          // per slot: state_tol_scale(p, rho) of the slot's segment
     double x[ND], xn[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) { x[i] = 0.0; xn[i] = 0.0; }
@@ -778,6 +797,7 @@ __global__ void __launch_bounds__(K4I_THREADS, 2) k_indirect_state(IndirectArgs 
                 lw.aL = tl * a.c.kthr / a.c.mass;                         // CRTBP_stateCostate_deriv.jl:33
                 lw.rho_inv = 1.0 / rho;
                 lw.rho_inv_quarter_aL = lw.aL / (4.0 * rho);
+                { const double ts = state_tol_scale(a.c.p, rho); atol = a.cfg.atol * ts; rtol = a.cfg.rtol * ts; }
                 na = 0; nt = 0; status = 0; lastrej = false;
                 active = true; fresh = true;
             } else {
@@ -817,7 +837,7 @@ __global__ void __launch_bounds__(K4I_THREADS, 2) k_indirect_state(IndirectArgs 
         state_only_stage<4>(K, x, h, h2, a.c, lw);  state_only_stage<5>(K, x, h, h2, a.c, lw);  state_only_stage<6>(K, x, h, h2, a.c, lw);
         state_only_stage<7>(K, x, h, h2, a.c, lw);  state_only_stage<8>(K, x, h, h2, a.c, lw);  state_only_stage<9>(K, x, h, h2, a.c, lw);
         state_only_stage<10>(K, x, h, h2, a.c, lw); state_only_stage<11>(K, x, h, h2, a.c, lw); state_only_stage<12>(K, x, h, h2, a.c, lw);
-        esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+        esum = step_finish<true, true>(K, x, h, h2, atol, rtol, xn);
         have = true;
     }
 }

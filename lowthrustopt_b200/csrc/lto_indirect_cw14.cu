@@ -79,7 +79,7 @@ __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
 
 // y = [r(0..2) v(3..5) m(6) lr(7..9) lv(10..12) lm(13)].  Stage derivatives kept: v', lr', lv' (Nystrom form for
 // (r, v) as in K3) and m'; lm' only as running sums.
-struct KStore { double kv[13][3], kl[13][3], km[13][3], kq[13]; double slm, elm; };
+struct KStore { double kv[13][3], kl[13][3], km[13][3], kq[13]; double slm, elm, ela; };   // ela: klm_1 - klm_12 (robust estimate)
 
 template <int J, bool SPLIT = false>
 __device__ __forceinline__ void stage_input(const KStore& K, const double (&y)[ND], double h, double h2,
@@ -127,14 +127,24 @@ __device__ __forceinline__ void stage_input(const KStore& K, const double (&y)[N
 
 template <int J>
 __device__ __forceinline__ void lm_accumulate(KStore& K, double klm) {
-    if (J == 0) { K.slm = 0.0; K.elm = 0.0; }
+    if (J == 0) { K.slm = 0.0; K.elm = 0.0; K.ela = klm; }
+    if (J == 11) K.ela -= klm;
     if (lto_tab::CHIf(J) != 0.0) K.slm = fma(lto_tab::CHIf(J), klm, K.slm);
     if (lto_tab::PSIf(J) != 0.0) K.elm = fma(lto_tab::PSIf(J), klm, K.elm);
 }
 
+
+// State-only step control (LTO_NORM_STATE: K4, and K3 when the columns are not in the norm): the embedded estimate e = ga + gb is the
+// sum of the differences ga ~ (k1 - k12) and gb ~ (k11 - k13), which can cancel; the controller then takes max(|e|, |ga|, |gb|)
+// per component (lto_prop_generic.cuh drive_rk8 `robust`).  A NaN estimate stays NaN.
+__device__ __forceinline__ double rob_est(double e, double ga) {
+    const double m = fmax(fabs(e), fmax(fabs(ga), fabs(e - ga)));
+    return (e == e) ? m : e;
+}
+
 // 8th-order update (ode.jl:937) and, if ERR, the scaled squared error of the embedded estimate (ode.jl:940 with the
 // controller's scaling atol + rtol*max(|y|, |ynew|)).
-template <bool ERR>
+template <bool ERR, bool ROB = false>
 __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)[ND], double h, double h2, double atol, double rtol,
                                               double (&yn)[ND]) {
     double esum = 0.0;
@@ -162,6 +172,16 @@ __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)
             e[1] = ce * ((K.kv[0][q] + K.kv[10][q]) - (K.kv[11][q] + K.kv[12][q]));
             e[2] = ce * ((K.kl[0][q] + K.kl[10][q]) - (K.kl[11][q] + K.kl[12][q]));
             e[3] = ce * ((K.km[0][q] + K.km[10][q]) - (K.km[11][q] + K.km[12][q]));
+            if (ROB) {
+                double gr = 0.0;                                                              // (k1 - k12) of r' = v: -h B[11] . kv
+#pragma unroll
+                for (int l = 0; l < 11; ++l)
+                    if (lto_tab::Bf(11, l) != 0.0) gr = fma(lto_tab::Bf(11, l), K.kv[l][q], gr);
+                e[0] = rob_est(e[0], -ce2 * gr);
+                e[1] = rob_est(e[1], ce * (K.kv[0][q] - K.kv[11][q]));
+                e[2] = rob_est(e[2], ce * (K.kl[0][q] - K.kl[11][q]));
+                e[3] = rob_est(e[3], ce * (K.km[0][q] - K.km[11][q]));
+            }
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const double sc = fma(rtol, fmax(fabs(y[idx[b]]), fabs(yn[idx[b]])), atol);
@@ -178,8 +198,9 @@ __device__ __forceinline__ double step_finish(const KStore& K, const double (&y)
         yn[6] = fma(h, sq, y[6]);
         yn[13] = fma(h, K.slm, y[13]);
         if (ERR) {
-            const double eq = ce * ((K.kq[0] + K.kq[10]) - (K.kq[11] + K.kq[12]));
-            const double el = ce * K.elm;
+            double eq = ce * ((K.kq[0] + K.kq[10]) - (K.kq[11] + K.kq[12]));
+            double el = ce * K.elm;
+            if (ROB) { eq = rob_est(eq, ce * (K.kq[0] - K.kq[11])); el = rob_est(el, ce * K.ela); }
             const double r1 = eq * fast_rcp(fma(rtol, fmax(fabs(y[6]), fabs(yn[6])), atol));
             const double r2 = el * fast_rcp(fma(rtol, fmax(fabs(y[13]), fabs(yn[13])), atol));
             esum = fma(r1, r1, esum);
@@ -653,7 +674,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 double x[ND], xn[ND];
 #pragma unroll
                 for (int i = 0; i < ND; ++i) x[i] = xs[i * TS];
-                c.esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+                c.esum = step_finish<true, !JOINT>(K, x, h, h2, atol, rtol, xn);
                 double* xc = xbuf + (c.xi ^ 1) * ND * TS;
 #pragma unroll
                 for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
@@ -694,7 +715,7 @@ constexpr int K4_THREADS = 128;
 
 __global__ void __launch_bounds__(K4_THREADS, 2) k_indirect_state14(IndirectArgs a) {
     const unsigned fullmask = 0xffffffffu;
-    const double atol = a.cfg.atol, rtol = a.cfg.rtol;
+    double atol = a.cfg.atol, rtol = a.cfg.rtol;                          // per slot: state_tol_scale(p, rho) of the slot's segment
     double x[ND], xn[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) { x[i] = (i == 6) ? 1.0 : 0.0; xn[i] = x[i]; }
@@ -754,6 +775,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) k_indirect_state14(IndirectArgs
                 lw.tk = tl * a.c.kthr;
                 lw.rho_inv = 1.0 / rho;
                 lw.rho_inv_quarter = 0.25 / rho;
+                { const double ts = state_tol_scale(a.c.p, rho); atol = a.cfg.atol * ts; rtol = a.cfg.rtol * ts; }
                 na = 0; nt = 0; status = 0; lastrej = false;
                 active = true; fresh = true;
             } else {
@@ -775,7 +797,7 @@ __global__ void __launch_bounds__(K4_THREADS, 2) k_indirect_state14(IndirectArgs
         state_stage<4>(K, x, h, h2, a.c, lw, nullptr);  state_stage<5>(K, x, h, h2, a.c, lw, nullptr);  state_stage<6>(K, x, h, h2, a.c, lw, nullptr);
         state_stage<7>(K, x, h, h2, a.c, lw, nullptr);  state_stage<8>(K, x, h, h2, a.c, lw, nullptr);  state_stage<9>(K, x, h, h2, a.c, lw, nullptr);
         state_stage<10>(K, x, h, h2, a.c, lw, nullptr); state_stage<11>(K, x, h, h2, a.c, lw, nullptr); state_stage<12>(K, x, h, h2, a.c, lw, nullptr);
-        esum = step_finish<true>(K, x, h, h2, atol, rtol, xn);
+        esum = step_finish<true, true>(K, x, h, h2, atol, rtol, xn);
         have = true;
     }
 }

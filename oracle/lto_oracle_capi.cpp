@@ -210,7 +210,8 @@ int oracle_direct_jac_var(long long n_seg, int n, int nsteps, const double* Xa, 
 int oracle_indirect_prop(long long n_seg, int ndim, const double* x0, const double* t0, const double* t1,
                          const double* ip, const double* thrustLimit_arr, const double* rho_arr,
                          double atol, double rtol, int controller, double* xend, int* status, int* nacc, int* natt,
-                         int nthreads) {
+                         int nthreads, int est /* -1: default (1, the state-only controller of the kernels); 0: plain Fehlberg estimate */) {
+    if (est < 0) est = 1;
     IndirectParams P0 = make_ip(ip);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
     for (long long s = 0; s < n_seg; ++s) {
@@ -219,10 +220,33 @@ int oracle_indirect_prop(long long n_seg, int ndim, const double* x0, const doub
         if (rho_arr) P.rho = rho_arr[s];
         auto rhs = [&](const double* y, double* dy) { return sc_rhs<double>(ndim, y, P, dy); };
         int na = 0, nt = 0, st;
-        if (controller == 0) st = rk8_adaptive<double>(rhs, ndim, t0[s], t1[s], atol, rtol, false, x0 + s * ndim, xend + s * ndim, &na, &nt);
+        const double ts = (est == 1) ? state_tol_scale(P.p, P.rho) : 1.0;      // est = 1: the kernels' state-only controller
+        if (controller == 0) st = rk8_adaptive<double>(rhs, ndim, t0[s], t1[s], atol * ts, rtol * ts, false, x0 + s * ndim, xend + s * ndim, &na, &nt, 100000, est);
         else                 st = ode78<double>(rhs, ndim, t0[s], t1[s], rtol, false, x0 + s * ndim, xend + s * ndim, &na, &nt);
         for (int c = 0; c < ndim; ++c) if (std::isnan(xend[s * ndim + c]) && !st) st = 1;
         if (status) status[s] = st; if (nacc) nacc[s] = na; if (natt) natt[s] = nt;
+    }
+    return 0;
+}
+
+// Extended-precision truth for the end states: the same right-hand side and RKF7(8) controller in 80-bit long double at
+// a tolerance below the double-precision runs' (SURVEY 7.1 "long double truth for error budgets").  xend is rounded to double.
+int oracle_indirect_prop_ld(long long n_seg, int ndim, const double* x0, const double* t0, const double* t1,
+                            const double* ip, const double* thrustLimit_arr, const double* rho_arr,
+                            double atol, double rtol, double* xend, int* status, int nthreads) {
+    IndirectParams P0 = make_ip(ip);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
+    for (long long s = 0; s < n_seg; ++s) {
+        IndirectParams P = P0;
+        if (thrustLimit_arr) P.thrustLimit = thrustLimit_arr[s];
+        if (rho_arr) P.rho = rho_arr[s];
+        auto rhs = [&](const long double* y, long double* dy) { return sc_rhs<long double>(ndim, y, P, dy); };
+        long double xi[MAXN], xo[MAXN];
+        for (int c = 0; c < ndim; ++c) xi[c] = x0[s * ndim + c];
+        int na = 0, nt = 0;
+        int st = rk8_adaptive<long double>(rhs, ndim, t0[s], t1[s], atol, rtol, false, xi, xo, &na, &nt);
+        for (int c = 0; c < ndim; ++c) { xend[s * ndim + c] = (double)xo[c]; if (std::isnan(xend[s * ndim + c]) && !st) st = 1; }
+        if (status) status[s] = st;
     }
     return 0;
 }

@@ -137,7 +137,7 @@ def direct_jac_var(Xa, Xb, ua, ub, ta, tb, nsteps=10, dp=None, mode=0, tol=1e-13
     return defect, errors, jac.transpose(0, 2, 1).copy(), status
 
 
-def indirect_prop(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-13, rtol=1e-13, controller=0, nthreads=1):
+def indirect_prop(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-13, rtol=1e-13, controller=0, nthreads=1, est=-1):
     x0 = _f64(x0); t0 = _f64(t0); t1 = _f64(t1)
     n_seg, ndim = x0.shape
     tl = None if thrustLimit is None else _f64(thrustLimit); rh = None if rho is None else _f64(rho)
@@ -145,8 +145,19 @@ def indirect_prop(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-13, rtol=1
     na = np.zeros(n_seg, dtype=np.int32); nt = np.zeros(n_seg, dtype=np.int32)
     lib().oracle_indirect_prop(C.c_longlong(n_seg), C.c_int(ndim), _p(x0), _p(t0), _p(t1), _p(ip), _p(tl), _p(rh),
                                C.c_double(atol), C.c_double(rtol), C.c_int(controller), _p(xend), _p(status), _p(na),
-                               _p(nt), C.c_int(nthreads))
+                               _p(nt), C.c_int(nthreads), C.c_int(est))
     return xend, status, na, nt
+
+
+def indirect_prop_ld(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-17, rtol=1e-17, nthreads=1):
+    """End states in 80-bit long double at a tolerance below the double runs' (truth for error budgets); rounded to double."""
+    x0 = _f64(x0); t0 = _f64(t0); t1 = _f64(t1)
+    n_seg, ndim = x0.shape
+    tl = None if thrustLimit is None else _f64(thrustLimit); rh = None if rho is None else _f64(rho)
+    xend = np.zeros_like(x0); status = np.zeros(n_seg, dtype=np.int32)
+    lib().oracle_indirect_prop_ld(C.c_longlong(n_seg), C.c_int(ndim), _p(x0), _p(t0), _p(t1), _p(ip), _p(tl), _p(rh),
+                                  C.c_double(atol), C.c_double(rtol), _p(xend), _p(status), C.c_int(nthreads))
+    return xend, status
 
 
 def indirect_prop_jac(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-13, rtol=1e-13, controller=0, nthreads=1):

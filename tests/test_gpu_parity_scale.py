@@ -1,0 +1,113 @@
+"""GPU: parity at the BASELINE config sizes against the oracle itself (not only oracle-free properties).
+
+  * config 3: all 65,536 direct-7 segments vs the oracle's variational Jacobian of the same discrete map;
+  * config 4: 65,536-segment samples of each sub-batch (p=2 / 10 N; p=1 / 0.05 N / rho=1; rho=1e-2), K3 (defect + STM) vs the
+    oracle's dual numbers through the same controller, and K3 and K4 (defect only) vs an 80-bit long-double propagation at
+    1e-17 -- the "truth" both 1e-13 runs are judged against;
+  * rho = 1e-3 and 1e-4 on a converged bang-bang trajectory (tests/golden/bangbang_v1.json), the regime of the demo's
+    continuation target (CRTBP_Multishoot_indirect_demo.jl:276-281).
+
+Tolerances (BASELINE.json north_star): end states 1e-10, STM entries 1e-8, relative to max(1, scale).  The worst segment of every
+case is written to gpurun_out/parity_scale.json (copied to profiles/ per round).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from lowthrustopt_b200 import capi, synthetic as S
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+TOL_STATE, TOL_JAC = 1e-10, 1e-8
+REPORT = {}
+
+
+def _note(key, **kw):
+    REPORT[key] = {k: (float(v) if isinstance(v, (float, np.floating)) else int(v) if isinstance(v, (int, np.integer)) else v) for k, v in kw.items()}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_scale.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+
+
+def test_direct_config3_every_segment_vs_oracle(lto, oracle):
+    n = 65536
+    b = S.direct_batch(n, nstate=7)                       # the bench's default batch (seed 20180001)
+    r = lto.direct(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nsteps=10)
+    do, eo, Jo, so = oracle.direct_jac_var(b["Xa"], b["Xb"], b["ua"], b["ub"], b["ta"], b["tb"], nthreads=oracle.num_threads())
+    xs = np.maximum(1.0, np.maximum(np.abs(b["Xa"]), np.abs(b["Xb"])))
+    ed = (np.abs(r["defect"] - do) / xs).max(axis=1)
+    ej = (np.abs(r["jac"].transpose(0, 2, 1) - Jo) / np.maximum(1.0, np.abs(Jo))).reshape(n, -1).max(axis=1)
+    _note("direct7_fixed_65536", defect_max=ed.max(), defect_argmax=int(ed.argmax()), jac_max=ej.max(), jac_argmax=int(ej.argmax()),
+          errors_max=np.abs(r["errors"] - eo).max())
+    assert np.all(r["status"] == 0) and np.all(so == 0)
+    assert ed.max() < 1e-13 and ej.max() < 1e-12          # same discrete map: far inside 1e-10 / 1e-8
+
+
+CONFIG4 = [("p2_10N", dict(p=2.0, rho=1.0, thrustLimit=10.0)), ("p1_rho1", dict(p=1.0, rho=1.0, thrustLimit=0.05)),
+           ("p1_rho1e-2", dict(p=1.0, rho=1e-2, thrustLimit=0.05))]
+
+
+@pytest.mark.parametrize("name,law", CONFIG4)
+@pytest.mark.parametrize("nd,n", [(12, 65536), (14, 16384)])
+def test_indirect_config4_sample_vs_oracle_and_truth(nd, n, name, law, lto, oracle):
+    b = S.indirect_batch(n, ndim=nd)                      # the bench's batch (seed 20180002), first n segments' worth
+    p = capi.indirect_params(**law)
+    ip = oracle.iparams(law["thrustLimit"], p=law["p"], rho=law["rho"])
+    nth = oracle.num_threads()
+    r = lto.indirect(b["x0"], b["t0"], b["t1"], params=p)                       # K3 / K3-14: defect + STM, joint step control
+    r0 = lto.indirect(b["x0"], b["t0"], b["t1"], params=p, jac=False)            # K4: state-only step control
+    xo, Po, so, nao, nto = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip, nthreads=nth)
+    xt, st = oracle.indirect_prop_ld(b["x0"], b["t0"], b["t1"], ip, nthreads=nth)  # long double, 1e-17
+    assert np.all(r["status"] == 0) and np.all(r0["status"] == 0) and np.all(so == 0) and np.all(st == 0)
+    sx = np.maximum(1.0, np.abs(xt))
+    e3o = (np.abs(r["defect"] - xo) / sx).max(axis=1)
+    e3t = (np.abs(r["defect"] - xt) / sx).max(axis=1)
+    e4t = (np.abs(r0["defect"] - xt) / sx).max(axis=1)
+    e34 = (np.abs(r0["defect"] - r["defect"]) / sx).max(axis=1)
+    eot = (np.abs(xo - xt) / sx).max(axis=1)
+    sp = np.maximum(1.0, np.abs(Po).max(axis=(1, 2)))
+    ep = np.abs(r["phi"].transpose(0, 2, 1) - Po).reshape(n, -1).max(axis=1) / sp
+    lv = slice(9, 12) if nd == 12 else slice(10, 13)
+    lvmin = np.minimum(np.linalg.norm(b["x0"][:, lv], axis=1), np.linalg.norm(xt[:, lv], axis=1))
+    w = int(e4t.argmax())
+    _note("indirect%d_%s_%d" % (nd, name, n), K3_vs_oracle_state=e3o.max(), K3_vs_truth_state=e3t.max(), K4_vs_truth_state=e4t.max(),
+          K3_vs_K4_state=e34.max(), oracle_vs_truth_state=eot.max(), K3_vs_oracle_stm=ep.max(), K4_worst_segment=w, K4_worst_lv_norm=lvmin[w],
+          attempts_K3=float(r["nsteps"][:, 1].mean()), attempts_K4=float(r0["nsteps"][:, 1].mean()), attempts_oracle=float(nto.mean()))
+    assert e3o.max() < TOL_STATE and ep.max() < TOL_JAC
+    assert e3t.max() < TOL_STATE and e4t.max() < TOL_STATE and e34.max() < TOL_STATE
+
+
+def _bangbang(rho_key, copies, rng):
+    with open(os.path.join(ROOT, "tests", "golden", "bangbang_v1.json")) as f:
+        g = json.load(f)
+    XC = np.array(g["XC_nodes"][rho_key]); t = np.array(g["t_TU"])
+    x0 = np.tile(XC[:-1], (copies, 1)); t0 = np.tile(t[:-1], copies); t1 = np.tile(t[1:], copies)
+    x0[29:] += 1e-4 * rng.standard_normal(x0[29:].shape)            # the converged segments themselves + perturbed copies
+    return x0, t0, t1
+
+
+@pytest.mark.parametrize("rho", [1e-3, 1e-4])
+def test_indirect_bangbang_small_rho_vs_oracle(rho, lto, oracle):
+    """Segments of the converged rho = 1e-4 trajectory cross the thrust switches (|lv| = 1): with rho = 1e-3 / 1e-4 the tanh law is
+    nearly discontinuous there, which is what stresses the controller, the clamped exp and the work queue (4-67 accepted steps per
+    segment)."""
+    x0, t0, t1 = _bangbang("0.0001", 12, np.random.default_rng(5))
+    law = dict(p=1.0, rho=rho, thrustLimit=0.05)
+    p = capi.indirect_params(**law)
+    ip = oracle.iparams(0.05, p=1.0, rho=rho)
+    r = lto.indirect(x0, t0, t1, params=p)
+    r0 = lto.indirect(x0, t0, t1, params=p, jac=False)
+    xo, Po, so, nao, nto = oracle.indirect_prop_jac(x0, t0, t1, ip, nthreads=oracle.num_threads())
+    xs, ss, nas, nts = oracle.indirect_prop(x0, t0, t1, ip, nthreads=oracle.num_threads())
+    assert np.all(r["status"] == 0) and np.all(r0["status"] == 0) and np.all(so == 0)
+    sx = np.maximum(1.0, np.abs(xo))
+    sp = np.maximum(1.0, np.abs(Po).max(axis=(1, 2)))
+    ex = (np.abs(r["defect"] - xo) / sx).max()
+    e0 = (np.abs(r0["defect"] - xs) / sx).max()
+    ep = (np.abs(r["phi"].transpose(0, 2, 1) - Po).reshape(len(t0), -1).max(axis=1) / sp).max()
+    _note("bangbang_rho%g" % rho, K3_vs_oracle_state=ex, K4_vs_oracle_state=e0, K3_vs_oracle_stm=ep, accepted_max=int(r["nsteps"][:, 0].max()),
+          accepted_min=int(r["nsteps"][:, 0].min()), attempts_mean=float(r["nsteps"][:, 1].mean()), phi_max=float(np.abs(Po).max()))
+    assert ex < TOL_STATE and e0 < TOL_STATE and ep < TOL_JAC
+    assert r["nsteps"][:, 0].max() >= 15                          # the switches are really in there

@@ -70,13 +70,20 @@ def test_indirect_demo_gpu_vs_oracle(backends):
         XC, d, st = S.multiShoot_CRTBP_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 0.05, False, False, 30, 1.0, 1.0, backend=be)
         hist.append(st); Xp1 = XC.copy()
         XC, d, st = S.reduceFuel_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 0.05, 1.0, 1e-2, backend=be)
+        hist.append(st); Xr2 = XC.copy(); d2 = np.abs(d).max()
+        # ... and on to the demo's own target rho = 1e-4 (CRTBP_Multishoot_indirect_demo.jl:276-281): bang-bang control
+        XC, d, st = S.reduceFuel_indirect(XC, t_TU, MU, DU, TU, 30, 1e3, 0.05, 1e-2, 1e-4, backend=be)
         hist.append(st)
-        res[name] = (hist, Xp2, Xp1, XC, np.abs(d).max())
-    assert res["gpu"][0] == res["cpu"][0] == [1, 0, 0, 0]
+        res[name] = (hist, Xp2, Xp1, Xr2, d2, XC, np.abs(d).max())
+    assert res["gpu"][0] == res["cpu"][0] == [1, 0, 0, 0, 0]
     assert np.abs(res["gpu"][1] - res["cpu"][1]).max() < TOL_TRAJ               # p = 2 solution
     assert np.abs(res["gpu"][2] - res["cpu"][2]).max() < TOL_TRAJ               # p = 1, rho = 1
     assert np.abs(res["gpu"][3] - res["cpu"][3]).max() < TOL_TRAJ               # rho-continuation to 1e-2
     assert res["gpu"][4] < 1e-10                                                # converged to the reference's threshold (:280)
+    assert np.abs(res["gpu"][5] - res["cpu"][5]).max() < TOL_TRAJ               # rho-continuation to 1e-4
+    assert res["gpu"][6] < 1e-10
+    lv = np.linalg.norm(res["gpu"][5][9:12], axis=0)
+    assert (lv > 1.0).any() and (lv < 1.0).any()                                # thrust and coast arcs both present
 
 
 def test_line_search_batch_equals_sequential(backends):

@@ -174,3 +174,25 @@ def test_densify_and_jacobi_constant(demo):
     D2, _ = S.densify(XC2, t_TU, params, 56, backend=be)
     assert np.array_equal(D2[:, :20], XC_dense[:, :20]) and np.array_equal(D2[:, 20], XC2[:, 4]) and np.abs(D2[0, 21] - XC_dense[0, 21]) > 1e-4
     assert np.array_equal(D2[:, 25:], XC_dense[:, 25:])                     # the end column comes from the last segment's propagation
+
+
+def test_bangbang_fixture_is_a_converged_rho_1e4_solution(oracle):
+    """tests/golden/bangbang_v1.json (made by make_bangbang.py) holds the demo's continuation down to the reference's target
+    rho = 1e-4 (CRTBP_Multishoot_indirect_demo.jl:276-281): each stored trajectory satisfies its own defect constraints to the
+    reference's threshold (multiShoot_CRTBP_indirect.jl:280) under the oracle, and the last one is bang-bang."""
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bangbang_v1.json")) as f:
+        g = json.load(f)
+    t = np.array(g["t_TU"])
+    be = OracleBackend()
+    for key, rho in (("0.01", 1e-2), ("0.001", 1e-3), ("0.0001", 1e-4)):
+        XC = np.array(g["XC_nodes"][key])
+        d = be.indirect_defect(XC[None], t[None], (MU, DU, TU, g["thrustLimit"], g["mass"], 1.0, g["p"], rho))
+        assert np.abs(d).max() < 1e-10, (key, np.abs(d).max())
+    lv = np.linalg.norm(XC[:, 9:12], axis=1)
+    assert (lv > 1.0).any() and (lv < 1.0).any()
+    # the long-double truth sees the same defects to 1e-8: what the 1e-13 state-only controller (robust estimate + sharp-law
+    # safeguard) leaves at rho = 1e-4
+    xt, st = oracle.indirect_prop_ld(XC[:-1], t[:-1], t[1:], oracle.iparams(g["thrustLimit"], p=1.0, rho=1e-4), atol=1e-18, rtol=1e-18,
+                                     nthreads=oracle.num_threads())
+    assert np.abs(xt - XC[1:]).max() < 5e-8
