@@ -96,3 +96,28 @@ def test_kernel_arithmetic_14_matches_symbolic_golden(oracle, hostcheck, golden1
         if "phi_richardson" in g:
             P = np.array(g["phi_richardson"])
             assert np.abs(Phi.T - P).max() < 5e-8 * max(1.0, np.abs(P).max() / 10)
+
+
+@pytest.mark.parametrize("law", [dict(p=1.0, rho=1.0, thrustLimit=0.05), dict(p=2.0, rho=1.0, thrustLimit=10.0), dict(p=1.0, rho=1e-2, thrustLimit=0.05),
+                                 dict(p=0.0, rho=1.0, thrustLimit=0.05), dict(p=2.0, rho=1.0, thrustLimit=1e-3)])
+@pytest.mark.parametrize("td", [1.0, -1.0])
+def test_half_column_formulation_matches_dual_numbers(law, td, oracle, hostcheck):
+    """lto_hc_math.cuh -- the arithmetic of the half-column kernel K3 (second-order variables (r, v, lv, lv'), every STM column as a
+    lane pair in Nystrom form) replayed thread by thread on the host -- against the oracle's dual numbers through RKF7(8):
+    end states 1e-11, STM 1e-10 relative, about the same number of accepted steps (the initial step is taken over the state alone)."""
+    from lowthrustopt_b200 import synthetic as S
+    b = S.indirect_batch(24, ndim=12, seed=31)
+    b["x0"][::3, 9:12] *= 8.0
+    ip = oracle.iparams(law["thrustLimit"], td=td, p=law["p"], rho=law["rho"])
+    xo, Po, so, nao, nto = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip)
+    xs, ss, nas, nts = oracle.indirect_prop(b["x0"], b["t0"], b["t1"], ip)
+    hostcheck.hc_halfcol_seg12.restype = C.c_int
+    for s in range(24):
+        for joint, xr, nar in ((1, xo[s], nao[s]), (0, xs[s], nas[s])):
+            xe = np.zeros(12); Phi = np.zeros((12, 12)); na = C.c_int(); nt = C.c_int()
+            st = hostcheck.hc_halfcol_seg12(ptr(b["x0"][s]), C.c_double(b["t0"][s]), C.c_double(b["t1"][s]), C.c_double(1e-13), C.c_double(1e-13),
+                                            joint, ptr(ip), ptr(xe), ptr(Phi), C.byref(na), C.byref(nt))
+            assert st == 0
+            assert (np.abs(xe - xr) / np.maximum(1.0, np.abs(xr))).max() < 1e-11, (s, joint)
+            assert abs(na.value - nar) <= max(2, nar // 8)
+            assert np.abs(Phi.T - Po[s]).max() < (1e-10 if joint else 1e-8) * max(1.0, np.abs(Po[s]).max()), (s, joint)
