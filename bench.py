@@ -27,12 +27,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic FLOPs per unit (sparsity-exploiting minimal formulation; DESIGN.md "Measurement")
-FLOPS_PER_SEG = {"direct7": 284040.0, "direct6": 217836.0}
-# ndim 14, minimal formulation: the STM column d/d(lm0) is the constant e_14 (lm enters no right-hand side), so 13
-# columns are integrated: 13 stages x (240 state + 13 columns x 82) = 16,978; RK combinations over 14 + 13*14 = 196 components
-# 2*75*196 + error 10*196 = 31,360, minus the beta-combinations of the 14 lm components (pure quadratures: 14 x 134) = 29,484
-FLOPS_PER_STEP_INDIRECT = {12: 39468.0, 14: 46462.0}
+# Algorithmic FLOPs per unit: profiles/flops_per_unit.json, written by tools/flopcount/count.py -- the kernels' own host-device
+# arithmetic compiled with a FLOP-counting scalar; `used` = min(survey-time figure, every counted formulation).
+def _flop_table():
+    with open(os.path.join(ROOT, "profiles", "flops_per_unit.json")) as f:
+        return json.load(f)
+
+
+FLOP_TABLE = _flop_table()
+FLOPS_PER_SEG = {"direct7": float(FLOP_TABLE["used"]["direct7_segment"]), "direct6": float(FLOP_TABLE["used"]["direct6_segment"])}
+FLOPS_PER_STEP_INDIRECT = {12: float(FLOP_TABLE["used"]["indirect12_step"]), 14: float(FLOP_TABLE["used"]["indirect14_step"])}
+FLOPS_COUNTED = {"direct7": FLOP_TABLE["counted"]["direct7_segment"]["flops"], "direct6": FLOP_TABLE["counted"]["direct6_segment"]["flops"],
+                 12: min(FLOP_TABLE["counted"]["indirect12_step_first_order"]["flops"], FLOP_TABLE["counted"]["indirect12_step_half_column"]["flops"]),
+                 14: FLOP_TABLE["counted"]["indirect14_step_first_order"]["flops"]}
 # Algorithmic HBM bytes per unit
 BYTES_PER_SEG = {"direct7": 1360.0, "direct6": (2 * 6 + 6 + 2 + 6 + 1 + 6 * 18) * 8.0, 12: 1360.0, 14: 1808.0}
 
@@ -147,6 +154,27 @@ def numa_restore(old):
 
 
 # --------------------------------------------------------------------------- CPU legs (oracle = checker / baseline only)
+def host_threads():
+    """Threads the CPU legs use: every CPU this process may run on.  NOT the OpenMP default -- torch.distributed.run exports
+    OMP_NUM_THREADS=1 into its workers, which silently turned the N > 1 reference arm of round 1 into a 1-thread run; the oracle's
+    entry points take the count explicitly (an `omp parallel for num_threads(n)` clause overrides the environment)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_variational_pass(batch, n, nthreads):
+    """One pass of the SAME MATHS as the GPU path on the host (mode 2): the state and its variational
+    equations in one RKF7(8) integration per leg (dual numbers through ode7_8), instead of the reference's 2(n+3) finite-difference
+    re-propagations.  Direct workloads only -- for the indirect ones the reference algorithm already is this."""
+    from oracle import oracle as O
+    sl = {k: v[:n] for k, v in batch.items()}
+    t = time.perf_counter()
+    O.direct_jac_var(sl["Xa"], sl["Xb"], sl["ua"], sl["ub"], sl["ta"], sl["tb"], nthreads=nthreads)
+    return time.perf_counter() - t
+
+
 def cpu_reference_pass(workload, batch, n, nthreads):
     """One pass of the REFERENCE ALGORITHM on the host: direct = defectCalc + forward-FD jacobianCalc
     (multiShoot_CRTBP_direct.jl:66-143, pert 1e-8, both legs re-propagated per variable); indirect = dual numbers
@@ -169,17 +197,25 @@ def cpu_baseline(workload, batch, sample, seconds=12.0):
     `sample` segments of the same batch."""
     from oracle import oracle as O
     O.build()
-    nthreads = O.num_threads()
+    nthreads = host_threads()
     n = min(sample, len(next(iter(batch.values()))))
     cpu_reference_pass(workload, batch, min(n, 256), nthreads)        # warm the thread pool
     dt, passes = 0.0, 0
     while dt < seconds and passes < 10000:
         dt += cpu_reference_pass(workload, batch, n, nthreads); passes += 1
-    return {"value": n * passes / dt, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
-            "sample": "%d passes over the first %d segments of the same batch, reference algorithm (%s) restated in C++ (oracle/), "
-                      "OpenMP over segments on %d threads, %.1f s"
-                      % (passes, n, "defectCalc + forward-FD jacobianCalc, pert 1e-8" if workload.startswith("direct") else
-                         "dual numbers through the adaptive RK8", nthreads, dt)}
+    out = {"value": n * passes / dt, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
+           "sample": "%d passes over the first %d segments of the same batch, reference algorithm (%s) restated in C++ (oracle/), "
+                     "OpenMP over segments on %d threads, %.1f s"
+                     % (passes, n, "defectCalc + forward-FD jacobianCalc, pert 1e-8" if workload.startswith("direct") else
+                        "dual numbers through the adaptive RK8", nthreads, dt)}
+    if workload.endswith("_fixed"):                                   # equal-algorithm comparison next to the reference-algorithm one
+        dv, pv = 0.0, 0
+        while dv < seconds / 3.0 and pv < 10000:
+            dv += cpu_variational_pass(batch, n, nthreads); pv += 1
+        out["variational"] = {"value": n * pv / dv, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
+                              "sample": "%d passes over the same %d segments, the GPU path's own maths (state + variational equations in one "
+                                        "RKF7(8) integration per leg, dual numbers in the C++ oracle), %.1f s" % (pv, n, dv)}
+    return out
 
 
 def run_reference(args):
@@ -188,7 +224,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     O.build()
-    nthreads = O.num_threads()
+    nthreads = host_threads()
     if args.workload == "continuation_solve":
         from lowthrustopt_b200 import synthetic as S
         c = S.continuation_batch(n_traj=64, n_seg_per_traj=200, ndim=12)
@@ -255,7 +291,23 @@ def dist_setup():
     return world, rank, local
 
 
-def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl):
+def executed_flops(wl, units_per_launch, kernel_ms, peak):
+    """What ncu counted for the dominant kernel of this workload (profiles/executed.json: thread-level DFMA/DMUL/DADD executed per
+    unit and FP64-pipe-active %, from the committed --set full capture of the same build) next to the algorithmic figure: the
+    achieved rate in EXECUTED flops and its fraction of the measured peak.  None when no capture is on file for the workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "executed.json")) as f:
+            e = json.load(f).get(wl)
+    except Exception:
+        e = None
+    if not e:
+        return None
+    ach = e["flops_per_unit"] * units_per_launch / (kernel_ms * 1e-3) / 1e12
+    return {"flops_per_unit": e["flops_per_unit"], "achieved": ach, "frac": ach / (peak / 1e12), "fp64_pipe_active_pct": e.get("fp64_pipe_active_pct"),
+            "source": e.get("source")}
+
+
+def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl, flops_counted=None):
     peak_burst, _ = h.fp64_peak_probe(2048)
     peak_sust, ms_p = h.fp64_peak_probe(200000)
     achieved = flops_unit * units_per_launch / (kernel_ms * 1e-3) / 1e12
@@ -278,6 +330,10 @@ def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl):
                            "burst %.2f; MEASURED_PEAKS.json carries no FP64 figure; spec 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2"
                            % (peak_sust / 1e12, ms_p, peak_burst / 1e12),
             "flops_per_unit": flops_unit, "units_per_launch": units_per_launch, "kernel_ms": kernel_ms,
+            "flops_source": "profiles/flops_per_unit.json (tools/flopcount/count.py: the kernels' host-device arithmetic compiled with a counting "
+                            "scalar); used = min(SURVEY 8(d) figure, every counted formulation)",
+            "flops_per_unit_counted": flops_counted,
+            "executed": executed_flops(wl, units_per_launch, kernel_ms, peak_sust),
             "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": (gbs / hbm) if hbm else None}}
 
 
@@ -455,7 +511,8 @@ def run_sharded(args):
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
-    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, units_per_launch, kernel_ms, BYTES_PER_SEG[nd], "indirect12")
+    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, units_per_launch, kernel_ms, BYTES_PER_SEG[nd], "indirect12",
+                         FLOPS_COUNTED[nd] * attempted)
     roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
     roof["kernel"] = "k_indirect_cw (the STM pass); launches of %d segments" % units_per_launch
     gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + (2 * n_seg * (nd * 8 + 12) + n_units * N_ALPHA * 12 if passes_def else 0)
@@ -579,7 +636,7 @@ def cpu_solve_baseline(XC, tt, n_traj, seconds):
     import scipy.sparse.linalg as spl
     from oracle import oracle as O
     O.build()
-    nthreads = O.num_threads()
+    nthreads = host_threads()
     ip = O.iparams(10.0, p=2.0, rho=1.0)
     N = XC.shape[1]; m = 12
 
@@ -705,7 +762,7 @@ def run_solve(args):
     nwt_ms = timed(lambda: h.indirect_newton_dev(T, n_nodes, 0, d_phi.data_ptr(), d_def.data_ptr(), d_upd.data_ptr()))
     nst = d_ns.cpu().numpy()
     attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
-    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, T * spu, stm_ms, BYTES_PER_SEG[nd], "indirect12")
+    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, T * spu, stm_ms, BYTES_PER_SEG[nd], "indirect12", FLOPS_COUNTED[nd] * attempted)
     roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
     roof["kernel"] = "k_indirect_cw (the STM pass of every iteration); launches of %d segments" % (T * spu)
     # Newton update: HBM-side accounting (factor rows written once, read once; Phi and defects read once; update written once)
@@ -790,6 +847,7 @@ def run_ours(args):
         h2d = sum(v.nbytes for v in batch.values())
         d2h = sum(b.array.nbytes for b in pin_out.values())
         flops_unit = FLOPS_PER_SEG["direct7" if ns == 7 else "direct6"]
+        flops_counted = FLOPS_COUNTED["direct7" if ns == 7 else "direct6"]
         bytes_unit = BYTES_PER_SEG["direct7" if ns == 7 else "direct6"]
         attempted = None
     else:
@@ -819,6 +877,7 @@ def run_ours(args):
         h2d = sum(v.nbytes for v in batch.values())
         d2h = n_seg * (nd * 8 + 4 + 8 + nd * nd * 8)
         flops_unit = None
+        flops_counted = None
         bytes_unit = BYTES_PER_SEG[nd]
         attempted = None
     numa_restore(numa_old)                                               # the CPU baseline below uses every host thread again
@@ -858,6 +917,7 @@ def run_ours(args):
         nst = d_ns.cpu().numpy()
         attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
         flops_unit = FLOPS_PER_STEP_INDIRECT[nd] * attempted
+        flops_counted = FLOPS_COUNTED[nd] * attempted
     # ---- e2e through the host-buffer C ABI
     for _ in range(2):
         step_e2e()
@@ -874,7 +934,7 @@ def run_ours(args):
     clocks = sampler.stop()
     # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
     per_gpu_ms = float(np.mean(times))
-    roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl)
+    roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl, flops_counted)
     if wl.endswith("adaptive"):
         # the direct entry points do not return step counts, so the algorithmic FLOPs of an ADAPTIVE pass are not known here
         roof["achieved"] = None; roof["frac"] = None; roof["flops_per_unit"] = None

@@ -1,5 +1,4 @@
 # UNEXECUTED in this repository's environment (no Julia in the image); kept in sync with INTEGRATION.md section 2.
-using LinearAlgebra
 # lto_b200.jl -- ccall binding of liblto_b200.so (include/lto_b200.h)
 module LtoB200
 const lib = get(ENV, "LTO_B200_LIB", "liblto_b200.so")
@@ -75,7 +74,7 @@ function jacobianCalc_indirect(XC_all, t_TU, nstate, n_nodes, params)
     for i = 1:(n_nodes - 1)                                                               # :128-138
         r = ((i - 1) * m + 1):(i * m)
         Jac_full[r, ((i - 1) * m + 1):(i * m)] = phi[:, :, i]
-        Jac_full[r, (i * m + 1):((i + 1) * m)] = -Matrix(1.0I, m, m)
+        for k = 1:m; Jac_full[r[k], i * m + k] = -1.0; end                                # hcat(Phi_i, -I) without LinearAlgebra's `I`
     end
     Jac_full[:, 1:nstate] .= 0.0; Jac_full[:, (end - 2 * nstate + 1):(end - nstate)] .= 0.0   # :141-142
     Jac_full

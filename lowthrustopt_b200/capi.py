@@ -157,6 +157,36 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _shaped(name, a, shape):
+    """An input array of exactly `shape` (C-contiguous float64); the C side reads prod(shape) doubles from it unchecked."""
+    a = _f64(a)
+    if a.shape != tuple(shape):
+        raise ValueError("%s must have shape %s (got %s)" % (name, tuple(shape), a.shape))
+    return a
+
+
+def _per_unit(name, a, n):
+    """Optional per-segment / per-trajectory parameter array: None, a scalar (broadcast) or exactly (n,) values."""
+    if a is None:
+        return None
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 0:
+        return np.full(n, float(a))
+    if a.shape != (n,):
+        raise ValueError("%s must be a scalar or have shape (%d,) (got %s)" % (name, n, a.shape))
+    return np.ascontiguousarray(a)
+
+
+def _out(o, key, shape, dtype=np.float64):
+    """A caller-supplied output array (e.g. pinned memory) or a fresh one; the library writes prod(shape) items into it."""
+    a = o.get(key)
+    if a is None:
+        return np.empty(shape, dtype=dtype)
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or a.shape != tuple(shape) or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+        raise ValueError("out[%r] must be a writeable C-contiguous %s array of shape %s" % (key, np.dtype(dtype).name, tuple(shape)))
+    return a
+
+
 class PinnedBuffer:
     """Pinned host memory from lto_host_alloc, viewed as a numpy array."""
 
@@ -250,16 +280,18 @@ class Handle:
         """pairs form.  Xa, Xb: (n_seg, nstate); ua, ub: (n_seg, 3); ta, tb: (n_seg,).
         Returns dict(defect (n_seg,nstate), errors, status, jac (n_seg, 2(nstate+3), nstate) = column-major blocks)."""
         p = params or direct_params()
-        Xa, Xb, ua, ub, ta, tb = map(_f64, (Xa, Xb, ua, ub, ta, tb))
-        n_seg, ns = Xa.shape if Xa.ndim == 2 else (0, 0)
+        Xa = _f64(Xa)
         if Xa.ndim != 2:
             raise ValueError("Xa must be (n_seg, nstate)")
+        n_seg, ns = Xa.shape
+        Xb = _shaped("Xb", Xb, (n_seg, ns)); ua = _shaped("ua", ua, (n_seg, 3)); ub = _shaped("ub", ub, (n_seg, 3))
+        ta = _shaped("ta", ta, (n_seg,)); tb = _shaped("tb", tb, (n_seg,))
         nv = 2 * (ns + 3)
         o = out or {}
-        defect = o.get("defect", np.empty((n_seg, ns))); errors = o.get("errors", np.empty(n_seg))
-        status = o.get("status", np.empty(n_seg, dtype=np.int32))
+        defect = _out(o, "defect", (n_seg, ns)); errors = _out(o, "errors", (n_seg,))
+        status = _out(o, "status", (n_seg,), np.int32)
         if jac:
-            J = o.get("jac", np.empty((n_seg, nv, ns)))
+            J = _out(o, "jac", (n_seg, nv, ns))
             self._ck(lib().lto_direct_defect_jac(self._h, C.addressof(p), n_seg, ns, int(nsteps), _ptr(Xa), _ptr(Xb), _ptr(ua),
                                                  _ptr(ub), _ptr(ta), _ptr(tb), _ptr(defect), _ptr(errors), _ptr(status), _ptr(J)))
             return dict(defect=defect, errors=errors, status=status, jac=J)
@@ -273,7 +305,10 @@ class Handle:
         X_all, u_all, t_TU = map(_f64, (X_all, u_all, t_TU))
         if X_all.ndim == 2:
             X_all, u_all, t_TU = X_all[None], u_all[None], t_TU[None]
+        if X_all.ndim != 3:
+            raise ValueError("X_all must be (n_traj, n_nodes, nstate)")
         n_traj, n_nodes, ns = X_all.shape
+        u_all = _shaped("u_all", u_all, (n_traj, n_nodes, 3)); t_TU = _shaped("t_TU", t_TU, (n_traj, n_nodes))
         n_seg = n_traj * (n_nodes - 1); nv = 2 * (ns + 3)
         defect = np.empty((n_seg, ns)); errors = np.empty(n_seg); status = np.empty(n_seg, dtype=np.int32)
         if jac:
@@ -290,18 +325,19 @@ class Handle:
         """pairs form.  x0: (n_seg, ndim).  Returns dict(defect, status, nsteps (n_seg,2), phi (n_seg, ndim, ndim) column-major).
         `out` may supply preallocated (e.g. pinned) arrays under the same keys."""
         p = params or indirect_params()
-        x0, t0, t1 = map(_f64, (x0, t0, t1))
+        x0 = _f64(x0)
         if x0.ndim != 2:
             raise ValueError("x0 must be (n_seg, ndim)")
         n_seg, nd = x0.shape
-        xt = None if x_target is None else _f64(x_target)
-        tl = None if thrustLimit is None else _f64(thrustLimit)
-        rh = None if rho is None else _f64(rho)
+        t0 = _shaped("t0", t0, (n_seg,)); t1 = _shaped("t1", t1, (n_seg,))
+        xt = None if x_target is None else _shaped("x_target", x_target, (n_seg, nd))
+        tl = _per_unit("thrustLimit", thrustLimit, n_seg)
+        rh = _per_unit("rho", rho, n_seg)
         o = out or {}
-        defect = o.get("defect", np.empty((n_seg, nd))); status = o.get("status", np.empty(n_seg, dtype=np.int32))
-        nst = o.get("nsteps", np.empty((n_seg, 2), dtype=np.int32))
+        defect = _out(o, "defect", (n_seg, nd)); status = _out(o, "status", (n_seg,), np.int32)
+        nst = _out(o, "nsteps", (n_seg, 2), np.int32)
         if jac:
-            phi = o.get("phi", np.empty((n_seg, nd, nd)))
+            phi = _out(o, "phi", (n_seg, nd, nd))
             self._ck(lib().lto_indirect_defect_jac(self._h, C.addressof(p), n_seg, nd, _ptr(x0), _ptr(t0), _ptr(t1), _ptr(xt),
                                                    _ptr(tl), _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst), _ptr(phi)))
             return dict(defect=defect, status=status, nsteps=nst, phi=phi)
@@ -315,10 +351,13 @@ class Handle:
         XC_all, t_TU = _f64(XC_all), _f64(t_TU)
         if XC_all.ndim == 2:
             XC_all, t_TU = XC_all[None], t_TU[None]
+        if XC_all.ndim != 3:
+            raise ValueError("XC_all must be (n_traj, n_nodes, ndim)")
         n_traj, n_nodes, nd = XC_all.shape
+        t_TU = _shaped("t_TU", t_TU, (n_traj, n_nodes))
         n_seg = n_traj * (n_nodes - 1)
-        tl = None if thrustLimit is None else _f64(thrustLimit)
-        rh = None if rho is None else _f64(rho)
+        tl = _per_unit("thrustLimit", thrustLimit, n_traj)
+        rh = _per_unit("rho", rho, n_traj)
         defect = np.empty((n_seg, nd)); status = np.empty(n_seg, dtype=np.int32); nst = np.empty((n_seg, 2), dtype=np.int32)
         if jac:
             phi = np.empty((n_seg, nd, nd))
@@ -422,21 +461,14 @@ class Handle:
         n_traj, n_nodes, nd = XC.shape
         if nd != 12:
             raise ValueError("the reference's indirect solver is 12-dimensional (multiShoot_CRTBP_indirect.jl:258)")
-        tl = None if thrustLimit is None else _f64(thrustLimit)
-        rh = None if rho is None else _f64(rho)
+        t_TU = _shaped("t_TU", t_TU, (n_traj, n_nodes))
+        tl = _per_unit("thrustLimit", thrustLimit, n_traj)
+        rh = _per_unit("rho", rho, n_traj)
         o = out or {}
-        defect = o.get("defect", None)
-        if defect is None:
-            defect = np.empty((n_traj, n_nodes - 1, nd))
-        flag = o.get("status_flag", None)
-        if flag is None:
-            flag = np.empty(n_traj, dtype=np.int32)
-        iters = o.get("iters", None)
-        if iters is None:
-            iters = np.empty(n_traj, dtype=np.int32)
-        er = o.get("er", None)
-        if er is None:
-            er = np.empty(n_traj)
+        defect = _out(o, "defect", (n_traj, n_nodes - 1, nd))
+        flag = _out(o, "status_flag", (n_traj,), np.int32)
+        iters = _out(o, "iters", (n_traj,), np.int32)
+        er = _out(o, "er", (n_traj,))
         self._ck(lib().lto_indirect_solve_batch(self._h, C.addressof(p), n_traj, n_nodes, int(max_iter), int(bool(flag_adjointsOnly)),
                                                 _ptr(XC), _ptr(t_TU), _ptr(tl), _ptr(rh), _ptr(defect), _ptr(flag), _ptr(iters), _ptr(er)))
         return dict(XC_all=XC, defect=defect, status_flag=flag, iters=iters, er=er)

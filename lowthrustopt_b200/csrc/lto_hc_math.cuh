@@ -1,6 +1,6 @@
 // lto_hc_math.cuh -- per-thread arithmetic of the "half-column" throughput kernel of the indirect method
 // (lto_indirect_hc.cu; K3, ndim = 12).  __host__ __device__, so that tests/native/lto_hostcheck.cpp runs the very same
-// arithmetic on the CPU against the oracle's dual numbers (tests/test_host_math.py) before any GPU time is spent.
+// arithmetic on the CPU against the CPU checker's dual numbers (tests/test_host_math.py) before any GPU time is spent.
 //
 // Formulation.  CRTBP_stateCostate_deriv! (src/CRTBP_stateCostate_deriv.jl:78-88) is
 //     r'  = v                       v'  = grad(Omega)(r) + C v - uon(|lv|) lv

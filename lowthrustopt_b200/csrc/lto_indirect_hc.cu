@@ -9,7 +9,7 @@
 // second-order variables (r, v, lv, lv') (lto_hc_math.cuh): every STM column splits into two 3-vector second-order halves of the
 // SAME shape, each advanced in Nystrom form with 39 stored doubles.  One thread = one half-column:
 //   * ~150 registers -> 12 warps per SM, three per sub-partition; all four FP64 pipes carry column work;
-//   * setmaxnreg moves registers from the 8 column warps (152) to the state warps (208), which keep their 78 stage derivatives
+//   * setmaxnreg moves registers from the 8 column warps (128) to the state warps (248), which keep their 78 stage derivatives
 //     in registers;
 //   * 3 tiles of 32 segment slots in flight (stage records 3 x 59.9 KB of shared memory), one state warp per tile, so a tile's
 //     next attempt has two column visits of the other tiles to be ready: the state warp's dependent chain is off the critical
@@ -47,7 +47,7 @@ constexpr int NTHREADS = 32 * NW;
 constexpr int NTASK = 24;         // warp-tasks per tile visit: 6 column pairs x 4 slot octets
 constexpr int NPH = NTASK / NCW;  // tasks per column warp and tile visit
 constexpr int NC2 = 9;            // double2 per stage record: U[6] W[6] G[6]
-constexpr int REG_COL = 152, REG_STATE = 208;   // setmaxnreg: 2 x 152 + 208 = 512 per sub-partition lane
+constexpr int REG_COL = 128, REG_STATE = 248;   // setmaxnreg: launched at 168; the 8 column warps release 8 x 40 registers per lane, the 4 warps of the state group claim 4 x 80 -- only what was released inside the CTA can be claimed (a larger claim spins forever)
 
 enum { F_STORE = 2, F_RESET = 4, F_ACTIVE = 8, F_PAR = 16 };
 

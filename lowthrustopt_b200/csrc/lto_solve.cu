@@ -90,7 +90,9 @@ __global__ void k_tile(const double* __restrict__ src, double* __restrict__ dst,
 
 // end of an iteration (:328-341): er = norm(defect[:], Inf); iterCount += 1; abort above 1e3; loop condition er > 1e-10.
 // Rows are the WORK SET (trajectories still iterating); orig[row] is the trajectory's index in the caller's arrays.
-//   flag: 0 converged / still iterating, 1 gave up (maxIter or abort)
+//   flag: 0 converged / still iterating, 1 gave up (maxIter or abort), 2 the defects went NaN (the reference's evident intent at
+//   :339-341; its own test looks at XC_all[1,1] only, a pinned entry that can never be NaN -- a latent bug that is NOT mirrored:
+//   a NaN trajectory must not come back as "converged", the continuation driver would walk on from it)
 __global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ active, const int* __restrict__ orig, int* __restrict__ iters,
                            int* __restrict__ flag, double* __restrict__ er_full, unsigned long long* __restrict__ n_active, long long n, int it,
                            int max_iter, double tol = 1e-10, double abort_above = 1e3, int force_first = 0) {
@@ -101,6 +103,7 @@ __global__ void k_iter_end(const double* __restrict__ er, int* __restrict__ acti
     er_full[o] = e;
     if (it > 0) iters[o] = it;
     bool go = e > tol || (force_first && it == 0);        // NaN -> false: the reference's while-condition ends the loop as well
+    if (!(e == e)) flag[o] = 2;
     if (go && !(e <= abort_above) && !(force_first && it == 0)) { go = false; flag[o] = 1; }   // "Not likely to converge. Aborting." (:333-336)
     if (go && it >= max_iter) { go = false; flag[o] = 1; }   // "Reached max iteration count" (:282-286)
     active[j] = go ? 1 : 0;
@@ -634,7 +637,9 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
     if (status_flag) {
         for (long long j = 0; j < T; ++j) {
             int f = flag[(size_t)j];
-            if (std::isnan(XC_all[(size_t)j * N * ND])) f = 2;                                 // :339-341
+            if (f != 2)                                                                        // :339-341, over the whole trajectory
+                for (long long i = 0; i < (long long)N * ND; ++i)
+                    if (!std::isfinite(XC_all[(size_t)j * N * ND + i])) { f = 2; break; }
             status_flag[j] = f;
         }
     }

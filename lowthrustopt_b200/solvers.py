@@ -459,7 +459,9 @@ def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLi
             iterCount += 100
             if np.isnan(er):
                 break
-    if np.isnan(XC_all[0, 0]):                                                                            # :339-341
+    # :339-341 tests XC_all[1,1] only -- a pinned entry whose update is exactly 0, so it can never be NaN (a latent bug of the
+    # reference, not mirrored): a trajectory whose defects or nodes went non-finite is reported as such, never as "converged"
+    if np.isnan(er) or not np.all(np.isfinite(XC_all)):
         status_flag = 2
     return XC_all, defect, status_flag
 

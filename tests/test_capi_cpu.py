@@ -140,3 +140,20 @@ def test_library_carries_sm100a_kernels_only(capi):
         assert kern in usage, kern
     sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN3lto3icw16k_indirect_stateENS_12IndirectArgsE", so], capture_output=True, text=True).stdout
     assert sass.count("DFMA") > 500
+
+
+def test_wrapper_argument_validation():
+    """the ctypes wrappers check every auxiliary array before the C side reads n doubles from it -- a scalar
+    thrustLimit / rho is broadcast, wrong shapes and unsuitable `out` arrays are ValueErrors (no GPU needed: validation comes first)."""
+    from lowthrustopt_b200 import capi
+    assert np.array_equal(capi._per_unit("rho", 0.5, 3), [0.5, 0.5, 0.5]) and capi._per_unit("rho", None, 3) is None
+    with pytest.raises(ValueError):
+        capi._per_unit("thrustLimit", np.ones(2), 3)
+    with pytest.raises(ValueError):
+        capi._shaped("t0", np.zeros(4), (5,))
+    o = {"phi": np.zeros((4, 12, 12), dtype=np.float32)}
+    with pytest.raises(ValueError):
+        capi._out(o, "phi", (4, 12, 12))
+    with pytest.raises(ValueError):
+        capi._out({"phi": np.zeros((12, 12, 4)).T}, "phi", (4, 12, 12))          # right shape, not C-contiguous
+    assert capi._out({}, "status", (4,), np.int32).dtype == np.int32

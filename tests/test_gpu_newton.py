@@ -194,3 +194,21 @@ def test_solve_batch_edge_cases(lto):
     bad = c["XC_all"].copy(); bad[1, 0, 0] = np.nan
     r = lto.indirect_solve_batch(bad, c["t_TU"], params=p, max_iter=5)
     assert r["status_flag"][1] == 2 and r["status_flag"][0] == 0 and r["status_flag"][2] == 0   # isnan(XC_all[1]) -> 2 (:339-341)
+
+
+def test_nan_inside_a_batch_is_never_reported_as_converged(lto):
+    """the reference tests XC_all[1,1] only (:339), a pinned entry that the update never touches, so a trajectory whose
+    interior went NaN came back with status_flag 0 and the continuation driver walked on from it.  Here: a NaN in an interior
+    (non-pinned) costate of one trajectory of a batch -> that trajectory reports 2, its neighbours converge, and the batched
+    continuation ladder does not accept it."""
+    p = capi.indirect_params(p=2.0, thrustLimit=10.0)
+    c = synthetic.continuation_batch(n_traj=4, n_seg_per_traj=29, ndim=12)
+    XC = c["XC_all"].copy(); XC[:, :, 6:] *= 0.1
+    XC[2, 7, 9] = np.nan                                                         # interior node, costate component
+    r = lto.indirect_solve_batch(XC, c["t_TU"], params=p, max_iter=8)
+    assert r["status_flag"][2] == 2 and np.all(r["status_flag"][[0, 1, 3]] == 0)
+    assert not np.isnan(XC[2, 0, 0])                                             # the entry the reference looks at is fine
+    # host mirror, same input
+    out, d, st = S.multiShoot_CRTBP_indirect(XC[2].T.copy(), c["t_TU"][2], MU, DU, TU, 30, 1e3, 10.0, False, False, 8, 2.0, 1.0,
+                                             backend=S.GpuBackend(handle=lto))
+    assert st == 2

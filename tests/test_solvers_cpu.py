@@ -148,6 +148,10 @@ def test_invalid_p_and_nan_status():
     XC[:, 0] = np.nan
     out, d, st = S.multiShoot_CRTBP_indirect(XC, np.array([0.0, 0.1, 0.2]), MU, DU, TU, 3, 1e3, 0.05, False, False, 3, 1.0, 1.0, backend=be)
     assert st == 2                                                              # isnan(XC_all[1]) -> status_flag 2 (:339-341)
+    # a NaN in an interior, non-pinned entry: XC_all[1,1] stays finite, which the reference would report as "converged" 
+    XC = np.zeros((12, 4)); XC[0] = 1.0; XC[9] = 0.1; XC[10, 2] = np.nan
+    out, d, st = S.multiShoot_CRTBP_indirect(XC, np.array([0.0, 0.1, 0.2, 0.3]), MU, DU, TU, 4, 1e3, 0.05, False, False, 3, 1.0, 1.0, backend=be)
+    assert st == 2 and np.isfinite(out[0, 0])
 
 
 def test_densify_and_jacobi_constant(demo):
