@@ -18,7 +18,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "liblto_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-              "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"]
+              "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"] + os.environ.get("LTO_NVCC_EXTRA", "").split()   # (development: -D switches)
 
 
 def _nvcc():

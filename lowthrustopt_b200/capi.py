@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblto_b200.so")
+LIB_PATH = os.environ.get("LTO_B200_LIB") or os.path.join(HERE, "liblto_b200.so")   # LTO_B200_LIB: same override as julia/lto_b200.jl
 
 # src/LowThrustOpt.jl:24-29
 MU = 0.012150585609624037
@@ -270,7 +270,7 @@ class Handle:
         self._ck(lib().lto_fp64_peak_probe(self._h, int(iters), C.byref(f), C.byref(ms)))
         return f.value, ms.value
 
-    def debug_profile(self, n_words=8192):
+    def debug_profile(self, n_words=16384):
         out = np.zeros(n_words, dtype=np.uint64)
         self._ck(lib().lto_debug_profile(self._h, _ptr(out), n_words))
         return out

@@ -60,6 +60,7 @@ int lto_device_count(void) {
 }
 
 int lto_init(int device, lto_handle** out) {
+    LTO_NVTX();
     if (!out) return fail(nullptr, LTO_ERR_ARG, "lto_init: null handle pointer");
     *out = nullptr;
     int n = 0;
@@ -94,6 +95,7 @@ int lto_init(int device, lto_handle** out) {
 }
 
 int lto_init_devices(int n_devices, const int* devices, lto_handle** out) {
+    LTO_NVTX();
     if (!out) return fail(nullptr, LTO_ERR_ARG, "lto_init_devices: null handle pointer");
     *out = nullptr;
     if (n_devices < 1 || n_devices > LTO_MAX_DEVICES || !devices)
@@ -156,6 +158,7 @@ double lto_last_kernel_ms(const lto_handle* h) {
 int lto_n_devices(const lto_handle* h) { return h ? (h->n_child > 0 ? h->n_child : 1) : 0; }
 void* lto_stream(lto_handle* h) { return (h && h->n_child == 0) ? (void*)h->s_compute : nullptr; }
 int lto_sync(lto_handle* h) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     for (int i = 0; i < h->n_child; ++i) { int rc = lto_sync(h->child[i]); if (rc) return fail(h, rc, "%s", h->child[i]->err); }
     if (h->n_child > 0) return LTO_SUCCESS;
@@ -522,16 +525,19 @@ int lto_host_chunk_plan(int method, int n_sm, int64_t n_seg, int n_nodes, int nv
 int lto_direct_defect(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps, const double* Xa,
                       const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,
                       double* defect, double* errors, int32_t* status) {
+    LTO_NVTX();
     return direct_host(h, p, n_seg, 0, 0, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, nullptr, false);
 }
 int lto_direct_defect_jac(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int nstate, int nsteps,
                           const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta,
                           const double* tb, double* defect, double* errors, int32_t* status, double* jac) {
+    LTO_NVTX();
     return direct_host(h, p, n_seg, 0, 0, nstate, nsteps, Xa, Xb, ua, ub, ta, tb, defect, errors, status, jac, true);
 }
 int lto_direct_defect_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate, int nsteps,
                            const double* X_all, const double* u_all, const double* t_TU, double* defect, double* errors,
                            int32_t* status) {
+    LTO_NVTX();
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     return direct_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, nstate, nsteps, X_all, nullptr, u_all, nullptr,
                        t_TU, nullptr, defect, errors, status, nullptr, false);
@@ -539,6 +545,7 @@ int lto_direct_defect_traj(lto_handle* h, const lto_direct_params* p, int64_t n_
 int lto_direct_defect_jac_traj(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate,
                                int nsteps, const double* X_all, const double* u_all, const double* t_TU, double* defect,
                                double* errors, int32_t* status, double* jac) {
+    LTO_NVTX();
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     return direct_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, nstate, nsteps, X_all, nullptr, u_all, nullptr,
                        t_TU, nullptr, defect, errors, status, jac, true);
@@ -547,18 +554,21 @@ int lto_direct_defect_jac_traj(lto_handle* h, const lto_direct_params* p, int64_
 int lto_indirect_defect(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim, const double* x0,
                         const double* t0, const double* t1, const double* x_target, const double* thrustLimit_seg,
                         const double* rho_seg, double* defect, int32_t* status, int32_t* nsteps_out) {
+    LTO_NVTX();
     return indirect_host(h, p, n_seg, 0, 0, 0, ndim, x0, t0, t1, x_target, thrustLimit_seg, rho_seg, defect, status, nsteps_out,
                          nullptr, false);
 }
 int lto_indirect_defect_jac(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int ndim, const double* x0,
                             const double* t0, const double* t1, const double* x_target, const double* thrustLimit_seg,
                             const double* rho_seg, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    LTO_NVTX();
     return indirect_host(h, p, n_seg, 0, 0, 0, ndim, x0, t0, t1, x_target, thrustLimit_seg, rho_seg, defect, status, nsteps_out,
                          phi, true);
 }
 int lto_indirect_defect_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
                              const double* XC_all, const double* t_TU, const double* thrustLimit_traj, const double* rho_traj,
                              double* defect, int32_t* status, int32_t* nsteps_out) {
+    LTO_NVTX();
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     return indirect_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, n_traj, ndim, XC_all, t_TU, nullptr, nullptr,
                          thrustLimit_traj, rho_traj, defect, status, nsteps_out, nullptr, false);
@@ -566,6 +576,7 @@ int lto_indirect_defect_traj(lto_handle* h, const lto_indirect_params* p, int64_
 int lto_indirect_defect_jac_traj(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int ndim,
                                  const double* XC_all, const double* t_TU, const double* thrustLimit_traj,
                                  const double* rho_traj, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    LTO_NVTX();
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
     return indirect_host(h, p, n_traj * (n_nodes - 1), n_nodes, n_traj * n_nodes, n_traj, ndim, XC_all, t_TU, nullptr, nullptr,
                          thrustLimit_traj, rho_traj, defect, status, nsteps_out, phi, true);
@@ -574,6 +585,7 @@ int lto_indirect_defect_jac_traj(lto_handle* h, const lto_indirect_params* p, in
 int lto_direct_dev(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int n_nodes, int nstate, int nsteps,
                    const double* Xa, const double* Xb, const double* ua, const double* ub, const double* ta, const double* tb,
                    double* defect, double* errors, int32_t* status, double* jac) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     DirectArgs a; memset(&a, 0, sizeof a);
@@ -590,6 +602,7 @@ int lto_direct_dev(lto_handle* h, const lto_direct_params* p, int64_t n_seg, int
 int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg, int n_nodes, int ndim, const double* x0,
                      const double* t0, const double* t1, const double* x_target, const double* thrustLimit_arr,
                      const double* rho_arr, double* defect, int32_t* status, int32_t* nsteps_out, double* phi) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     IndirectArgs a; memset(&a, 0, sizeof a);
@@ -608,6 +621,7 @@ int lto_indirect_dev(lto_handle* h, const lto_indirect_params* p, int64_t n_seg,
 }
 
 int lto_sumsq_dev(lto_handle* h, const double* v, int64_t n_rows, int64_t row_len, double* out) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     if (n_rows < 0 || row_len < 0 || (n_rows > 0 && (!v || !out))) return fail(h, LTO_ERR_ARG, "bad argument");
@@ -657,6 +671,7 @@ int lto_ipc_close(lto_handle* h, void* dev_ptr) {
 // dst/src: device pointers (local or peer-mapped).  Enqueued on the copy stream after everything enqueued so far on the
 // compute stream, i.e. a DMA-engine push that overlaps the next kernel.  lto_sync_copies waits for all of them.
 int lto_push_async(lto_handle* h, void* dst, const void* src, size_t bytes) {
+    LTO_NVTX();
     if (!h || h->n_child > 0) return fail(h, LTO_ERR_ARG, "needs a single-device handle");
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaEventRecord(h->ev_in, h->s_compute));
@@ -665,6 +680,7 @@ int lto_push_async(lto_handle* h, void* dst, const void* src, size_t bytes) {
     return LTO_SUCCESS;
 }
 int lto_sync_copies(lto_handle* h) {
+    LTO_NVTX();
     if (!h || h->n_child > 0) return fail(h, LTO_ERR_ARG, "needs a single-device handle");
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaStreamSynchronize(h->s_copy));

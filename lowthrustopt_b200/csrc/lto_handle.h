@@ -3,10 +3,11 @@
 #pragma once
 #include "../../include/lto_b200.h"
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stddef.h>
 #include <stdint.h>
 
-static const size_t LTO_PROF_WORDS = 8192;
+static const size_t LTO_PROF_WORDS = 16384;
 #define LTO_MAX_DEVICES 16
 
 struct lto_handle {
@@ -29,6 +30,14 @@ struct lto_handle {
     int n_child;                                // > 0: a multi-device handle (lto_init_devices); the work is done by the children
     lto_handle* child[LTO_MAX_DEVICES];
 };
+
+// NVTX range around every C-ABI entry point that does device work (tracing): shows up as a named span on the
+// calling thread's timeline in Nsight Systems / ncu --nvtx; header-only NVTX3, a no-op when no tool is attached.
+struct LtoNvtxRange {
+    explicit LtoNvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~LtoNvtxRange() { nvtxRangePop(); }
+};
+#define LTO_NVTX() LtoNvtxRange lto_nvtx_range__(__func__)
 
 int lto_fail(lto_handle* h, int code, const char* fmt, ...);
 int lto_ensure(lto_handle* h, void** p, size_t* cap, size_t need);      // grow-only device buffer

@@ -293,5 +293,38 @@ LTO_HD double state_err_sumsq(const K3& Kr, const K3& Kl, double w2, double h, d
     return s;
 }
 
+// Same sum from error vectors that were accumulated stage by stage (the rolled state loop of lto_indirect_hc.cu):
+//   e1 = (psi^T B) . k, e2 = psi . k per component c = [r-part (3) | lv-part (3)]; g1 = -(B[11] . k), g2 = k_1 - k_12 (ROB only)
+template <bool ROB>
+LTO_HD double state_err_sumsq_acc(const double (&e1)[6], const double (&e2)[6], const double (&g1)[6], const double (&g2)[6], double w2, double h,
+                                  double h2, const double (&z)[12], const double (&zn)[12], double atol, double rtol) {
+    const double ce = h * lto_tab::ERRC, ce2 = h2 * lto_tab::ERRC;
+    double er[3], ev[3], el[3], eld[3], elr[3], lr[3], lrn[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { er[q] = ce2 * e1[q]; ev[q] = ce * e2[q]; el[q] = ce2 * e1[3 + q]; eld[q] = ce * e2[3 + q]; }
+    const double lv[3] = {z[6], z[7], z[8]}, lvd[3] = {z[9], z[10], z[11]}, lvn[3] = {zn[6], zn[7], zn[8]}, lvdn[3] = {zn[9], zn[10], zn[11]};
+    lr_of(w2, el, eld, elr);
+    lr_of(w2, lv, lvd, lr);
+    lr_of(w2, lvn, lvdn, lrn);
+    if (ROB) {
+        double gr[3], gv[3], gl[3], gld[3], glr[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { gr[q] = ce2 * g1[q]; gv[q] = ce * g2[q]; gl[q] = ce2 * g1[3 + q]; gld[q] = ce * g2[3 + q]; }
+        lr_of(w2, gl, gld, glr);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { er[q] = rob_abs(er[q], gr[q]); ev[q] = rob_abs(ev[q], gv[q]); el[q] = rob_abs(el[q], gl[q]); elr[q] = rob_abs(elr[q], glr[q]); }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double q0 = er[q] * f_rcp(fma(rtol, fmax(fabs(z[q]), fabs(zn[q])), atol));
+        const double q1 = ev[q] * f_rcp(fma(rtol, fmax(fabs(z[3 + q]), fabs(zn[3 + q])), atol));
+        const double q2 = elr[q] * f_rcp(fma(rtol, fmax(fabs(lr[q]), fabs(lrn[q])), atol));
+        const double q3 = el[q] * f_rcp(fma(rtol, fmax(fabs(lv[q]), fabs(lvn[q])), atol));
+        s = fma(q0, q0, s); s = fma(q1, q1, s); s = fma(q2, q2, s); s = fma(q3, q3, s);
+    }
+    return s;
+}
+
 }  // namespace hcm
 }  // namespace lto

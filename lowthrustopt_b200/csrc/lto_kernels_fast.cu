@@ -18,10 +18,13 @@ cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st,
     return launch_direct_cw(a, nstate, st, n_launch);
 }
 
-// (development switch of round 2, removed once the half-column kernel has replaced the column-per-thread one: LTO_K3=cw)
+// LTO_K3=hc selects the half-column layout of round 2 (lto_indirect_hc.cu: second-order variables, one thread per 3-vector Nystrom
+// half-column, 12 warps with setmaxnreg, three tiles in flight).  Bit-for-bit parity with the default is NOT expected (different
+// variables, same controller); it passes the same parity tests.  Default stays the column-per-thread kernel until the half-column
+// one is faster on the bench (DESIGN.md section 4 has both sets of numbers).
 static bool use_old_k3() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("LTO_K3"); v = (e && strcmp(e, "cw") == 0) ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("LTO_K3"); v = (e && strcmp(e, "hc") == 0) ? 0 : 1; }
     return v == 1;
 }
 

@@ -200,6 +200,7 @@ extern "C" {
 
 int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
                             const double* defect, double* xc_update, int32_t* status) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
@@ -219,6 +220,7 @@ int lto_indirect_newton_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag
 
 int lto_indirect_newton_resolve_dev(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* defect,
                                     double* xc_update, int32_t* status) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     if (n_traj == 0) return LTO_SUCCESS;
@@ -235,6 +237,7 @@ int lto_indirect_newton_resolve_dev(lto_handle* h, int64_t n_traj, int n_nodes, 
 
 int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adjointsOnly, const double* phi,
                         const double* defect, double* xc_update, int32_t* status) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
@@ -269,6 +272,7 @@ int lto_indirect_newton(lto_handle* h, int64_t n_traj, int n_nodes, int flag_adj
 int lto_direct_qp_dev(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect,
                       const double* u_all, const double* t_TU, const double* b0, const double* bf, double* x_update, double* u_update,
                       int32_t* status) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (h->n_child > 0) return fail(h, LTO_ERR_ARG, "device-pointer entry points need a single-device handle (lto_init)");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
@@ -288,6 +292,7 @@ int lto_direct_qp_dev(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, co
 
 int lto_direct_qp(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const double* jac, const double* defect, const double* u_all,
                   const double* t_TU, const double* b0, const double* bf, double* x_update, double* u_update, int32_t* status) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
     if (n_nodes < 2) return fail(h, LTO_ERR_ARG, "n_nodes must be >= 2");
@@ -334,6 +339,7 @@ int lto_direct_qp(lto_handle* h, int64_t n_traj, int n_nodes, int nstate, const 
 int lto_direct_solve_batch(lto_handle* h, const lto_direct_params* p, int64_t n_traj, int n_nodes, int nstate, int nsteps, int max_iter,
                            double* X_all, double* u_all, const double* t_TU, const double* state_0, const double* state_f, double mass,
                            double* defect, int32_t* iters, double* er_out) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (!p) return fail(h, LTO_ERR_ARG, "null params");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");
@@ -478,6 +484,7 @@ int lto_direct_solve_batch(lto_handle* h, const lto_direct_params* p, int64_t n_
 int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_t n_traj, int n_nodes, int max_iter,
                              int flag_adjointsOnly, double* XC_all, const double* t_TU, const double* thrustLimit_traj,
                              const double* rho_traj, double* defect, int32_t* status_flag, int32_t* iters, double* er_out) {
+    LTO_NVTX();
     if (!h) return fail(nullptr, LTO_ERR_ARG, "null handle");
     if (!p) return fail(h, LTO_ERR_ARG, "null params");
     if (n_traj < 0) return fail(h, LTO_ERR_ARG, "negative trajectory count");

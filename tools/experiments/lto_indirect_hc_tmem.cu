@@ -58,8 +58,7 @@ constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h,
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot (both halves summed)
 constexpr int NXW = ND + 7;                                                // next-segment stash: x0, t0, tf, aL, 1/rho, aL/(4 rho), h0, tol scale
 constexpr size_t NXT_BYTES = (size_t)NXW * TS * sizeof(double);
-constexpr size_t ZN_BYTES = (size_t)2 * ND * TS * sizeof(double);           // the state z and the candidate of the attempt in flight (double buffer; not live in registers across the right-hand-side calls)
-constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + ERR_BYTES + ZN_BYTES + NXT_BYTES;
+constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + ERR_BYTES + NXT_BYTES;
 constexpr size_t BAR_BYTES = 32;                                           // full, done, tile_done
 constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
 static_assert(SMEM <= 232448, "three tiles must fit the 227 KB of shared memory per CTA");
@@ -67,7 +66,7 @@ static_assert(TILE_BYTES % 16 == 0, "tiles must stay 16-byte aligned");
 constexpr size_t SCR_DOUBLES_PER_CTA = (size_t)NTILE * 2 * NTASK * 6 * 32; // [tile][parity][task][component][lane]
 
 struct TileSmem {
-    double2* rec; double* hval; int2* hctl; double* errp; double* zn; double* nx;
+    double2* rec; double* hval; int2* hctl; double* errp; double* nx;
     unsigned bar_full, bar_done; volatile int* tile_done;
 };
 
@@ -78,7 +77,6 @@ __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
     s.hval = reinterpret_cast<double*>(p); p += TS * sizeof(double);
     s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
-    s.zn = reinterpret_cast<double*>(p); p += ZN_BYTES;
     s.nx = reinterpret_cast<double*>(p);
     unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * BAR_BYTES;
     s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 8);
@@ -224,43 +222,71 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
 }
 
 // ---------------------------------------------------------------------------
-// State warp.  The 78 stage derivatives of z = (r, v, lv, lvd) stay in registers (13 unrolled stages, compile-time tableau
-// sparsity); ONE out-of-line copy of the right-hand side serves all 13 stages, and the claim of the next segment is inlined at
-// its one call site -- the state warps' code competes with the column warps' ~19 KB loop body for the instruction caches
-// (sm__icc_request_hit_rate, stall_no_instruction in profiles/), so every duplicate counts.  Measured alternative (kept in
-// tools/experiments/lto_indirect_hc_tmem.cu): stages rolled into a loop with the derivatives in the warp's lane quadrant of TENSOR
-// MEMORY (tcgen05.st / tcgen05.ld) -- a third of the code, correct results, but the dependent load -> wait -> FMA rounds of the
-// stage-input loop cost 24 k cycles per attempt (48 k in all against 28 k here), so the state warps became the bound.
+// State warp.
+//
+// Code size matters as much as arithmetic here: the column warps stream a ~19 KB straight-line body, and every other instruction
+// stream on the SM competes with it for the instruction caches (round 2, first version: 13 unrolled stages with the 78 stage
+// derivatives in registers = 33 KB of state code, sm__icc_request_hit_rate 66 %, stall_no_instruction the top stall of BOTH warp
+// kinds, the columns 55 % slower than with idle state warps; profiles/r02_*).  So the state warp runs ROLLED loops over stages:
+//   * the stage derivatives k_J = (r'', lv'') live in the warp's own lane quadrant of TENSOR MEMORY (tcgen05.st / tcgen05.ld,
+//     16 columns per stage and lane; 12-cycle loads, dynamically addressed) -- TMEM is otherwise unused by this FP64 kernel and is
+//     the only on-chip store left: registers and shared memory are full;
+//   * tableau coefficients come from __constant__ tables (uniform loads), zero entries skipped by uniform branches;
+//   * the 8th-order update and the error estimate are accumulated stage by stage;
+//   * one out-of-line copy of the right-hand side serves all 13 stages, arguments and results in registers.
 // ---------------------------------------------------------------------------
-struct Out6 { double v[6]; };
-__device__ __noinline__ Out6 sc_eval2_call(double r0, double r1, double r2, double v0, double v1, double m0, double m1, double m2, double n0, double n1,
-                                           double mu, double mu1, double w2, double pexp, double aL, double rho_inv, double rq, double2* w) {
-    const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, 0.0}, M[3] = {m0, m1, m2}, N[3] = {n0, n1, 0.0};
-    Law lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rq = rq;
-    double kr[3], kl[3], U[6], W[6], G[6];
-    sc_eval2<true>(R, V, M, N, mu, mu1, w2, pexp, lw, kr, kl, U, W, G);
-    w[0 * TS] = make_double2(U[0], U[1]); w[1 * TS] = make_double2(U[2], U[3]); w[2 * TS] = make_double2(U[4], U[5]);
-    w[3 * TS] = make_double2(W[0], W[1]); w[4 * TS] = make_double2(W[2], W[3]); w[5 * TS] = make_double2(W[4], W[5]);
-    w[6 * TS] = make_double2(G[0], G[1]); w[7 * TS] = make_double2(G[2], G[3]); w[8 * TS] = make_double2(G[4], G[5]);
-    Out6 o;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { o.v[q] = kr[q]; o.v[3 + q] = kl[q]; }
-    return o;
+// the non-zero (stage J, earlier stage l) couplings of B and G = B*B, stage after stage: J's entries are [start[J], start[J+1])
+struct PairTab { int start[14]; int l[80]; double b[80]; double g[80]; };
+constexpr PairTab make_pairs() {
+    PairTab t{};
+    int n = 0;
+    for (int J = 0; J < 13; ++J) {
+        t.start[J] = n;
+        for (int l = 0; l < J; ++l)
+            if (lto_tab::Bf(J, l) != 0.0 || lto_tab::Gf(J, l) != 0.0) { t.l[n] = l; t.b[n] = lto_tab::Bf(J, l); t.g[n] = lto_tab::Gf(J, l); ++n; }
+    }
+    t.start[13] = n;
+    return t;
 }
+__constant__ PairTab tPairs = make_pairs();
+__constant__ double tB11[13] = {lto_tab::Bf(11, 0), lto_tab::Bf(11, 1), lto_tab::Bf(11, 2), lto_tab::Bf(11, 3), lto_tab::Bf(11, 4), lto_tab::Bf(11, 5), lto_tab::Bf(11, 6),
+                                lto_tab::Bf(11, 7), lto_tab::Bf(11, 8), lto_tab::Bf(11, 9), lto_tab::Bf(11, 10), 0.0, 0.0};
+__constant__ double tC[13] = LTO_TAB_C_INIT;
+__constant__ double tCHI[13] = LTO_TAB_CHI_INIT;
+__constant__ double tCHIB[13] = LTO_TAB_CHIB_INIT;
+__constant__ double tPSI[13] = LTO_TAB_PSI_INIT;
+__constant__ double tPSIB[13] = LTO_TAB_PSIB_INIT;
 
-// one stage of the state: inputs from the stage derivatives in REGISTERS (compile-time tableau sparsity), right-hand side + record
-template <int J>
-__device__ __forceinline__ void state_stage(K3& Kr, K3& Kl, const double* __restrict__ z, double h, double h2, const SCConst& c, double w2,
-                                            const Law& lw, double2* __restrict__ rec) {
-    const double r[3] = {z[0 * TS], z[1 * TS], z[2 * TS]}, v[3] = {z[3 * TS], z[4 * TS], z[5 * TS]}, lv[3] = {z[6 * TS], z[7 * TS], z[8 * TS]},
-                 lvd[3] = {z[9 * TS], z[10 * TS], z[11 * TS]};
-    double R[3], V[3], M[3], N[3];
-    stage_in<J>(Kr, r, v, h, h2, R, V);
-    stage_in<J>(Kl, lv, lvd, h, h2, M, N);
-    const Out6 o = sc_eval2_call(R[0], R[1], R[2], V[0], V[1], M[0], M[1], M[2], N[0], N[1], c.mu, c.m1, w2, c.p, lw.aL, lw.rho_inv, lw.rq,
-                                 rec + J * NC2 * TS);
+// ---- tensor memory as a per-lane scratch: lane l of warp w owns columns [0, 512) of TMEM lane 32 (w % 4) + l
+constexpr int TMEM_COLS = 512;
+constexpr int KCOLS = 16;                                               // 32-bit columns per stage: 6 doubles + padding
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst) {        // one warp; writes the base address to shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_st6(unsigned taddr, const double (&v)[6]) {
+    unsigned r[12];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { Kr.k[J][q] = o.v[q]; Kl.k[J][q] = o.v[3 + q]; }
+    for (int i = 0; i < 6; ++i) { r[2 * i] = (unsigned)__double2loint(v[i]); r[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + 8), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// issue / complete halves of a load, so that the next stage derivative is in flight while the present one is being used
+struct TmemRegs { unsigned r[12]; };
+__device__ __forceinline__ void tmem_ld6_issue(unsigned taddr, TmemRegs& t) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(t.r[0]), "=r"(t.r[1]), "=r"(t.r[2]), "=r"(t.r[3]),
+                 "=r"(t.r[4]), "=r"(t.r[5]), "=r"(t.r[6]), "=r"(t.r[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.r[8]), "=r"(t.r[9]), "=r"(t.r[10]), "=r"(t.r[11]) : "r"(taddr + 8) : "memory");
+}
+__device__ __forceinline__ void tmem_ld6_wait(const TmemRegs& t, double (&v)[6]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v[i] = __hiloint2double((int)t.r[2 * i + 1], (int)t.r[2 * i]);
 }
 
 __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
@@ -350,18 +376,18 @@ __device__ __forceinline__ Claim prepare_next(const IndirectArgs& a, double* nxs
 }
 
 template <bool JOINT>
-__device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem) {
+__device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lane, unsigned char* smem, unsigned tmem_base) {
     const TileSmem S = tile_smem(smem, t);
     const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double w2 = 2.0 * a.c.omega;
+    const unsigned tk = tmem_base + ((unsigned)(32 * ((NCW + t) & 3)) << 16);   // this warp's lane quadrant, column 0: k_J at columns [16 J, 16 J + 12)
     double atol = a.cfg.atol, rtol = a.cfg.rtol;                          // per slot when the norm is the state's alone (state_tol_scale)
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
     int par = 0;                                                          // which scratch buffer holds the slot's current columns
-    int zi = 0;                                                           // which half of the double buffer holds z = (r, v, lv, lvd)
-    double* const zbuf = S.zn + slot;
+    double z[ND], zn[ND];                                                 // z = (r, v, lv, lvd) and the candidate of the attempt in flight
 #pragma unroll
-    for (int i = 0; i < ND; ++i) { zbuf[i * TS] = 0.0; zbuf[(ND + i) * TS] = 0.0; }
+    for (int i = 0; i < ND; ++i) { z[i] = 0.0; zn[i] = 0.0; }
     double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
     Law lw; lw.aL = 0.0; lw.rho_inv = 1.0; lw.rq = 0.0;
     long long seg = -1, ia = 0;
@@ -371,7 +397,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     unsigned visit = 0;
     double2* rec = S.rec + slot;
     double* const nxs = S.nx + slot;
-    long long c_wait = 0, c_work = 0, c_pre = 0;
+    long long c_wait = 0, c_work = 0, c_pre = 0, c_qin = 0, c_qev = 0, c_qst = 0;
     const long long c_begin = clock64();
     bool soon = true, retried = false;
     int flags = 0, store_seg = 0;                                         // published with the next attempt
@@ -398,7 +424,9 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                     q = fmin(5.0, fmax(0.2, q));
                     if (u <= 1.0) {
                         ++na;
-                        par ^= 1; zi ^= 1;                                // the candidates become z and the current columns
+                        par ^= 1;                                         // the candidates become z and the current columns
+#pragma unroll
+                        for (int i = 0; i < ND; ++i) z[i] = zn[i];
                         if (last) { tcur = tf; finished = true; }
                         else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
                     } else {
@@ -414,11 +442,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         }
         if (active && finished) {
             // ---- defect = x(t1) - XC_all[:, i+1] (multiShoot_CRTBP_indirect.jl:82), back in the reference's variables
-            const double* zs = zbuf + zi * ND * TS;
             double xv[ND];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { xv[q] = zs[q * TS]; xv[3 + q] = zs[(3 + q) * TS]; xv[9 + q] = zs[(6 + q) * TS]; }
-            xv[6] = fma(w2, xv[10], -zs[9 * TS]); xv[7] = fma(-w2, xv[9], -zs[10 * TS]); xv[8] = -zs[11 * TS];
+            for (int q = 0; q < 3; ++q) { xv[q] = z[q]; xv[3 + q] = z[3 + q]; xv[9 + q] = z[6 + q]; }
+            xv[6] = fma(w2, z[7], -z[9]); xv[7] = fma(-w2, z[6], -z[10]); xv[8] = -z[11];
             bool nan = false;
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
@@ -433,10 +460,9 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         }
         if (!active && nxt.nseg >= 0) {                                  // take the successor prepared by prepare_next()
             seg = nxt.nseg; nxt.nseg = -1; ia = lto_node_a(seg, a.npt);
-            double* zs = zbuf + zi * ND * TS;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { zs[q * TS] = nxs[q * TS]; zs[(3 + q) * TS] = nxs[(3 + q) * TS]; zs[(6 + q) * TS] = nxs[(9 + q) * TS]; }
-            zs[9 * TS] = fma(w2, nxs[10 * TS], -nxs[6 * TS]); zs[10 * TS] = fma(-w2, nxs[9 * TS], -nxs[7 * TS]); zs[11 * TS] = -nxs[8 * TS];
+            for (int q = 0; q < 3; ++q) { z[q] = nxs[q * TS]; z[3 + q] = nxs[(3 + q) * TS]; z[6 + q] = nxs[(9 + q) * TS]; }
+            z[9] = fma(w2, nxs[10 * TS], -nxs[6 * TS]); z[10] = fma(-w2, nxs[9 * TS], -nxs[7 * TS]); z[11] = -nxs[8 * TS];
             tcur = nxs[(ND + 0) * TS]; tf = nxs[(ND + 1) * TS];
             span = tf - tcur;
             lw.aL = nxs[(ND + 2) * TS]; lw.rho_inv = nxs[(ND + 3) * TS]; lw.rq = nxs[(ND + 4) * TS];
@@ -464,24 +490,80 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         if (active) ++nt;
         S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0) | (par ? F_PAR : 0), store_seg);
         const double h2 = h * h;
-        K3 Kr, Kl;
-        const double* z = zbuf + zi * ND * TS;
-        state_stage<0>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<1>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<2>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<3>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<4>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<5>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<6>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<7>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<8>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<9>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<10>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);  state_stage<11>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<12>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        {
-            const double r[3] = {z[0 * TS], z[1 * TS], z[2 * TS]}, v[3] = {z[3 * TS], z[4 * TS], z[5 * TS]}, lv[3] = {z[6 * TS], z[7 * TS], z[8 * TS]},
-                         lvd[3] = {z[9 * TS], z[10 * TS], z[11 * TS]};
-            double rn[3], vn[3], lvn[3], lvdn[3];
-            step_update(Kr, r, v, h, h2, rn, vn);
-            step_update(Kl, lv, lvd, h, h2, lvn, lvdn);
-            esum = state_err_sumsq<!JOINT>(Kr, Kl, w2, h, h2, r, v, lv, lvd, rn, vn, lvn, lvdn, atol, rtol);
-            double* zc = zbuf + (zi ^ 1) * ND * TS;
+        double su[6], sp[6], e1[6], e2[6], g1[6], g2[6];                 // update (chi, chi^T B) and error (psi, psi^T B; ROB: -B[11], e1 - e12) sums
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { zc[q * TS] = rn[q]; zc[(3 + q) * TS] = vn[q]; zc[(6 + q) * TS] = lvn[q]; zc[(9 + q) * TS] = lvdn[q]; }
+        for (int c = 0; c < 6; ++c) { su[c] = 0.0; sp[c] = 0.0; e1[c] = 0.0; e2[c] = 0.0; g1[c] = 0.0; g2[c] = 0.0; }
+        long long q_in = 0, q_ev = 0, q_st = 0;
+        double kp[6];                                                    // k_{J-1}: used from registers, every older one comes back from tensor memory
+#pragma unroll
+        for (int c = 0; c < 6; ++c) kp[c] = 0.0;
+#pragma unroll 1
+        for (int J = 0; J < 13; ++J) {
+            double sb[6], sg[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { sb[c] = 0.0; sg[c] = 0.0; }
+            const int n0 = tPairs.start[J], n1 = tPairs.start[J + 1];
+            const long long q0 = a.prof ? clock64() : 0;
+            tmem_st_wait();                                              // k_0 .. k_{J-1} are in tensor memory
+            TmemRegs tr;
+            int n = n0;
+            bool inflight = false;
+            if (n < n1 && tPairs.l[n] != J - 1) { tmem_ld6_issue(tk + (unsigned)(KCOLS * tPairs.l[n]), tr); inflight = true; }
+#pragma unroll 1
+            for (; n < n1; ++n) {
+                const int l = tPairs.l[n];
+                const double b = tPairs.b[n], g = tPairs.g[n];
+                double k[6];
+                if (l == J - 1) {                                        // (uniform) the newest one never left the registers
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) k[c] = kp[c];
+                } else {
+                    tmem_ld6_wait(tr, k);
+                    inflight = false;
+                }
+                if (n + 1 < n1 && tPairs.l[n + 1] != J - 1) { tmem_ld6_issue(tk + (unsigned)(KCOLS * tPairs.l[n + 1]), tr); inflight = true; }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { sb[c] = fma(b, k[c], sb[c]); sg[c] = fma(g, k[c], sg[c]); }
+            }
+            (void)inflight;
+            const long long q1 = a.prof ? clock64() : 0;
+            const double ch = h * tC[J];
+            const double R[3] = {fma(h2, sg[0], fma(ch, z[3], z[0])), fma(h2, sg[1], fma(ch, z[4], z[1])), fma(h2, sg[2], fma(ch, z[5], z[2]))};
+            const double M[3] = {fma(h2, sg[3], fma(ch, z[9], z[6])), fma(h2, sg[4], fma(ch, z[10], z[7])), fma(h2, sg[5], fma(ch, z[11], z[8]))};
+            const double V[3] = {fma(h, sb[0], z[3]), fma(h, sb[1], z[4]), 0.0}, N[3] = {fma(h, sb[3], z[9]), fma(h, sb[4], z[10]), 0.0};
+            double U[6], W[6], G[6];
+            {   // right-hand side + stage record: ONE inlined copy (the stage loop is rolled)
+                double kr[3], kl[3];
+                sc_eval2<true>(R, V, M, N, a.c.mu, a.c.m1, w2, a.c.p, lw, kr, kl, U, W, G);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { kp[q] = kr[q]; kp[3 + q] = kl[q]; }
+            }
+            const long long q2 = a.prof ? clock64() : 0;
+            double2* w = rec + J * NC2 * TS;
+            w[0 * TS] = make_double2(U[0], U[1]); w[1 * TS] = make_double2(U[2], U[3]); w[2 * TS] = make_double2(U[4], U[5]);
+            w[3 * TS] = make_double2(W[0], W[1]); w[4 * TS] = make_double2(W[2], W[3]); w[5 * TS] = make_double2(W[4], W[5]);
+            w[6 * TS] = make_double2(G[0], G[1]); w[7 * TS] = make_double2(G[2], G[3]); w[8 * TS] = make_double2(G[4], G[5]);
+            tmem_st6(tk + (unsigned)(KCOLS * J), kp);
+            const double wc = tCHI[J], wb = tCHIB[J], wp = tPSI[J], wq = tPSIB[J];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { su[c] = fma(wc, kp[c], su[c]); sp[c] = fma(wb, kp[c], sp[c]); e2[c] = fma(wp, kp[c], e2[c]); e1[c] = fma(wq, kp[c], e1[c]); }
+            if (!JOINT) {                                                // robust estimate of the state-only controller (lto_prop_generic.cuh drive_rk8)
+                const double wa = -tB11[J], wd = (J == 0) ? 1.0 : (J == 11) ? -1.0 : 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { g1[c] = fma(wa, kp[c], g1[c]); g2[c] = fma(wd, kp[c], g2[c]); }
+            }
+            if (a.prof) { const long long q3 = clock64(); q_in += q1 - q0; q_ev += q2 - q1; q_st += q3 - q2; }
         }
+        if (a.prof) { c_qin += q_in; c_qev += q_ev; c_qst += q_st; }
+        tmem_st_wait();
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {                                    // 8th-order update (ode.jl:937)
+            zn[q] = fma(h2, sp[q], fma(h, z[3 + q], z[q]));
+            zn[3 + q] = fma(h, su[q], z[3 + q]);
+            zn[6 + q] = fma(h2, sp[3 + q], fma(h, z[9 + q], z[6 + q]));
+            zn[9 + q] = fma(h, su[3 + q], z[9 + q]);
+        }
+        esum = state_err_sumsq_acc<!JOINT>(e1, e2, g1, g2, w2, h, h2, z, zn, atol, rtol);
         mbar_arrive(S.bar_full);                                         // the whole attempt's record
         c_work += clock64() - c2;
         have = true; ++visit;
@@ -492,12 +574,15 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + NCW + t) * 4;
         o[0] = c_work; o[1] = c_wait; o[2] = visit; o[3] = clock64() - c_begin;
         a.prof[(size_t)gridDim.x * NW * 4 + (size_t)blockIdx.x * NTILE + t] = c_pre;
+        unsigned long long* q = a.prof + (size_t)gridDim.x * (NW * 4 + NTILE + NCW) + ((size_t)blockIdx.x * NTILE + t) * 3;
+        q[0] = c_qin; q[1] = c_qev; q[2] = c_qst;                        // stage-input loop | right-hand side | record + tensor-memory store + sums
     }
 }
 
 template <bool JOINT, int RC = REG_COL, int RS = REG_STATE>
 __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_constant__ IndirectArgs a) {   // (grid constant: out-of-line callees take its address without a local copy)
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned tmem_addr;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < NTILE) {
         const TileSmem S = tile_smem(smem_raw, threadIdx.x);
@@ -505,7 +590,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_consta
         mbar_init(S.bar_done, NCT);
         *S.tile_done = 0;
     }
+    if (warp == NW - 1) tmem_alloc(smem_u32(&tmem_addr));                // the fourth warp of the state group owns the TMEM allocation
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // warp groups 0 and 1 (warps 0..7, two per SM sub-partition): column warps, give registers away;
     // warp group 2 (warps 8..11, one per sub-partition): state warps of tiles 0..2 take them (warp 11 has no tile)
     if (warp < NCW) {
@@ -513,7 +601,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_consta
         column_warp<JOINT>(a, warp, lane, smem_raw);
     } else {
         reg_inc<RS>();
-        if (warp - NCW < NTILE) state_warp<JOINT>(a, warp - NCW, lane, smem_raw);
+        const unsigned tb = tmem_addr;
+        if (warp - NCW < NTILE) state_warp<JOINT>(a, warp - NCW, lane, smem_raw, tb);
+        asm volatile("bar.sync 2, 128;" ::: "memory");                   // the state group is done with its tensor-memory scratch
+        if (warp == NW - 1) tmem_dealloc(tb);
     }
 }
 

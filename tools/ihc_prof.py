@@ -34,5 +34,7 @@ print("state : alive %.0f  work/attempt %.0f  wait/attempt %.0f  pre/attempt %.0
     sw[..., 3].mean(), (sw[..., 0] / sw[..., 2]).mean(), (sw[..., 1] / sw[..., 2]).mean(), (pre / sw[..., 2]).mean(), sw[..., 2].mean()))
 print("column: alive %.0f  work/task %.0f  wait/tile-visit %.0f  tasks %.0f  busy %.1f%%" % (
     co[..., 3].mean(), (co[..., 0] / co[..., 2]).mean(), (co[..., 1] / (co[..., 2] / 3)).mean(), co[..., 2].mean(), 100 * (co[..., 0] / co[..., 3]).mean()))
+att = w[grid * NW * 4 + grid * NT: grid * NW * 4 + grid * NT + grid * NCW].reshape(grid, NCW)
+print("column: cycles inside col_attempt per task %.0f (the rest of a task: column load from the L2 scratch, header, candidate store, error hand-over)" % (att / co[..., 2]).mean())
 for wi in range(NCW):
     print("  col warp %d: work/task %.0f busy %.1f%%" % (wi, (co[:, wi, 0] / co[:, wi, 2]).mean(), 100 * (co[:, wi, 0] / co[:, wi, 3]).mean()))
