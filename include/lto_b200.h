@@ -40,6 +40,12 @@ extern "C" {
 #define LTO_B200_VERSION 100
 
 /* per-segment status codes */
+/* Time spans: every indirect segment is integrated FORWARDS from t0 to t1.  t1 == t0 is allowed (returns x0 and Phi = I).  t1 < t0
+ * (the reference's ODEProblem would integrate backwards) is NOT supported: the host-buffer entry points refuse the call with
+ * LTO_ERR_ARG naming the first such segment; the device-pointer entry points (lto_indirect_dev, the batched solver) cannot look at
+ * the times and treat such a segment as an empty span -- callers of those must not pass reversed spans.  time_direction = -1 in the
+ * parameters (the backward legs of the reference's direct method and of its trajectory stacking) is the supported way of
+ * integrating the time-reversed dynamics. */
 enum { LTO_ST_OK = 0, LTO_ST_NAN = 1, LTO_ST_HMIN = 2, LTO_ST_MAXSTEPS = 3, LTO_ST_BADP = 4 };
 /* return codes */
 enum { LTO_SUCCESS = 0, LTO_ERR_CUDA = -1, LTO_ERR_ARG = -2, LTO_ERR_NODEVICE = -3, LTO_ERR_NOMEM = -4 };

@@ -80,16 +80,27 @@ int lto_init(int device, lto_handle** out) {
     lto_handle* h = (lto_handle*)calloc(1, sizeof(lto_handle));
     if (!h) return fail(nullptr, LTO_ERR_NOMEM, "lto_init: out of host memory");
     h->device = device; h->n_sm = prop.multiProcessorCount;
-    CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
-    CK(h, cudaEventCreate(&h->ev_t0));
-    CK(h, cudaEventCreate(&h->ev_t1));
-    for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
-    for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-    CK(h, cudaMalloc((void**)&h->d_ctr, 256));                             // work-queue counter of the throughput kernels
-    if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
+    auto setup = [&]() -> int {
+        CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CK(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        CK(h, cudaEventCreate(&h->ev_t0));
+        CK(h, cudaEventCreate(&h->ev_t1));
+        for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+        for (int i = 0; i < 8; ++i) CK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        CK(h, cudaMalloc((void**)&h->d_ctr, 256));                         // work-queue counter of the throughput kernels
+        if (getenv("LTO_ICW_PROF")) { CK(h, cudaMalloc((void**)&h->d_prof, LTO_PROF_WORDS * 8)); CK(h, cudaMemset(h->d_prof, 0, LTO_PROF_WORDS * 8)); }
+        return LTO_SUCCESS;
+    };
+    const int rc = setup();
+    if (rc) {                                                              // no handle leaves this function: the message moves to the global slot
+        char msg[sizeof h->err];
+        memcpy(msg, h->err, sizeof msg); msg[sizeof msg - 1] = 0;
+        lto_destroy(h);
+        cudaGetLastError();
+        return fail(nullptr, rc, "lto_init: %s", msg);
+    }
     *out = h;
     return LTO_SUCCESS;
 }
@@ -445,6 +456,13 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     if (rc) return rc;
     if (n_seg == 0) return LTO_SUCCESS;
     if (!x0 || !t0 || !defect || (npt == 0 && !t1) || (want_jac && !phi)) return fail(h, LTO_ERR_ARG, "null array argument");
+    // Reversed spans (t1 < t0): the reference's solve(ODEProblem(.., (t0, t1))) would integrate backwards; the kernels step forwards
+    // only and would hand back x0 and Phi = I.  A wrong answer with status OK is worse than a refused call: reject.
+    for (long long sgm = 0; sgm < n_seg; ++sgm) {
+        const long long ia = lto_node_a(sgm, npt);
+        const double ta = t0[ia], tb = npt > 0 ? t0[ia + 1] : t1[ia];
+        if (tb < ta) return fail(h, LTO_ERR_ARG, "segment %lld has t1 < t0 (%.17g < %.17g): reversed spans are not supported", sgm, tb, ta);
+    }
     CK(h, cudaSetDevice(h->device));
     const int ND = ndim;
     const long long rows = npt > 0 ? n_nodes_total : n_seg;

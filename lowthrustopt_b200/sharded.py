@@ -277,7 +277,11 @@ class PeerGather:
     the transfer overlaps the computation segment by segment.  Completion is a stream-ordered 64-bit flag per rank in the
     solver rank's memory (lto_signal_dev / lto_wait_dev): nothing in the steady state touches the host.
 
-    Units are split into contiguous, equal slabs (rank r: [n*r/W, n*(r+1)/W)).  spec: name -> (per-unit shape, dtype)."""
+    Units are split into contiguous, equal slabs (rank r: [n*r/W, n*(r+1)/W)).  spec: name -> (per-unit shape, dtype).
+
+    Pass separation: a rank that starts pass k+1 overwrites its slab of the solver rank's arrays, and nothing here tells it that
+    the solver rank has finished READING pass k.  Callers must put a collective (or any root -> ranks synchronisation) between the
+    solver rank's use of one pass and the next `run` -- in this package that is the broadcast of the next iterate in `load()`."""
 
     def __init__(self, handle, spec, n_units, device, group=None, root=0):
         self.h, self.spec, self.n_units, self.device, self.group, self.root = handle, dict(spec), int(n_units), torch.device(device), group, root
@@ -289,8 +293,8 @@ class PeerGather:
         if self.rank == root:
             for k in self.spec:
                 self._owned[k] = handle.dev_alloc(max(256, self.n_units * self.unit_bytes[k]))
-            self._owned["__flags"] = handle.dev_alloc(256)
-            self.flags_t = torch.as_tensor(_DevArray(self._owned["__flags"], (32,), "<i8"), device=self.device)
+            self._owned["__flags"] = handle.dev_alloc(max(256, 8 * self.world))          # one 64-bit completion flag per rank
+            self.flags_t = torch.as_tensor(_DevArray(self._owned["__flags"], (max(32, self.world),), "<i8"), device=self.device)
             self.flags_t.zero_()
             torch.cuda.synchronize(self.device)
             payload = [{k: handle.ipc_export(p) for k, p in self._owned.items()}]

@@ -201,6 +201,11 @@ def test_indirect_traj_form_and_edge_cases(lto):
     # invalid control-law exponent is an error like the reference's error("Invalid value of p!")
     with pytest.raises(capi.LtoError, match="Invalid value of p"):
         lto.indirect(np.ones((1, 12)), np.zeros(1), np.ones(1), params=capi.indirect_params(p=0.5))
+    # a reversed span is refused, not silently treated as empty; a zero-length span is fine (x0, Phi = I)
+    with pytest.raises(capi.LtoError, match="reversed spans"):
+        lto.indirect(np.ones((2, 12)), np.array([0.0, 0.3]), np.array([0.1, 0.2]), params=p)
+    rz = lto.indirect(np.ones((1, 12)) * 0.5, np.array([0.2]), np.array([0.2]), params=p)
+    assert rz["status"][0] == 0 and np.array_equal(rz["defect"][0], np.full(12, 0.5)) and np.array_equal(rz["phi"][0], np.eye(12))
     # NaN input -> status 1, not a crash
     bad = S.indirect_batch(4, ndim=12)
     bad["x0"][2, 0] = np.nan
