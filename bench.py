@@ -932,6 +932,43 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = n_seg * world * args.steps / float(t_e2e.item())
     clocks = sampler.stop()
+    # ---- the same call with PAGEABLE caller memory (what a Julia / numpy caller holds).  (a) inputs pageable, results in
+    # the arrays the binding allocates itself -- pinned, from its pool (capi.PinnedPool; julia/lto_b200.jl `pinned_array`): the documented
+    # way;  (b) results into caller-supplied pageable arrays as well: the driver stages every copy and the pipeline serialises.
+    pageable = None
+    if rank == 0 or world > 1:
+        pg_in = {k: np.array(v, copy=True) for k, v in batch.items()}
+        if direct:
+            def call(out):
+                return h.direct(pg_in["Xa"], pg_in["Xb"], pg_in["ua"], pg_in["ub"], pg_in["ta"], pg_in["tb"], nsteps=10, params=p, jac=True, out=out)
+            pg_out = {"defect": np.empty((n_seg, ns)), "errors": np.empty(n_seg), "status": np.empty(n_seg, dtype=np.int32), "jac": np.empty((n_seg, nv, ns))}
+        else:
+            def call(out):
+                return h.indirect(pg_in["x0"], pg_in["t0"], pg_in["t1"], params=p, jac=True, out=out)
+            pg_out = {"defect": np.empty((n_seg, nd)), "status": np.empty(n_seg, dtype=np.int32), "nsteps": np.empty((n_seg, 2), dtype=np.int32),
+                      "phi": np.empty((n_seg, nd, nd))}
+        for v in pg_out.values():
+            v.fill(0)                                                   # touch the pages: no first-touch faults inside the timed region
+        res = {}
+        for name, out in (("pinned_results", None), ("pageable_results", pg_out)):
+            r = None
+            for _ in range(2):
+                r = call(out)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                r = call(out)
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            barrier()
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            res[name] = n_seg * world * args.steps / float(tt.item())
+            del r
+        pageable = {"inputs": "pageable numpy arrays (what a Julia / numpy caller holds)",
+                    "pinned_results": {"value": res["pinned_results"], "what": "results in the arrays the binding allocates itself (pinned, pooled) -- the documented "
+                                       "way, what julia/lto_b200.jl does"},
+                    "pageable_results": {"value": res["pageable_results"], "what": "results copied into caller-supplied pageable arrays as well"},
+                    "unit": "segment-propagations/s"}
     # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
     per_gpu_ms = float(np.mean(times))
     roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl, flops_counted)
@@ -948,7 +985,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "segment-propagations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "timing": "host wall clock around the blocking lto_*_defect_jac call, pinned host buffers, max over ranks",
-                    "host_buffers": numa_note},
+                    "host_buffers": numa_note, "pageable": pageable},
             "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
     if world > 1:
         # N > 1: `value` is the rate at which results ARRIVE ON THE SOLVER RANK (north_star: defects + Jacobian blocks delivered to the

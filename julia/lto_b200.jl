@@ -22,10 +22,38 @@ function init(devices::Vector{Int32} = Int32[0])
 end
 check(rc) = rc == 0 || error("liblto_b200: ", unsafe_string(ccall((:lto_last_error, lib), Cstring, (Ptr{Cvoid},), handle[])))
 
+# ---- pinned (page-locked) result arrays.  The device-to-host copy of the Jacobian / STM blocks is most of a call's bytes; into a
+# pinned array it runs asynchronously at the PCIe rate and overlaps the kernels, into an ordinary (pageable) Julia array the driver
+# stages it and the pipeline serialises (bench.py `e2e.pageable`).  Blocks are recycled through a small pool (cudaHostAlloc costs
+# milliseconds); a finalizer gives the block back when the array is collected.
+const _pool = Dict{Int, Vector{Ptr{Cvoid}}}()
+const _pool_lock = ReentrantLock()
+_size_class(n) = (c = 4096; while c < n; c <<= 1; end; c)
+function pinned_array(::Type{T}, dims::Int...) where {T}
+    nbytes = sizeof(T) * prod(dims)
+    nbytes == 0 && return zeros(T, dims...)
+    sz = _size_class(nbytes)
+    ptr = lock(_pool_lock) do
+        v = get(_pool, sz, nothing)
+        (v === nothing || isempty(v)) ? C_NULL : pop!(v)
+    end
+    if ptr == C_NULL
+        ptr = ccall((:lto_host_alloc, lib), Ptr{Cvoid}, (Csize_t,), sz)
+        ptr == C_NULL && return zeros(T, dims...)          # pinned memory exhausted: a pageable array is still correct
+    end
+    a = unsafe_wrap(Array, Ptr{T}(ptr), dims; own = false)
+    finalizer(a) do _
+        lock(_pool_lock) do
+            push!(get!(_pool, sz, Ptr{Cvoid}[]), ptr)
+        end
+    end
+    a                                                       # contents unspecified: every caller below has the library overwrite all of it
+end
+
 # ---- direct: replaces defectCalc (multiShoot_CRTBP_direct.jl:66-109)
 function defectCalc(X_all::Matrix{Float64}, u_all::Matrix{Float64}, t_TU::Vector{Float64}, nstate, n_nodes, nsteps, Isp, MU, DU, TU)
     p = DirectParams(); p.MU, p.DU, p.TU, p.Isp = MU, DU, TU, Isp
-    defect = zeros(nstate, n_nodes - 1); errors = zeros(n_nodes - 1); status = zeros(Int32, n_nodes - 1)
+    defect = pinned_array(Float64, nstate, n_nodes - 1); errors = pinned_array(Float64, n_nodes - 1); status = pinned_array(Int32, n_nodes - 1)
     GC.@preserve X_all u_all t_TU defect errors status check(ccall((:lto_direct_defect_traj, lib), Cint,
         (Ptr{Cvoid}, Ref{DirectParams}, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
         handle[], p, 1, n_nodes, nstate, nsteps, X_all, u_all, t_TU, defect, errors, status))
@@ -36,8 +64,8 @@ end
 function jacobianCalc(X_all, u_all, t_TU, nstate, n_nodes, nsteps, Isp, MU, DU, TU)
     p = DirectParams(); p.MU, p.DU, p.TU, p.Isp = MU, DU, TU, Isp
     nvar = 2 * (nstate + 3)
-    defect = zeros(nstate, n_nodes - 1); errors = zeros(n_nodes - 1); status = zeros(Int32, n_nodes - 1)
-    blocks = zeros(nstate, nvar, n_nodes - 1)              # block i == Jac_temp[(i-1)n+1 : i n, :]  (:139-140)
+    defect = pinned_array(Float64, nstate, n_nodes - 1); errors = pinned_array(Float64, n_nodes - 1); status = pinned_array(Int32, n_nodes - 1)
+    blocks = pinned_array(Float64, nstate, nvar, n_nodes - 1)              # block i == Jac_temp[(i-1)n+1 : i n, :]  (:139-140)
     GC.@preserve X_all u_all t_TU defect errors status blocks check(ccall((:lto_direct_defect_jac_traj, lib), Cint,
         (Ptr{Cvoid}, Ref{DirectParams}, Int64, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}),
         handle[], p, 1, n_nodes, nstate, nsteps, X_all, u_all, t_TU, defect, errors, status, blocks))
@@ -59,14 +87,14 @@ function iparams(params)
     p
 end
 function defectCalc_indirect(XC_all::Matrix{Float64}, t_TU::Vector{Float64}, nstate, n_nodes, params)
-    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1)
+    m = 2 * nstate; defect = pinned_array(Float64, m, n_nodes - 1); status = pinned_array(Int32, n_nodes - 1)
     GC.@preserve XC_all t_TU defect status check(ccall((:lto_indirect_defect_traj, lib), Cint,
         (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
         handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL))
     (defect, zeros(n_nodes - 1))                                                          # errors == 0 (:85)
 end
 function jacobianCalc_indirect(XC_all, t_TU, nstate, n_nodes, params)
-    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1); phi = zeros(m, m, n_nodes - 1)
+    m = 2 * nstate; defect = pinned_array(Float64, m, n_nodes - 1); status = pinned_array(Int32, n_nodes - 1); phi = pinned_array(Float64, m, m, n_nodes - 1)
     GC.@preserve XC_all t_TU defect status phi check(ccall((:lto_indirect_defect_jac_traj, lib), Cint,
         (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
         handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL, phi))
@@ -88,7 +116,7 @@ function densify(XC_all::Matrix{Float64}, t_TU::Vector{Float64}, params, n_desir
     keep = seg .<= N - 1                                                                  # t < t_TU[end] (:64)
     seg = vcat(seg[keep], N - 1); t1 = vcat(t_dense[keep], t_TU[end])                     # + the last segment's end state (:94-97)
     x0 = XC_all[:, seg]; t0 = t_TU[seg]; n = length(seg)
-    xend = zeros(m, n); status = zeros(Int32, n)
+    xend = pinned_array(Float64, m, n); status = pinned_array(Int32, n)
     GC.@preserve x0 t0 t1 xend status check(ccall((:lto_indirect_defect, lib), Cint,
         (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
         handle[], iparams(params), n, m, x0, t0, t1, C_NULL, C_NULL, C_NULL, xend, status, C_NULL))
@@ -98,7 +126,7 @@ end
 # ---- indirect: the linear step of optimizeTraj_OLS (multiShoot_CRTBP_indirect.jl:181-182, :207) on the device.
 # `phi` is what jacobianCalc_blocks returns (m x m x (n_nodes-1)); Jac_full is never formed.
 function jacobianCalc_blocks(XC_all, t_TU, nstate, n_nodes, params)
-    m = 2 * nstate; defect = zeros(m, n_nodes - 1); status = zeros(Int32, n_nodes - 1); phi = zeros(m, m, n_nodes - 1)
+    m = 2 * nstate; defect = pinned_array(Float64, m, n_nodes - 1); status = pinned_array(Int32, n_nodes - 1); phi = pinned_array(Float64, m, m, n_nodes - 1)
     GC.@preserve XC_all t_TU defect status phi check(ccall((:lto_indirect_defect_jac_traj, lib), Cint,
         (Ptr{Cvoid}, Ref{IndirectParams}, Int64, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
         handle[], iparams(params), 1, n_nodes, m, XC_all, t_TU, C_NULL, C_NULL, defect, status, C_NULL, phi))

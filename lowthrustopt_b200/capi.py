@@ -178,10 +178,10 @@ def _per_unit(name, a, n):
 
 
 def _out(o, key, shape, dtype=np.float64):
-    """A caller-supplied output array (e.g. pinned memory) or a fresh one; the library writes prod(shape) items into it."""
+    """A caller-supplied output array or a fresh one from the pinned pool; the library writes prod(shape) items into it."""
     a = o.get(key)
     if a is None:
-        return np.empty(shape, dtype=dtype)
+        return _POOL.empty(shape, dtype)
     if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or a.shape != tuple(shape) or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
         raise ValueError("out[%r] must be a writeable C-contiguous %s array of shape %s" % (key, np.dtype(dtype).name, tuple(shape)))
     return a
@@ -211,6 +211,73 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+class _PoolBlock:
+    """A pinned block on loan from the pool: goes back when the last numpy view of it is garbage-collected."""
+    __slots__ = ("pool", "ptr", "size")
+
+    def __init__(self, pool, ptr, size):
+        self.pool, self.ptr, self.size = pool, ptr, size
+
+    def __del__(self):
+        try:
+            self.pool._give_back(self.ptr, self.size)
+        except Exception:
+            pass
+
+
+class PinnedPool:
+    """Result arrays of the host-buffer wrappers come out of pinned (page-locked) memory: the device-to-host copy of the Jacobian
+    blocks -- 87 % of a config-3 call's bytes -- then runs asynchronously at the PCIe rate and overlaps the kernels, where a copy
+    into pageable numpy memory is staged by the driver and serialises the pipeline (bench.py `e2e_pageable`).  cudaHostAlloc is
+    expensive (milliseconds), so blocks are recycled: size classes of powers of two, at most `cap_bytes` parked.  This is what
+    julia/lto_b200.jl does for the arrays it allocates itself."""
+
+    def __init__(self, cap_bytes=2 << 30):
+        self.cap, self.parked, self.free = int(cap_bytes), 0, {}
+
+    @staticmethod
+    def _cls(nbytes):
+        n = 4096
+        while n < nbytes:
+            n <<= 1
+        return n
+
+    def _give_back(self, ptr, size):
+        if self.parked + size > self.cap:
+            lib().lto_host_free(ptr)
+            return
+        self.free.setdefault(size, []).append(ptr)
+        self.parked += size
+
+    def empty(self, shape, dtype=np.float64):
+        shape = tuple(int(x) for x in np.atleast_1d(shape))
+        dt = np.dtype(dtype)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = count * dt.itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype=dt)
+        size = self._cls(nbytes)
+        lst = self.free.get(size)
+        if lst:
+            ptr = lst.pop(); self.parked -= size
+        else:
+            ptr = lib().lto_host_alloc(size)
+            if not ptr:
+                return np.empty(shape, dtype=dt)          # pinned memory exhausted: a pageable array is still correct
+        buf = (C.c_char * nbytes).from_address(ptr)
+        buf._block = _PoolBlock(self, ptr, size)            # lives as long as any view of the array does
+        return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+    def trim(self):
+        for size, lst in self.free.items():
+            for ptr in lst:
+                lib().lto_host_free(ptr)
+        self.free, self.parked = {}, 0
+
+
+_POOL = PinnedPool()
 
 
 class Handle:
@@ -310,9 +377,9 @@ class Handle:
         n_traj, n_nodes, ns = X_all.shape
         u_all = _shaped("u_all", u_all, (n_traj, n_nodes, 3)); t_TU = _shaped("t_TU", t_TU, (n_traj, n_nodes))
         n_seg = n_traj * (n_nodes - 1); nv = 2 * (ns + 3)
-        defect = np.empty((n_seg, ns)); errors = np.empty(n_seg); status = np.empty(n_seg, dtype=np.int32)
+        defect = _POOL.empty((n_seg, ns)); errors = _POOL.empty((n_seg,)); status = _POOL.empty((n_seg,), np.int32)
         if jac:
-            J = np.empty((n_seg, nv, ns))
+            J = _POOL.empty((n_seg, nv, ns))
             self._ck(lib().lto_direct_defect_jac_traj(self._h, C.addressof(p), n_traj, n_nodes, ns, int(nsteps), _ptr(X_all),
                                                       _ptr(u_all), _ptr(t_TU), _ptr(defect), _ptr(errors), _ptr(status), _ptr(J)))
             return dict(defect=defect, errors=errors, status=status, jac=J)
@@ -358,9 +425,9 @@ class Handle:
         n_seg = n_traj * (n_nodes - 1)
         tl = _per_unit("thrustLimit", thrustLimit, n_traj)
         rh = _per_unit("rho", rho, n_traj)
-        defect = np.empty((n_seg, nd)); status = np.empty(n_seg, dtype=np.int32); nst = np.empty((n_seg, 2), dtype=np.int32)
+        defect = _POOL.empty((n_seg, nd)); status = _POOL.empty((n_seg,), np.int32); nst = _POOL.empty((n_seg, 2), np.int32)
         if jac:
-            phi = np.empty((n_seg, nd, nd))
+            phi = _POOL.empty((n_seg, nd, nd))
             self._ck(lib().lto_indirect_defect_jac_traj(self._h, C.addressof(p), n_traj, n_nodes, nd, _ptr(XC_all), _ptr(t_TU),
                                                         _ptr(tl), _ptr(rh), _ptr(defect), _ptr(status), _ptr(nst), _ptr(phi)))
             return dict(defect=defect, status=status, nsteps=nst, phi=phi)

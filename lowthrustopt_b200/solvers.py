@@ -51,7 +51,9 @@ class GpuBackend:
 
     # indirect: XC (B, N, m), t (B, N); params = the reference's tuple
     def _ip(self, params, **kw):
-        MU, DU, TU, thrustLimit, mass, td, p, rho = params
+        MU, DU, TU, thrustLimit, mass, td, p, rho = params[:8]
+        if len(params) > 8:                                                # 14-dim extension: the tuple carries Isp as a ninth entry
+            kw.setdefault("Isp", params[8])
         if not (p == 0 or p >= 1):
             raise ValueError("Invalid value of p!")                       # CRTBP_stateCostate_deriv.jl:52
         return capi.indirect_params(thrustLimit=thrustLimit, mass=mass, time_direction=td, p=p, rho=rho, MU_=MU, DU_=DU, TU_=TU, **kw)
@@ -383,6 +385,16 @@ def multiShoot_CRTBP_direct_batch(X_all, u_all, tau1, tau2, t_TU, MU, DU, TU, n_
 
 
 # --------------------------------------------------------------------------- indirect method
+def _end_pins(nstate):
+    """Components held at the first / last node (:141-142, :324-325).  12-dim: the 6 states of both ends.  14-dim ([r v m | lr lv lm]):
+    position, velocity and mass at the start; position, velocity and lm at the end -- the final mass is free (it follows from the
+    control history), and lm, which enters no right-hand side, is fixed by its end value lm(t_f) (any constant offset of lm solves
+    the defect equations, so one value must be held or the band is rank deficient)."""
+    first = list(range(nstate))
+    last = list(range(6)) + ([2 * nstate - 1] if nstate == 7 else [])
+    return first, last
+
+
 def _band_indirect(phi, nstate, N):
     """Band assembly of jacobianCalc (multiShoot_CRTBP_indirect.jl:127-142): phi (N-1, m, m) -> Jac_full."""
     m = 2 * nstate
@@ -391,23 +403,33 @@ def _band_indirect(phi, nstate, N):
     for i in range(N - 1):
         J[i * m:(i + 1) * m, i * m:(i + 1) * m] = phi[i]
         J[i * m:(i + 1) * m, (i + 1) * m:(i + 2) * m] = -eye
-    J[:, :nstate] = 0.0                                                                                   # :141
-    J[:, -2 * nstate:-nstate] = 0.0                                                                       # :142
+    first, last = _end_pins(nstate)
+    J[:, first] = 0.0                                                                                     # :141
+    J[:, [(N - 1) * m + c for c in last]] = 0.0                                                           # :142
     return J
 
 
 def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLimit, plot_yn=False, flag_adjointsOnly=False,
-                              maxIter=50, p=1.0, rho=1.0, backend=None, log=None, device_newton=False):
+                              maxIter=50, p=1.0, rho=1.0, backend=None, log=None, device_newton=False, Isp=2000.0):
     """(XC_all, defect, status_flag) = multiShoot_CRTBP_indirect(...)   (:58-59, :344).
-    device_newton: solve the update on the GPU (lto_indirect_newton) instead of the dense host least squares."""
+    device_newton: solve the update on the GPU (lto_indirect_newton) instead of the dense host least squares.
+
+    XC_all with 12 rows is the reference's system.  With 14 rows ([r v m | lr lv lm], BASELINE configs[1] as north_star words it) the
+    same loop runs on the 14-dim system with mass: nstate = 7, the band blocks are 14 x 14, and the end pins of :324-325 become
+    7-element (`_end_pins`: r, v, m at the first node; r, v and lm at the last -- the final mass is free).  The reference has no such solver -- its loop
+    hard-codes the 12-dim RHS (:258) and 6-element pins -- so this is the same algorithm on the larger system, not a mirror of
+    existing code; `Isp` enters the mass flow (GeneralCode/twoBody_stateCostate_mass_deriv.jl:61)."""
     be = backend or default_backend()
     XC_all = np.array(XC_all, dtype=np.float64); t_TU = np.asarray(t_TU, dtype=np.float64)
     nstate = XC_all.shape[0] // 2; m = 2 * nstate; N = n_nodes
-    if nstate != 6:
-        raise NotImplementedError("the reference's indirect solver hard-codes the 12-dim RHS (:258) and 6-element end pins (:324-325)")
-    params = (MU, DU, TU, thrustLimit, mass0, 1.0, p, rho)                                                # :260
+    if nstate not in (6, 7):
+        raise ValueError("XC_all must have 12 rows (the reference's system) or 14 ([r v m | lr lv lm])")
+    if nstate == 7 and device_newton:
+        raise NotImplementedError("the device-side Newton update (lto_indirect_newton) is 12-dim; the 14-dim loop solves the update on the host")
+    params = (MU, DU, TU, thrustLimit, mass0, 1.0, p, rho) + ((Isp,) if nstate == 7 else ())              # :260
     status_flag = 0
-    state_0 = XC_all[:nstate, 0].copy(); state_f = XC_all[:nstate, -1].copy()
+    pin0, pinf = _end_pins(nstate)
+    state_0 = XC_all[pin0, 0].copy(); state_f = XC_all[pinf, -1].copy()
 
     def defectCalc(XC):
         return be.indirect_defect(XC.T[None], t_TU[None], params)[0].T.copy()
@@ -450,7 +472,7 @@ def multiShoot_CRTBP_indirect(XC_all, t_TU, MU, DU, TU, n_nodes, mass0, thrustLi
             ers = np.sum(dd.reshape(20, -1) ** 2, axis=1)
             alpha = float(alpha_all[np.argmin(ers)])
         XC_all = XC_all + xc_update * alpha                                                               # :304
-        XC_all[:6, 0] = state_0; XC_all[:6, -1] = state_f                                                 # :324-325
+        XC_all[pin0, 0] = state_0; XC_all[pinf, -1] = state_f                                             # :324-325
         defect = defectCalc(XC_all)                                                                       # :328
         er = float(np.max(np.abs(defect)))
         if log is not None:

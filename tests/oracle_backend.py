@@ -39,8 +39,9 @@ class OracleBackend:
 
     @staticmethod
     def _ip(params):
-        MU, DU, TU, thrustLimit, mass, td, p, rho = params
-        return O.iparams(thrustLimit, mass=mass, td=td, p=p, rho=rho, MU_=MU, DU_=DU, TU_=TU)
+        MU, DU, TU, thrustLimit, mass, td, p, rho = params[:8]
+        kw = {"Isp": params[8]} if len(params) > 8 else {}
+        return O.iparams(thrustLimit, mass=mass, td=td, p=p, rho=rho, MU_=MU, DU_=DU, TU_=TU, **kw)
 
     def indirect_defect(self, XC, t, params):
         self.calls += 1

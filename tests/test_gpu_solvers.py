@@ -109,3 +109,22 @@ def test_densify_gpu_vs_oracle(backends):
         assert Dg.shape == (12, 1000) and np.array_equal(tg, tc)
         assert (np.abs(Dg - Dc) / np.maximum(1.0, np.abs(Dc))).max() < 1e-10
         assert np.array_equal(Dg[:, 0], XC[:, 0])                               # a dense time on a node is the node (zero-length span)
+
+
+def test_indirect_14dim_newton_to_convergence_gpu_vs_oracle(backends, oracle):
+    """BASELINE configs[1] as written: state + costate + mass (14-dim) with the 14 x 14 STM, single trajectory, Newton to convergence.
+    The same host loop GPU-backed (K3-14 for the STM pass, K4-14 for every defect evaluation) and oracle-backed: same iteration count,
+    converged trajectories within 1e-8, final mass within 1e-9 relative (north_star)."""
+    from test_solvers_cpu import _guess14
+    gpu, cpu = backends
+    XC0, t, tl = _guess14(oracle)
+    res = {}
+    for name, be in (("gpu", gpu), ("cpu", cpu)):
+        log = []
+        XC, d, st = S.multiShoot_CRTBP_indirect(XC0.copy(), t, MU, DU, TU, 30, 1000.0, tl, False, False, 30, 1.0, 1e-2, backend=be, log=log)
+        res[name] = (XC, st, len(log), log[-1]["er"])
+    (Xg, sg, ng, eg), (Xc, sc, nc, ec) = res["gpu"], res["cpu"]
+    assert sg == sc == 0 and ng == nc and eg <= 1e-10 and ec <= 1e-10
+    scale = np.maximum(1.0, np.abs(Xc))
+    assert (np.abs(Xg - Xc) / scale).max() < TOL_TRAJ
+    assert abs(Xg[6, -1] / Xc[6, -1] - 1.0) < TOL_MASS and np.abs(Xg[6] / Xc[6] - 1.0).max() < TOL_MASS

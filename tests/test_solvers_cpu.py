@@ -200,3 +200,36 @@ def test_bangbang_fixture_is_a_converged_rho_1e4_solution(oracle):
     xt, st = oracle.indirect_prop_ld(XC[:-1], t[:-1], t[1:], oracle.iparams(g["thrustLimit"], p=1.0, rho=1e-4), atol=1e-18, rtol=1e-18,
                                      nthreads=oracle.num_threads())
     assert np.abs(xt - XC[1:]).max() < 5e-8
+
+
+def _guess14(oracle, rho=1e-2, seed=3):
+    """A 14-dim start for the indirect loop ([r v m | lr lv lm], BASELINE configs[1]): the converged 12-dim trajectory of the
+    bang-bang fixture with a mass history propagated segment by segment (so masses and lm are consistent with 12-dim costates that
+    are NOT a 14-dim solution: the thrust acceleration now follows the falling mass), interior costates perturbed."""
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "bangbang_v1.json")) as f:
+        g = json.load(f)
+    XC12 = np.array(g["XC_nodes"]["%g" % rho]).T; t = np.array(g["t_TU"]); N = XC12.shape[1]
+    XC = np.zeros((14, N)); XC[:6] = XC12[:6]; XC[7:13] = XC12[6:12]; XC[6] = 1000.0
+    ip = oracle.iparams(g["thrustLimit"], p=1.0, rho=rho, Isp=2000.0)
+    for i in range(N - 1):
+        xe = oracle.indirect_prop(XC[:, i:i + 1].T.copy(), t[i:i + 1], t[i + 1:i + 2], ip)[0]
+        XC[6, i + 1] = xe[0, 6]; XC[13, i + 1] = xe[0, 13]
+    XC[13] -= XC[13, -1]                                                       # lm(t_f) = 0 is the value held at the last node
+    XC[7:13, 1:-1] += 1e-3 * np.random.default_rng(seed).standard_normal((6, N - 2))
+    return XC, t, g["thrustLimit"]
+
+
+def test_indirect_loop_on_the_14_dim_system(oracle):
+    """BASELINE configs[1] as north_star words it -- state + costate + mass (14-dim), 14 x 14 STM, single trajectory, Newton to
+    convergence -- through the host loop with the oracle backend: converges to the reference's threshold (:280); r, v, m of the first
+    node and r, v, lm of the last stay where they were put (:324-325 with 7-element pins); the final mass is an OUTPUT."""
+    XC0, t, tl = _guess14(oracle)
+    log = []
+    XC, d, st = S.multiShoot_CRTBP_indirect(XC0.copy(), t, MU, DU, TU, 30, 1000.0, tl, False, False, 30, 1.0, 1e-2, backend=OracleBackend(), log=log)
+    assert st == 0 and log[-1]["er"] <= 1e-10 and 2 <= len(log) <= 12
+    assert np.array_equal(XC[:7, 0], XC0[:7, 0]) and np.array_equal(XC[:6, -1], XC0[:6, -1]) and XC[13, -1] == XC0[13, -1]
+    assert 990.0 < XC[6, -1] < 1000.0 and np.all(np.diff(XC[6]) <= 0.0)       # propellant is spent, never gained
+    assert abs(XC[6, -1] - XC0[6, -1]) > 1e-6                                 # ... and the final mass moved: it is solved for, not held
+    with pytest.raises(ValueError):
+        S.multiShoot_CRTBP_indirect(np.zeros((10, 5)), np.linspace(0, 1, 5), MU, DU, TU, 5, 1e3, 0.05, backend=OracleBackend())
