@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline leg")
     ap.add_argument("--chunks", type=int, default=4, help="all-gather / compute overlap chunks of the sharded paths")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process drives --gpus devices through lto_init_devices (the form the Julia drop-in uses): host-buffer calls only, "
+                         "no torch.distributed; prints one JSON line whose value is the end-to-end rate")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="sharded workloads: deliver results to the solver rank by the kernels' own stores into its HBM over NVLink "
                          "peer memory (fused, default) or by a chunked NCCL all-gather")
@@ -166,12 +169,13 @@ def host_threads():
 
 def cpu_variational_pass(batch, n, nthreads):
     """One pass of the SAME MATHS as the GPU path on the host (mode 2): the state and its variational
-    equations in one RKF7(8) integration per leg (dual numbers through ode7_8), instead of the reference's 2(n+3) finite-difference
-    re-propagations.  Direct workloads only -- for the indirect ones the reference algorithm already is this."""
+    equations [Phi | Gamma] in one RKF7(8) integration per leg, structural zeros skipped -- the kernels' own __host__ __device__
+    arithmetic compiled for the host cores (oracle_direct_variational_host) -- instead of the reference's 2(n+3) finite-difference
+    re-propagations.  Direct workloads only -- for the indirect ones the reference algorithm (dual numbers) already is this."""
     from oracle import oracle as O
     sl = {k: v[:n] for k, v in batch.items()}
     t = time.perf_counter()
-    O.direct_jac_var(sl["Xa"], sl["Xb"], sl["ua"], sl["ub"], sl["ta"], sl["tb"], nthreads=nthreads)
+    O.direct_variational_host(sl["Xa"], sl["Xb"], sl["ua"], sl["ub"], sl["ta"], sl["tb"], nthreads=nthreads)
     return time.perf_counter() - t
 
 
@@ -214,7 +218,7 @@ def cpu_baseline(workload, batch, sample, seconds=12.0):
             dv += cpu_variational_pass(batch, n, nthreads); pv += 1
         out["variational"] = {"value": n * pv / dv, "unit": "segment-propagations/s", "cores": nthreads, "kind": "port",
                               "sample": "%d passes over the same %d segments, the GPU path's own maths (state + variational equations in one "
-                                        "RKF7(8) integration per leg, dual numbers in the C++ oracle), %.1f s" % (pv, n, dv)}
+                                        "RKF7(8) integration per leg: the kernels' host-device arithmetic compiled for the host), %.1f s" % (pv, n, dv)}
     return out
 
 
@@ -1016,9 +1020,66 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """One process, N devices, host buffers: lto_init_devices splits every call into contiguous unit ranges, one worker thread and one
+    H2D -> kernel -> D2H pipeline per device, each device copying its slab straight into the caller's arrays (no collective).  This is
+    what `julia/lto_b200.jl` gets when LowThrustOpt is started with several GPUs visible."""
+    from lowthrustopt_b200 import capi
+    wl = args.workload
+    direct = wl.startswith("direct")
+    n_dev = args.gpus
+    n_seg = (args.n_seg or (65536 if direct else 131072)) * n_dev         # weak scaling, like the multi-process default
+    batch = make_batch(wl, n_seg, 0)
+    res = {}
+    for devs in ([0], list(range(n_dev))):
+        h = capi.Handle(devs)
+        pin_in = {k: capi.PinnedBuffer(v.shape) for k, v in batch.items()}
+        for k, v in batch.items():
+            pin_in[k].array[...] = v
+        a_in = {k: b.array for k, b in pin_in.items()}
+        if direct:
+            ns = 7 if wl.startswith("direct7") else 6
+            p = capi.direct_params(mode=capi.LTO_ADAPTIVE if wl.endswith("adaptive") else capi.LTO_FIXED)
+            pin_out = {"defect": capi.PinnedBuffer((n_seg, ns)), "errors": capi.PinnedBuffer((n_seg,)), "status": capi.PinnedBuffer((n_seg,), np.int32),
+                       "jac": capi.PinnedBuffer((n_seg, 2 * (ns + 3), ns))}
+            out = {k: b.array for k, b in pin_out.items()}
+            call = lambda: h.direct(a_in["Xa"], a_in["Xb"], a_in["ua"], a_in["ub"], a_in["ta"], a_in["tb"], nsteps=10, params=p, jac=True, out=out)
+        else:
+            nd = 12 if wl == "indirect12" else 14
+            p = capi.indirect_params(p=1.0, rho=1.0, thrustLimit=0.05)
+            pin_out = {"defect": capi.PinnedBuffer((n_seg, nd)), "status": capi.PinnedBuffer((n_seg,), np.int32), "nsteps": capi.PinnedBuffer((n_seg, 2), np.int32),
+                       "phi": capi.PinnedBuffer((n_seg, nd, nd))}
+            out = {k: b.array for k, b in pin_out.items()}
+            call = lambda: h.indirect(a_in["x0"], a_in["t0"], a_in["t1"], params=p, jac=True, out=out)
+        for _ in range(max(args.warmup, 3)):
+            call()
+        l0 = h.launches
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = call()
+        dt = time.perf_counter() - t0
+        res[len(devs)] = {"value": n_seg * args.steps / dt, "ms_per_step": 1e3 * dt / args.steps, "launches": int(h.launches - l0),
+                          "checksum": float(np.asarray(r["defect"]).sum())}
+        h.close()
+        for b in list(pin_in.values()) + list(pin_out.values()):
+            b.free()
+    one, many = res[1], res[n_dev]
+    line = {"metric": "segment-propagations/s (fp64 state+STM)", "value": many["value"], "unit": "segment-propagations/s", "n_gpus": n_dev,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": many["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "segments_total": n_seg, "parallelism": "ONE process, %d devices through lto_init_devices (host buffers, a worker thread "
+                       "and a copy/compute pipeline per device)" % n_dev},
+            "e2e": {"value": many["value"], "unit": "segment-propagations/s", "timing": "host wall clock around the blocking host-buffer call, pinned buffers"},
+            "same_batch_on_one_device": one, "speedup_over_one_device": many["value"] / one["value"],
+            "identical_results": one["checksum"] == many["checksum"], "gpu_launches": many["launches"], "single_process": True}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.single_process:
+        run_single_process(a)
     else:
         run_ours(a)

@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE ONLY (see lto_oracle.hpp header).  Built by oracle/Makefile
 // into oracle/liblto_oracle.so.  Never linked into liblto_b200.so.
 #include "lto_oracle.hpp"
+#include "../lowthrustopt_b200/csrc/lto_prop_generic.cuh"   // equal-algorithm CPU baseline only (oracle_direct_variational_host)
 #include <cstring>
 #include <vector>
 #ifdef _OPENMP
@@ -267,6 +268,39 @@ int oracle_indirect_prop_jac(long long n_seg, int ndim, const double* x0, const 
         if (ndim == 12) st = indirect_segment_jac<12>(x0 + s * 12, t0[s], t1[s], P, atol, rtol, controller, xend + s * 12, phi + s * 144, &na, &nt);
         else            st = indirect_segment_jac<14>(x0 + s * 14, t0[s], t1[s], P, atol, rtol, controller, xend + s * 14, phi + s * 196, &na, &nt);
         if (status) status[s] = st; if (nacc) nacc[s] = na; if (natt) natt[s] = nt;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Equal-algorithm CPU baseline (mode 2): the GPU path's OWN arithmetic -- state + variational equations
+// [Phi | Gamma] in one RKF7(8) integration per leg, structural zeros skipped (lowthrustopt_b200/csrc/lto_math.cuh and
+// lto_prop_generic.cuh are __host__ __device__) -- compiled for the host cores and run with OpenMP over segments.  A baseline
+// only: nothing here feeds a parity check, and the product never links this file.
+// ---------------------------------------------------------------------------
+int oracle_direct_variational_host(long long n_seg, int n, int nsteps, const double* Xa, const double* Xb, const double* ua,
+                                   const double* ub, const double* ta, const double* tb, const double* dp, double* defect,
+                                   double* jac, int nthreads) {
+    lto::EPConst c; c.mu = dp[0]; c.m1 = 1.0 - dp[0]; c.kthr = dp[2] * dp[2] / dp[1] / 1e3; c.cmdot = dp[2] / (dp[3] * 9.81); c.default_mass = 1000.0;
+    lto::DirectCfg cfg; cfg.mode = 0; cfg.nsteps = nsteps; cfg.tol = 1e-13; cfg.err_norm = 0; cfg.max_attempts = 100000;
+    const int nv = 2 * (n + 3), nc = n + 3;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads > 0 ? nthreads : 1)
+    for (long long s = 0; s < n_seg; ++s) {
+        double xf[7], xb[7], Sf[7 * 10], Sb[7 * 10], ef, eb; int nf, nb;
+        const double tm = 0.5 * (ta[s] + tb[s]);
+        if (n == 7) {
+            lto::ep_leg<7, true>(Xa + s * 7, ua + s * 3, 0, ta[s], tm, cfg, c, xf, Sf, &ef, &nf);
+            lto::ep_leg<7, true>(Xb + s * 7, ub + s * 3, 1, tm, tb[s], cfg, c, xb, Sb, &eb, &nb);
+        } else {
+            lto::ep_leg<6, true>(Xa + s * 6, ua + s * 3, 0, ta[s], tm, cfg, c, xf, Sf, &ef, &nf);
+            lto::ep_leg<6, true>(Xb + s * 6, ub + s * 3, 1, tm, tb[s], cfg, c, xb, Sb, &eb, &nb);
+        }
+        for (int i = 0; i < n; ++i) defect[s * n + i] = xf[i] - xb[i];
+        // block columns [X_a | X_b | u_a | u_b] (multiShoot_CRTBP_direct.jl:125), column-major n x nv
+        double* J = jac + s * (long long)n * nv;
+        for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) { J[j * n + i] = Sf[j * n + i]; J[(n + j) * n + i] = -Sb[j * n + i]; }
+        for (int j = 0; j < 3; ++j) for (int i = 0; i < n; ++i) { J[(2 * n + j) * n + i] = Sf[(n + j) * n + i]; J[(2 * n + 3 + j) * n + i] = -Sb[(n + j) * n + i]; }
+        (void)nc;
     }
     return 0;
 }

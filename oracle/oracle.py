@@ -21,6 +21,7 @@ TU = 375699.81732246041     # src/LowThrustOpt.jl:26
 def build(force=False):
     so = os.path.join(_HERE, "liblto_oracle.so")
     src = [os.path.join(_HERE, f) for f in ("lto_oracle_capi.cpp", "lto_oracle.hpp", "Makefile")]
+    src += [os.path.join(_HERE, "..", "lowthrustopt_b200", "csrc", f) for f in ("lto_prop_generic.cuh", "lto_math.cuh", "lto_tableau.h")]   # equal-algorithm baseline
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -135,6 +136,18 @@ def direct_jac_var(Xa, Xb, ua, ub, ta, tb, nsteps=10, dp=None, mode=0, tol=1e-13
                                 _p(tb), _p(dp), C.c_int(mode), C.c_double(tol), C.c_int(int(with_partials)), _p(defect),
                                 _p(errors), _p(jac), _p(status), C.c_int(nthreads))
     return defect, errors, jac.transpose(0, 2, 1).copy(), status
+
+
+def direct_variational_host(Xa, Xb, ua, ub, ta, tb, nsteps=10, dp=None, nthreads=1):
+    """BASELINE ONLY: the GPU path's own arithmetic (state + variational equations, one integration per leg) on the host cores.
+    Returns defect (n_seg, n), jac (n_seg, n, 2(n+3)) [.., row, col]."""
+    Xa, Xb, ua, ub, ta, tb, n_seg, n = _seg_args(Xa, Xb, ua, ub, ta, tb)
+    dp = dparams() if dp is None else dp
+    nv = 2 * (n + 3)
+    defect = np.zeros((n_seg, n)); jac = np.zeros((n_seg, nv, n))
+    lib().oracle_direct_variational_host(C.c_longlong(n_seg), C.c_int(n), C.c_int(nsteps), _p(Xa), _p(Xb), _p(ua), _p(ub), _p(ta), _p(tb), _p(dp),
+                                         _p(defect), _p(jac), C.c_int(nthreads))
+    return defect, jac.transpose(0, 2, 1).copy()
 
 
 def indirect_prop(x0, t0, t1, ip, thrustLimit=None, rho=None, atol=1e-13, rtol=1e-13, controller=0, nthreads=1, est=-1):
