@@ -249,6 +249,8 @@ constexpr PairTab make_pairs() {
     return t;
 }
 __constant__ PairTab tPairs = make_pairs();
+__constant__ double tB[13][13] = LTO_TAB_B_INIT;
+__constant__ double tG[13][13] = LTO_TAB_G_INIT;
 __constant__ double tB11[13] = {lto_tab::Bf(11, 0), lto_tab::Bf(11, 1), lto_tab::Bf(11, 2), lto_tab::Bf(11, 3), lto_tab::Bf(11, 4), lto_tab::Bf(11, 5), lto_tab::Bf(11, 6),
                                 lto_tab::Bf(11, 7), lto_tab::Bf(11, 8), lto_tab::Bf(11, 9), lto_tab::Bf(11, 10), 0.0, 0.0};
 __constant__ double tC[13] = LTO_TAB_C_INIT;
@@ -502,30 +504,34 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             double sb[6], sg[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) { sb[c] = 0.0; sg[c] = 0.0; }
-            const int n0 = tPairs.start[J], n1 = tPairs.start[J + 1];
             const long long q0 = a.prof ? clock64() : 0;
-            tmem_st_wait();                                              // k_0 .. k_{J-1} are in tensor memory
-            TmemRegs tr;
-            int n = n0;
-            bool inflight = false;
-            if (n < n1 && tPairs.l[n] != J - 1) { tmem_ld6_issue(tk + (unsigned)(KCOLS * tPairs.l[n]), tr); inflight = true; }
+            tmem_st_wait();                                              // k_0 .. k_{J-2} are in tensor memory (k_{J-1} is still in registers)
+            // earlier stages four at a time: tensor-memory addresses and coefficient indices come from the loop counters alone, so the
+            // four loads and their coefficient fetches issue back to back and ONE wait covers them (zero coefficients cost an FMA, not a branch)
 #pragma unroll 1
-            for (; n < n1; ++n) {
-                const int l = tPairs.l[n];
-                const double b = tPairs.b[n], g = tPairs.g[n];
-                double k[6];
-                if (l == J - 1) {                                        // (uniform) the newest one never left the registers
+            for (int l0 = 0; l0 < J - 1; l0 += 4) {
+                TmemRegs tr[4];
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) k[c] = kp[c];
-                } else {
-                    tmem_ld6_wait(tr, k);
-                    inflight = false;
+                for (int u = 0; u < 4; ++u)
+                    if (l0 + u < J - 1) tmem_ld6_issue(tk + (unsigned)(KCOLS * (l0 + u)), tr[u]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (l0 + u < J - 1) {
+                        const double b = tB[J][l0 + u], g = tG[J][l0 + u];
+#pragma unroll
+                        for (int c = 0; c < 6; ++c) {
+                            const double k = __hiloint2double((int)tr[u].r[2 * c + 1], (int)tr[u].r[2 * c]);
+                            sb[c] = fma(b, k, sb[c]); sg[c] = fma(g, k, sg[c]);
+                        }
+                    }
                 }
-                if (n + 1 < n1 && tPairs.l[n + 1] != J - 1) { tmem_ld6_issue(tk + (unsigned)(KCOLS * tPairs.l[n + 1]), tr); inflight = true; }
-#pragma unroll
-                for (int c = 0; c < 6; ++c) { sb[c] = fma(b, k[c], sb[c]); sg[c] = fma(g, k[c], sg[c]); }
             }
-            (void)inflight;
+            if (J > 0) {
+                const double b = tB[J][J - 1], g = tG[J][J - 1];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { sb[c] = fma(b, kp[c], sb[c]); sg[c] = fma(g, kp[c], sg[c]); }
+            }
             const long long q1 = a.prof ? clock64() : 0;
             const double ch = h * tC[J];
             const double R[3] = {fma(h2, sg[0], fma(ch, z[3], z[0])), fma(h2, sg[1], fma(ch, z[4], z[1])), fma(h2, sg[2], fma(ch, z[5], z[2]))};
