@@ -134,7 +134,6 @@ void lto_destroy(lto_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy); cudaStreamSynchronize(h->s_h2d);
     if (h->d_in) cudaFree(h->d_in);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->d_scr) cudaFree(h->d_scr);
@@ -301,38 +300,14 @@ static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_se
 }
 
 // ---------------------------------------------------------------------------
-// Host -> device copies of CALLER inputs.  A Julia / numpy caller holds ordinary pageable arrays; cudaMemcpyAsync from pageable memory
-// is staged by the driver and blocks the calling thread, which serialises the chunk pipeline (H2D of chunk k+1 cannot be enqueued
-// while chunk k's kernel and D2H run).  Pageable sources are therefore copied by the calling thread into the handle's own pinned
-// staging block -- while the GPU works on the chunks already enqueued -- and shipped from there asynchronously.  Pinned or
-// registered sources go straight through.  (Pageable OUTPUT arrays are not staged: bind results to pinned arrays instead --
-// lto_host_alloc; the Python and Julia bindings do it for the arrays they allocate; INTEGRATION.md.)
+// Pageable caller memory (what a Julia / numpy caller holds).  Measured on config 3 (bench.py e2e.pageable): with pageable INPUTS and
+// pinned result arrays the call runs at 73 % of the all-pinned rate (28.8 vs 39.5 M segments/s: the driver stages the 11.5 MB of
+// inputs and blocks the enqueueing thread meanwhile); with pageable RESULT arrays as well at 27 % (the 78 MB of Jacobian blocks are
+// staged too and the copy/compute overlap is gone).  Tried and not kept: staging the inputs through a pinned block of the handle by the
+// calling thread (26.3 M: one core's memcpy is no faster than the driver's staging on these hosts) and by a pool of worker threads
+// (28.2 M, no gain).  What pays is pinned RESULT arrays: lto_host_alloc; the Python and Julia bindings allocate theirs from a pool of
+// such blocks (capi.PinnedPool, julia/lto_b200.jl pinned_array).
 // ---------------------------------------------------------------------------
-static bool is_pageable(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
-    return at.type == cudaMemoryTypeUnregistered;
-}
-static int stage_reserve(lto_handle* h, size_t bytes) {             // before the first copy of a call: room for all of its pageable inputs
-    h->h_stage_used = 0;
-    if (bytes <= h->h_stage_cap) return 0;
-    CK(h, cudaStreamSynchronize(h->s_h2d));
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    h->h_stage = nullptr; h->h_stage_cap = 0;
-    const size_t want = bytes + bytes / 4 + (1u << 20);
-    if (cudaHostAlloc(&h->h_stage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->h_stage = nullptr; return 0; }   // fall back to direct copies
-    h->h_stage_cap = want;
-    return 0;
-}
-static cudaError_t h2d(lto_handle* h, void* dst, const void* src, size_t bytes, bool pageable) {
-    if (pageable && h->h_stage && h->h_stage_used + bytes <= h->h_stage_cap) {
-        char* st = (char*)h->h_stage + h->h_stage_used;
-        h->h_stage_used += al(bytes);
-        memcpy(st, src, bytes);
-        return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, h->s_h2d);
-    }
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->s_h2d);
-}
 
 // ---------------------------------------------------------------------------
 // multi-device handles: contiguous, equal unit ranges (segments, or whole trajectories in the
@@ -413,8 +388,6 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
     double* dJ = want_jac ? (double*)dq : nullptr;
     // ---- H2D goes chunk by chunk on its own stream (below): the first kernel starts after the first chunk's inputs have
     // arrived, and host->device and device->host transfers run on different copy engines
-    const bool pg = is_pageable(Xa);
-    if (pg) { rc = stage_reserve(h, in_bytes + 4096); if (rc) return rc; }
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
     // ---- chunked compute + D2H pipeline
     std::vector<long long> plan;
@@ -425,13 +398,13 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
         const long long r0 = lto_node_a(s0, npt);
         {   // this chunk's input rows (trajectory form: whole trajectories, n_nodes rows each)
             const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
-            CK(h, h2d(h, dXa + r0 * NS, Xa + r0 * NS, nr * NS * 8, pg));
-            CK(h, h2d(h, dua + r0 * 3, ua + r0 * 3, nr * 3 * 8, pg));
-            CK(h, h2d(h, dta + r0, ta + r0, nr * 8, pg));
+            CK(h, cudaMemcpyAsync(dXa + r0 * NS, Xa + r0 * NS, nr * NS * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpyAsync(dua + r0 * 3, ua + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
+            CK(h, cudaMemcpyAsync(dta + r0, ta + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
             if (npt == 0) {
-                CK(h, h2d(h, dXb + r0 * NS, Xb + r0 * NS, nr * NS * 8, pg));
-                CK(h, h2d(h, dub + r0 * 3, ub + r0 * 3, nr * 3 * 8, pg));
-                CK(h, h2d(h, dtb + r0, tb + r0, nr * 8, pg));
+                CK(h, cudaMemcpyAsync(dXb + r0 * NS, Xb + r0 * NS, nr * NS * 8, cudaMemcpyHostToDevice, h->s_h2d));
+                CK(h, cudaMemcpyAsync(dub + r0 * 3, ub + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
+                CK(h, cudaMemcpyAsync(dtb + r0, tb + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
             }
             CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
             CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
@@ -522,10 +495,8 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
     const size_t scr_bytes = want_jac ? al(indirect_cw_scratch_bytes(h->n_sm)) : 0;
     if (want_jac) { rc = ensure(h, &h->d_scr, &h->d_scr_cap, scr_bytes); if (rc) return rc; }
     // per-trajectory / per-segment parameter arrays are small: up front; the node data goes chunk by chunk (below)
-    const bool pg = is_pageable(x0);
-    if (pg) { rc = stage_reserve(h, in_bytes + 4096); if (rc) return rc; }
-    if (tl_arr) CK(h, h2d(h, dTL, tl_arr, prow * 8, pg));
-    if (rho_arr) CK(h, h2d(h, dRH, rho_arr, prow * 8, pg));
+    if (tl_arr) CK(h, cudaMemcpyAsync(dTL, tl_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
+    if (rho_arr) CK(h, cudaMemcpyAsync(dRH, rho_arr, prow * 8, cudaMemcpyHostToDevice, h->s_h2d));
     CK(h, cudaEventRecord(h->ev_t0, h->s_compute));
     std::vector<long long> plan;
     plan_indirect(plan, h->n_sm, n_seg, npt, ndim, want_jac);
@@ -535,10 +506,10 @@ static int indirect_host(lto_handle* h, const lto_indirect_params* p, long long 
         const long long r0 = lto_node_a(s0, npt);
         const long long p0 = lto_traj_of(s0, npt);
         const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
-        CK(h, h2d(h, dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, pg));
-        CK(h, h2d(h, dT0 + r0, t0 + r0, nr * 8, pg));
-        if (npt == 0) CK(h, h2d(h, dT1 + r0, t1 + r0, nr * 8, pg));
-        if (sep_target) CK(h, h2d(h, dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, pg));
+        CK(h, cudaMemcpyAsync(dX + r0 * ND, x0 + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        CK(h, cudaMemcpyAsync(dT0 + r0, t0 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        if (npt == 0) CK(h, cudaMemcpyAsync(dT1 + r0, t1 + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
+        if (sep_target) CK(h, cudaMemcpyAsync(dXT + r0 * ND, x_target + r0 * ND, nr * ND * 8, cudaMemcpyHostToDevice, h->s_h2d));
         CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
         CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
         a.x0 = dX + r0 * ND; a.t0 = dT0 + r0; a.t1 = dT1 + r0; a.x_target = dXT ? dXT + r0 * ND : nullptr;

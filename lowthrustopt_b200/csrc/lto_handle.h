@@ -17,7 +17,6 @@ struct lto_handle {
     cudaEvent_t ev_in, ev_t0, ev_t1;
     cudaEvent_t ev_chunk[8], ev_h2d[8];
     void* d_in; size_t d_in_cap;
-    void* h_stage; size_t h_stage_cap, h_stage_used;   // pinned staging of PAGEABLE caller inputs (grow-only; one region per copy of a call)
     void* d_out; size_t d_out_cap;
     unsigned long long* d_ctr;
     void* d_scr; size_t d_scr_cap;

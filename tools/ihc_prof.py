@@ -25,7 +25,7 @@ for _ in range(2):
 ns = d_ns.cpu().numpy()
 kms = e0.elapsed_time(e1)
 w = h.debug_profile().astype(np.float64)
-grid, NW, NCW, NT = 148, 12, 8, 3
+grid, NW, NCW, NT = 148, 12, int(os.environ.get("IHC_NCW", "8")), 3
 c = w[:grid * NW * 4].reshape(grid, NW, 4)
 pre = w[grid * NW * 4: grid * NW * 4 + grid * NT].reshape(grid, NT)
 co, sw = c[:, :NCW], c[:, NCW:NCW + NT]

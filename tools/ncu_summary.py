@@ -21,6 +21,17 @@ for vals in rows[2:]:
     for k in KEYS:
         if k in d:
             print("%-80s %s %s" % (k, d[k], u.get(k, "")), file=out)
+    try:      # executed FP64 work: thread-level DFMA (2 flops) + DMUL + DADD over the launch (bench.py roofline.executed, profiles/executed.json)
+        cyc = float(d["sm__cycles_elapsed.avg"].replace(",", ""))
+        g = lambda k: float(d[k].replace(",", "")) * cyc
+        fl = 2 * g("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") + g("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed") \
+            + g("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed")
+        print("%-80s %.6e flop per launch" % ("executed_fp64_flops (2 DFMA + DMUL + DADD, thread level)", fl), file=out)
+        for k in ("sm__icc_request_hit_rate.pct", "smsp__warps_eligible.avg.per_cycle_active"):
+            if k in d:
+                print("%-80s %s" % (k, d[k]), file=out)
+    except Exception:
+        pass
     for h in hdr:
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and float(d[h] or 0) > 0.05:
             print("%-80s %s" % (h, d[h]), file=out)
