@@ -259,17 +259,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, n_seg, n_gpus):
+def workload_config(workload, n_seg, n_gpus, gather="peer"):
     if workload in SHARDED:
         desc = {"indirect12_1m": "BASELINE configs[3]: 1,048,576 perturbed indirect-shooting guesses (12-dim reference RHS, adaptive RK8 1e-13, "
-                                 "12x12 STM) in TOTAL, sharded across the GPUs, defects + STM blocks all-gathered to every rank",
+                                 "12x12 STM) in TOTAL, sharded across the GPUs, defects + STM blocks delivered to the solver rank",
                 "continuation": "BASELINE configs[4]: 1,024 trajectories x 200 segments (L2_Anderson_2 ballistic stack, thrustLimit ladder 10 -> 0.05 N); "
                                 "one step = one Newton iteration of multiShoot_CRTBP_indirect = 1 STM pass + 22 defect-only passes (SOC, check, and the "
                                 "20 line-search points as ONE batched pass of 20,480 trial trajectories reduced to sum(defect^2) on the device); "
-                                "results all-gathered to the solver rank"}[workload]
+                                "results delivered to the solver rank"}[workload]
         return {"workload": workload, "description": desc, "segments_total": n_seg, "segments_per_gpu": n_seg // n_gpus,
-                "l2": "not flushed: each pass writes more output than the 126 MB L2 holds", "parallelism": "units interleaved across %d GPU(s) "
-                "in chunks; NCCL all-gather of each chunk overlapped with the next chunk's kernel" % n_gpus}
+                "l2": "not flushed: each pass writes more output than the 126 MB L2 holds",
+                "parallelism": ("contiguous slabs of units on %d GPU(s), one launch per rank and pass; the kernels store their slab into the solver "
+                                "rank's HBM over NVLink peer memory (no collective)" % n_gpus if gather == "peer" else
+                                "units interleaved across %d GPU(s) in chunks; NCCL all-gather of each chunk overlapped with the next chunk's "
+                                "kernel" % n_gpus)}
     desc = {
         "direct7_fixed": "BASELINE configs[2]: synthetic batch of 65,536 direct-method segments per GPU, nstate 7 + STM + control "
                          "sensitivities (7x20 Jacobian block), FIXED RKF7(8) grid nsteps=10 both legs (reference ode7_8 path)",
@@ -342,7 +345,7 @@ def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl, fl
 
 
 def run_sharded(args):
-    """Strong-scaling workloads through lowthrustopt_b200.sharded (units interleaved over the ranks, chunked all-gather)."""
+    """Strong-scaling workloads through lowthrustopt_b200.sharded (results delivered to the solver rank: peer stores, or --gather nccl)."""
     import torch
     import torch.distributed as dist
     from lowthrustopt_b200 import capi, sharded, synthetic as S
@@ -522,7 +525,7 @@ def run_sharded(args):
     gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + (2 * n_seg * (nd * 8 + 12) + n_units * N_ALPHA * 12 if passes_def else 0)
     line = {"metric": "segment-propagations/s (fp64 state+STM)", "value": value, "unit": "segment-propagations/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world), "clocks": clocks,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(wl, n_seg, world, args.gather), "clocks": clocks,
             "passes_per_step": {"stm": 1, "defect_only": passes_def},
             "collective": ({"kind": "none: kernels store their slab into the solver rank's HBM over NVLink peer memory (CUDA IPC), "
                                     "stream-ordered completion flags", "bytes_into_solver_rank_per_step": int(gathered * (world - 1) // world)}
@@ -533,7 +536,7 @@ def run_sharded(args):
                     "h2d_bytes_per_step": int(n_seg * (nd + 2) * 8 if host_call is not None else n_units * n_nodes * (nd + 1) * 8),
                     "d2h_bytes_per_step": int(n_seg * (nd * 8 + nd * nd * 8 + 4 + (8 if host_call is not None else 0))),
                     "timing": ("host wall clock around the blocking lto_indirect_defect_jac call, pinned host buffers" if host_call is not None else
-                               "host wall clock on the solver rank: pinned host inputs -> H2D -> broadcast -> sharded passes + all-gather -> "
+                               "host wall clock on the solver rank: pinned host inputs -> H2D -> broadcast -> sharded passes + delivery to the solver rank -> "
                                "D2H of defect/STM/status into pinned memory; max over ranks")},
             "gpu_launches": int(launches), "roofline": roof, "kernel": args.kernel}
     if rank == 0:

@@ -5,12 +5,15 @@ Tolerances (BASELINE.json north_star): segment end states / defects 1e-10, Jacob
 entries 1e-8, both relative to max(1, |value scale|).  FIXED-mode results come from the same
 discrete map as the oracle, so they are held to much tighter bounds below.
 """
+import os
+
 import numpy as np
 import pytest
 
 from lowthrustopt_b200 import capi, synthetic as S
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 TOL_STATE = 1e-10
 TOL_JAC = 1e-8
@@ -150,6 +153,46 @@ def test_indirect_vs_oracle(nd, law, kernel, lto, oracle):
     r0 = lto.indirect(b["x0"], b["t0"], b["t1"], x_target=xt, params=p, jac=False)
     xo0, so0, _, _ = oracle.indirect_prop(b["x0"], b["t0"], b["t1"], ip, nthreads=oracle.num_threads())
     assert rel(r0["defect"] + xt, xo0) < TOL_STATE
+
+
+_HC_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from lowthrustopt_b200 import capi, synthetic as S
+h = capi.Handle(0)
+out = {}
+for i, law in enumerate(%r):
+    b = S.indirect_batch(4096 + 37, ndim=12, seed=303)
+    b["x0"][::3, 9:12] *= 8.0
+    r = h.indirect(b["x0"], b["t0"], b["t1"], params=capi.indirect_params(**law))
+    out["d%%d" %% i] = r["defect"]; out["p%%d" %% i] = r["phi"]; out["s%%d" %% i] = r["status"]; out["n%%d" %% i] = r["nsteps"]
+np.savez(sys.argv[1], **out)
+h.close()
+"""
+
+
+def test_k3_half_column_kernel_matches_default(lto, oracle, tmp_path):
+    """K3-hc (second-order half-column formulation, LTO_K3=hc) is selected once per process, so it runs in a child
+    process; its results are held to the same bars against the oracle as the default K3's, and to 1e-10 against the default K3."""
+    import subprocess
+    import sys
+    laws = LAWS[:3]
+    f = str(tmp_path / "hc.npz")
+    env = dict(os.environ, LTO_K3="hc")
+    cp = subprocess.run([sys.executable, "-c", _HC_CHILD % (ROOT, laws), f], env=env, capture_output=True, text=True, timeout=300)
+    assert cp.returncode == 0, cp.stderr[-2000:]
+    z = np.load(f)
+    for i, law in enumerate(laws):
+        b = S.indirect_batch(4096 + 37, ndim=12, seed=303)
+        b["x0"][::3, 9:12] *= 8.0
+        r = lto.indirect(b["x0"], b["t0"], b["t1"], params=capi.indirect_params(**law))
+        ip = oracle.iparams(law["thrustLimit"], p=law["p"], rho=law["rho"])
+        xo, Po, so, nao, nto = oracle.indirect_prop_jac(b["x0"], b["t0"], b["t1"], ip, nthreads=oracle.num_threads())
+        sp = np.abs(Po).max(axis=(1, 2), keepdims=True)
+        assert np.all(z["s%d" % i] == 0)
+        assert rel(z["d%d" % i], xo) < TOL_STATE and rel(z["p%d" % i].transpose(0, 2, 1), Po, sp) < TOL_JAC
+        assert rel(z["d%d" % i], r["defect"]) < TOL_STATE
+        assert np.abs(z["n%d" % i][:, 0].astype(np.int64) - r["nsteps"][:, 0]).max() <= 2
 
 
 def test_indirect_vs_golden(lto, golden):

@@ -8,4 +8,5 @@ bash tools/gpu_prof.sh "k_indirect_cw14" r02_k_indirect_cw14 --workload indirect
 LTO_K3=hc bash tools/gpu_prof.sh "k_indirect_hc" r02_k_indirect_hc --workload indirect12
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_direct7_fixed.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_launches.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_indirect12.csv python bench.py --workload indirect12 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_launches_i12.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_indirect14.csv python bench.py --workload indirect14 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_launches_i14.log 2>&1
 ls -la gpurun_out/r02_*
