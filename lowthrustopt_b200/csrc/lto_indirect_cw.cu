@@ -52,12 +52,16 @@ constexpr int NC2 = 9;            // double2 per stage record: U[6] W[6] G[6]
 constexpr int NW = NTILE + NCW;
 constexpr int NTHREADS = 32 * NW;
 
-enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };
+enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };   // F_STORE: the column threads store this slot's STM (only when the state warp could not, see STASH)
 
 // ---- shared-memory plan ------------------------------------------------------
 constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);      // stage records of one tile
 constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
-constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);        // current columns, both halves
+// Candidate stash, slot-major: the 12 columns of a slot are 1152 contiguous bytes in the output's own layout (column-major 12 x 12), so the
+// state warp sends a finished segment's STM as ONE bulk store (full packets when `phi` is NVLink peer memory of the solver rank).  Slot stride
+// 1168 B: 16-byte aligned for the bulk copy, and the 128-bit accesses of a quarter-warp (8 slots of one column) fall into 32 different banks.
+constexpr int STASH_STRIDE = ND * ND + 2;
+constexpr size_t CUR_BYTES = (size_t)TS * STASH_STRIDE * sizeof(double);
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot
 constexpr size_t XN_BYTES = (size_t)2 * ND * TS * sizeof(double);          // the state x and its candidate (double buffer; keeps 24 registers free in the state warps)
 constexpr int NXW = ND + 6;                                                // next-segment stash: x0, t0, tf, aL, 1/rho, aL/(4 rho), h0
@@ -289,7 +293,7 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 const int slot = hf * HS + (lane & (HS - 1));
                 const int2 hc = S.hctl[slot];
                 const double h = S.hval[slot];
-                double* sc = S.cur + (size_t)hf * ND * NCT + ct;
+                double2* sc = reinterpret_cast<double2*>(S.cur + (size_t)slot * STASH_STRIDE + col * ND);
                 double* sn = cand_base + (size_t)(t * 2 + hf) * ND * NCT;
                 // The CANDIDATE of the previous attempt lives in shared memory (sc), the CURRENT column (last accepted value) in
                 // the L2-resident scratch (sn): an accepted step -- 99.7 % of them -- reads shared memory and refreshes the
@@ -297,7 +301,10 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 double p[ND];
                 if (hc.x & F_ACCEPT) {
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) { p[i] = sc[i * NCT]; __stcg(sn + i * NCT, p[i]); }
+                    for (int i = 0; i < ND; i += 2) {
+                        const double2 v = sc[i >> 1];
+                        p[i] = v.x; p[i + 1] = v.y; __stcg(sn + i * NCT, v.x); __stcg(sn + (i + 1) * NCT, v.y);
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < ND; ++i) p[i] = __ldcg(sn + i * NCT);
@@ -323,11 +330,14 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 double pn[ND];
                 const double es = col_attempt<JOINT>(p, h, w2, S.rec + slot, S.bar_full, visit & 1, atol, rtol, pn);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) sc[i * NCT] = pn[i];
+                for (int i = 0; i < ND; i += 2) sc[i >> 1] = make_double2(pn[i], pn[i + 1]);
                 if (JOINT) S.errp[col * TS + slot] = es;
             }
             if (done) alive &= ~(1u << t);
-            else { mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += 2; }
+            else {
+                fence_proxy_async();                                    // the stash may leave through the async proxy (state warp's bulk store)
+                mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += 2;
+            }
         }
         ++visit;
     }
@@ -547,6 +557,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     const unsigned fullmask = 0xffffffffu;
     const double atol = a.cfg.atol, rtol = a.cfg.rtol;
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
+    const bool bulk = (reinterpret_cast<uintptr_t>(a.phi) & 15u) == 0;
     int xi = 0;                                                           // which half of the double buffer holds x
     double* const xbuf = S.xn + slot;
 #pragma unroll
@@ -611,7 +622,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             if (nan && status == 0) status = LTO_ST_NAN;
             if (a.status) a.status[seg] = status;
             if (a.nsteps_out) { a.nsteps_out[2 * seg] = na; a.nsteps_out[2 * seg + 1] = nt; }
-            flags |= F_STORE; store_seg = (int)seg;
+            // column j of ForwardDiff.jacobian(f, x0) (:121) is the slot's stash row j: after an accepted last step the stash IS the STM
+            if (bulk && (flags & F_ACCEPT)) bulk_store(a.phi + seg * (long long)(ND * ND), smem_u32(S.cur + (size_t)slot * STASH_STRIDE), ND * ND * sizeof(double));
+            else flags |= F_STORE;                                      // ended in error (the last accepted columns are in the L2 scratch), or unaligned `phi`
+            store_seg = (int)seg;
             active = false;
         }
         auto take_successor = [&]() {                                    // the successor prepared by prepare_next()
@@ -637,6 +651,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
             S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags, store_seg);
             if (lane == 0) *S.tile_done = 1;
             mbar_arrive(S.bar_full);
+            bulk_store_wait_all();                                       // the last bulk stores must have completed before the CTA retires
             break;
         }
         // ---- one attempted step (13 stages); a fresh slot first picks its initial step
@@ -664,6 +679,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
 #pragma unroll
             for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
         }
+        bulk_store_wait_read();                                          // the column warps overwrite the stash in this visit
         if (!STAGE_PIPE) mbar_arrive(S.bar_full);                        // the whole attempt's record
         c_work += clock64() - c2;
         have = true; ++visit;

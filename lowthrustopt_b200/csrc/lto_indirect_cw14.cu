@@ -40,7 +40,10 @@ enum { F_ACCEPT = 1, F_STORE = 2, F_RESET = 4, F_ACTIVE = 8 };
 constexpr int NSS = 4;            // double2 per published stage STATE: (r0,r1) (r2,lv0) (lv1,lv2) (m,-)
 constexpr size_t SST_BYTES = (size_t)13 * NSS * TS * sizeof(double2);       // stage states of one tile (state warp -> column warps)
 constexpr size_t HDR_BYTES = (size_t)TS * (4 * sizeof(double) + sizeof(int2));   // h, tk, 1/rho, 1/(4 rho), {flags, segment}
-constexpr size_t CUR_BYTES = (size_t)2 * ND * NCT * sizeof(double);          // candidate columns, both half-phases
+// Candidate stash, slot-major (as in K3): a slot's 14 columns are 1568 contiguous bytes in the output's layout, so the state warp sends a finished
+// segment's STM as ONE bulk store.  Slot stride 1584 B: 16-byte aligned, and a quarter-warp's 128-bit accesses fall into 32 different banks.
+constexpr int STASH_STRIDE = ND * ND + 2;
+constexpr size_t CUR_BYTES = (size_t)TS * STASH_STRIDE * sizeof(double);
 constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);
 constexpr size_t XN_BYTES = (size_t)2 * ND * TS * sizeof(double);
 constexpr size_t TILE_BYTES = SST_BYTES + HDR_BYTES + CUR_BYTES + ERR_BYTES + XN_BYTES;
@@ -416,12 +419,15 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 const int slot = hf * HS + (lane & (HS - 1));
                 const int2 hc = S.hctl[slot];
                 const double h = S.hval[slot];
-                double* sc = S.cur + (size_t)hf * ND * NCT + ct;       // candidate of the previous attempt (shared memory)
+                double2* sc = reinterpret_cast<double2*>(S.cur + (size_t)slot * STASH_STRIDE + col * ND);   // candidate of the previous attempt (shared memory)
                 double* sn = cur_base + (size_t)(t * 2 + hf) * ND * NCT;
                 double p[ND];
                 if (hc.x & F_ACCEPT) {                                 // an accepted step reads shared memory and refreshes the L2 copy
 #pragma unroll
-                    for (int i = 0; i < ND; ++i) { p[i] = sc[i * NCT]; __stcg(sn + i * NCT, p[i]); }
+                    for (int i = 0; i < ND; i += 2) {
+                        const double2 v = sc[i >> 1];
+                        p[i] = v.x; p[i + 1] = v.y; __stcg(sn + i * NCT, v.x); __stcg(sn + (i + 1) * NCT, v.y);
+                    }
                 } else {                                               // a rejected one reloads the last accepted column
 #pragma unroll
                     for (int i = 0; i < ND; ++i) p[i] = __ldcg(sn + i * NCT);
@@ -447,12 +453,15 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 double pn[ND];
                 const double es = col_attempt<JOINT>(p, h, w2, lin + (lane & (HS - 1)), atol, rtol, pn);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) sc[i * NCT] = pn[i];
+                for (int i = 0; i < ND; i += 2) sc[i >> 1] = make_double2(pn[i], pn[i + 1]);
                 if (JOINT) S.errp[col * TS + slot] = es;
                 LTO_ICW14_LOCKSTEP();                                  // all reads of the records done before the next phase rewrites them
             }
             if (done) alive &= ~(1u << t);
-            else { mbar_arrive(S.bar_done); n_work += 2; }
+            else {
+                fence_proxy_async();                                   // the stash may leave through the async proxy (state warp's bulk store)
+                mbar_arrive(S.bar_done); n_work += 2;
+            }
         }
         ++visit;
     }
@@ -555,6 +564,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
         for (int i = 0; i < ND; ++i) { xb[i * TS] = (i == 6) ? 1.0 : 0.0; xb[(ND + i) * TS] = (i == 6) ? 1.0 : 0.0; }
     }
     bool exhausted = false;
+    const bool bulk = (reinterpret_cast<uintptr_t>(a.phi) & 15u) == 0;
     unsigned alive = (1u << NTILE) - 1u;
     long long c_wait = 0, c_work = 0, c_pre = 0, n_att = 0;
     const long long c_begin = clock64();
@@ -613,7 +623,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
                 if (nan && c.status == 0) c.status = LTO_ST_NAN;
                 if (a.status) a.status[c.seg] = c.status;
                 if (a.nsteps_out) { a.nsteps_out[2 * c.seg] = c.na; a.nsteps_out[2 * c.seg + 1] = c.nt; }
-                flags |= F_STORE; store_seg = (int)c.seg;
+                // after an accepted last step the slot's stash IS the STM (column-major, :121): one bulk store; otherwise the column threads store
+                if (bulk && (flags & F_ACCEPT)) bulk_store(a.phi + c.seg * (long long)(ND * ND), smem_u32(S.cur + (size_t)slot * STASH_STRIDE), ND * ND * sizeof(double));
+                else flags |= F_STORE;
+                store_seg = (int)c.seg;
                 c.active = false;
             }
             bool fresh = false;
@@ -679,12 +692,14 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int lane, unsi
 #pragma unroll
                 for (int i = 0; i < ND; ++i) xc[i * TS] = xn[i];
             }
+            bulk_store_wait_read();                                     // the column warps overwrite the stash in this visit
             mbar_arrive(S.bar_full);
             c_work += clock64() - c2; ++n_att;
             c.have = true; ++c.visit;
             ctl[t] = c;
         }
     }
+    bulk_store_wait_all();                                              // the last bulk stores must have completed before the CTA retires
     if (a.prof && lane == 0) {
         unsigned long long* o = a.prof + (size_t)blockIdx.x * NW * 4;
         o[0] = c_work; o[1] = c_wait; o[2] = n_att; o[3] = clock64() - c_begin;
