@@ -28,6 +28,7 @@ import json; d=json.loads(open('$O/single_n$N.json').read().strip().splitlines()
     single_indirect) timeout 300 python bench.py --gpus $N --single-process --workload indirect12 --steps 5 --warmup 3 > $O/single_indirect12_n$N.json 2> $O/single_indirect12_n$N.err
             python -c "
 import json; d=json.loads(open('$O/single_indirect12_n$N.json').read().strip().splitlines()[-1]); print('single_indirect12_n$N', d['value'], 'one device', d['same_batch_on_one_device']['value'], 'speedup', d['speedup_over_one_device'], 'identical', d['identical_results'])" ;;
+    incast) timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/nvlink_incast.py > $O/incast_n$N.json 2> $O/incast_n$N.err; tail -1 $O/incast_n$N.json ;;
     *) run $N ${w}_n$N --workload $w --steps 5 --warmup 3 --no-cpu-baseline ;;
   esac
 done
