@@ -298,7 +298,7 @@ def dist_setup():
     return world, rank, local
 
 
-def executed_flops(wl, units_per_launch, kernel_ms, peak):
+def executed_flops(wl, units_per_launch, kernel_ms, peak, attempted=None):
     """What ncu counted for the dominant kernel of this workload (profiles/executed.json: thread-level DFMA/DMUL/DADD executed per
     unit and FP64-pipe-active %, from the committed --set full capture of the same build) next to the algorithmic figure: the
     achieved rate in EXECUTED flops and its fraction of the measured peak.  None when no capture is on file for the workload."""
@@ -309,12 +309,17 @@ def executed_flops(wl, units_per_launch, kernel_ms, peak):
         e = None
     if not e:
         return None
-    ach = e["flops_per_unit"] * units_per_launch / (kernel_ms * 1e-3) / 1e12
-    return {"flops_per_unit": e["flops_per_unit"], "achieved": ach, "frac": ach / (peak / 1e12), "fp64_pipe_active_pct": e.get("fp64_pipe_active_pct"),
+    per_unit = e["flops_per_unit"]
+    if e.get("attempted_steps_per_unit"):                      # adaptive kernels: the capture's count scales with the attempted steps of THIS batch
+        if attempted is None:
+            return None
+        per_unit = per_unit / e["attempted_steps_per_unit"] * attempted
+    ach = per_unit * units_per_launch / (kernel_ms * 1e-3) / 1e12
+    return {"flops_per_unit": per_unit, "achieved": ach, "frac": ach / (peak / 1e12), "fp64_pipe_active_pct": e.get("fp64_pipe_active_pct"),
             "source": e.get("source")}
 
 
-def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl, flops_counted=None):
+def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl, flops_counted=None, attempted=None):
     peak_burst, _ = h.fp64_peak_probe(2048)
     peak_sust, ms_p = h.fp64_peak_probe(200000)
     achieved = flops_unit * units_per_launch / (kernel_ms * 1e-3) / 1e12
@@ -340,7 +345,7 @@ def fp64_roofline(h, flops_unit, units_per_launch, kernel_ms, bytes_unit, wl, fl
             "flops_source": "profiles/flops_per_unit.json (tools/flopcount/count.py: the kernels' host-device arithmetic compiled with a counting "
                             "scalar); used = min(SURVEY 8(d) figure, every counted formulation)",
             "flops_per_unit_counted": flops_counted,
-            "executed": executed_flops(wl, units_per_launch, kernel_ms, peak_sust),
+            "executed": executed_flops(wl, units_per_launch, kernel_ms, peak_sust, attempted),
             "hbm": {"algorithmic_bytes_per_unit": bytes_unit, "achieved_gbs": gbs, "peak_gbs": hbm, "frac": (gbs / hbm) if hbm else None}}
 
 
@@ -519,7 +524,7 @@ def run_sharded(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
     roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, units_per_launch, kernel_ms, BYTES_PER_SEG[nd], "indirect12",
-                         FLOPS_COUNTED[nd] * attempted)
+                         FLOPS_COUNTED[nd] * attempted, attempted)
     roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
     roof["kernel"] = "k_indirect_cw (the STM pass); launches of %d segments" % units_per_launch
     gathered = n_seg * (nd * 8 + nd * nd * 8 + 12) + (2 * n_seg * (nd * 8 + 12) + n_units * N_ALPHA * 12 if passes_def else 0)
@@ -769,7 +774,7 @@ def run_solve(args):
     nwt_ms = timed(lambda: h.indirect_newton_dev(T, n_nodes, 0, d_phi.data_ptr(), d_def.data_ptr(), d_upd.data_ptr()))
     nst = d_ns.cpu().numpy()
     attempted = float(nst[:, 1].mean()); accepted = float(nst[:, 0].mean())
-    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, T * spu, stm_ms, BYTES_PER_SEG[nd], "indirect12", FLOPS_COUNTED[nd] * attempted)
+    roof = fp64_roofline(h, FLOPS_PER_STEP_INDIRECT[nd] * attempted, T * spu, stm_ms, BYTES_PER_SEG[nd], "indirect12", FLOPS_COUNTED[nd] * attempted, attempted)
     roof["attempted_steps_per_segment"] = attempted; roof["accepted_steps_per_segment"] = accepted
     roof["kernel"] = "k_indirect_cw (the STM pass of every iteration); launches of %d segments" % (T * spu)
     # Newton update: HBM-side accounting (factor rows written once, read once; Phi and defects read once; update written once)
@@ -978,7 +983,7 @@ def run_ours(args):
                     "unit": "segment-propagations/s"}
     # ---- FP64 peak, measured in the same run on the same device (MEASURED_PEAKS.json has no FP64 figure)
     per_gpu_ms = float(np.mean(times))
-    roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl, flops_counted)
+    roof = fp64_roofline(h, flops_unit, n_seg, per_gpu_ms, bytes_unit, wl, flops_counted, attempted)
     if wl.endswith("adaptive"):
         # the direct entry points do not return step counts, so the algorithmic FLOPs of an ADAPTIVE pass are not known here
         roof["achieved"] = None; roof["frac"] = None; roof["flops_per_unit"] = None

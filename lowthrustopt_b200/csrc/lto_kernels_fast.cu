@@ -11,6 +11,8 @@ cudaError_t launch_indirect_cw(const IndirectArgs& a, int ndim, cudaStream_t st,
 cudaError_t launch_indirect_cw14(const IndirectArgs& a, cudaStream_t st, int* n_launch);
 cudaError_t launch_indirect_hc(const IndirectArgs& a, cudaStream_t st, int* n_launch);
 size_t indirect_hc_scratch_bytes(int n_sm);
+cudaError_t launch_indirect_wl(const IndirectArgs& a, cudaStream_t st, int* n_launch);
+size_t indirect_wl_scratch_bytes(int n_sm);
 size_t indirect_cw14_scratch_bytes(int n_sm);
 size_t indirect_cwv2_scratch_bytes(int n_sm);
 
@@ -18,24 +20,37 @@ cudaError_t launch_direct_fast(const DirectArgs& a, int nstate, cudaStream_t st,
     return launch_direct_cw(a, nstate, st, n_launch);
 }
 
-// LTO_K3=hc selects the half-column layout of round 2 (lto_indirect_hc.cu: second-order variables, one thread per 3-vector Nystrom
-// half-column, 12 warps with setmaxnreg, three tiles in flight).  Bit-for-bit parity with the default is NOT expected (different
-// variables, same controller); it passes the same parity tests.  Default stays the column-per-thread kernel until the half-column
-// one is faster on the bench (DESIGN.md section 4 has both sets of numbers).
-static bool use_old_k3() {
+// Three layouts of the 12-dim STM kernel exist (DESIGN.md section 4 has the numbers of each):
+//   cw  lto_indirect_cw.cu  one thread per STM column, state warps + column warps, two tiles            (round 1)
+//   hc  lto_indirect_hc.cu  second-order variables, one thread per half-column, setmaxnreg, three tiles   (round 2, not faster)
+//   wl  lto_indirect_wl.cu  half-columns, every warp owns 8 segment slots outright: no roles, no protocol (round 2)
+// LTO_K3=cw|hc|wl selects one; bit-for-bit parity between them is NOT expected (different variables, same controller), all pass the
+// same parity tests.  The joint error norm is the only one hc / wl implement for wl; other configurations run on cw.
+enum { K3_CW = 0, K3_HC = 1, K3_WL = 2 };
+#ifndef LTO_K3_DEFAULT
+#define LTO_K3_DEFAULT K3_CW
+#endif
+static int k3_layout() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("LTO_K3"); v = (e && strcmp(e, "hc") == 0) ? 0 : 1; }
-    return v == 1;
+    if (v < 0) {
+        const char* e = getenv("LTO_K3");
+        v = !e ? LTO_K3_DEFAULT : strcmp(e, "hc") == 0 ? K3_HC : strcmp(e, "wl") == 0 ? K3_WL : strcmp(e, "cw") == 0 ? K3_CW : LTO_K3_DEFAULT;
+    }
+    return v;
 }
 
 cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t st, int* n_launch) {
     if (ndim == 14) return launch_indirect_cw14(a, st, n_launch);
-    if (a.phi != nullptr && !use_old_k3()) return launch_indirect_hc(a, st, n_launch);
+    if (a.phi != nullptr && a.cfg.controller == 0) {
+        const int k = k3_layout();
+        if (k == K3_HC) return launch_indirect_hc(a, st, n_launch);
+        if (k == K3_WL && a.cfg.err_norm != 0) return launch_indirect_wl(a, st, n_launch);
+    }
     return launch_indirect_cw(a, ndim, st, n_launch);
 }
 
 size_t indirect_cw_scratch_bytes(int n_sm) {
-    return std::max(indirect_hc_scratch_bytes(n_sm), std::max(indirect_cwv2_scratch_bytes(n_sm), indirect_cw14_scratch_bytes(n_sm)));
+    return std::max(std::max(indirect_hc_scratch_bytes(n_sm), indirect_wl_scratch_bytes(n_sm)), std::max(indirect_cwv2_scratch_bytes(n_sm), indirect_cw14_scratch_bytes(n_sm)));
 }
 
 }  // namespace lto

@@ -5,10 +5,11 @@ import json, os, re, sys
 ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 # workload -> (summary file stem, units (segments) per profiled launch)
-MAP = {"direct7_fixed": ("k_direct_cw", 65536), "direct6_fixed": ("k_direct_cw_n6", 65536), "indirect12": ("k_indirect_cw", 131072),
-       "indirect14": ("k_indirect_cw14", 131072), "indirect12_hc": ("k_indirect_hc", 131072)}
+# (adaptive kernels: attempted steps per segment of the profiled batch, bench.py roofline.attempted_steps_per_segment of the same workload)
+MAP = {"direct7_fixed": ("k_direct_cw", 65536, None), "direct6_fixed": ("k_direct_cw_n6", 65536, None), "indirect12": ("k_indirect_cw", 131072, 7.05),
+       "indirect14": ("k_indirect_cw14", 131072, 6.94), "indirect12_hc": ("k_indirect_hc", 131072, 7.05), "indirect12_wl": ("k_indirect_wl", 131072, 7.05)}
 ex, tr = {}, {}
-for wl, (stem, units) in MAP.items():
+for wl, (stem, units, att) in MAP.items():
     f = os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.txt" % (tag, stem))
     if not os.path.exists(f):
         continue
@@ -21,6 +22,8 @@ for wl, (stem, units) in MAP.items():
     ex[wl] = {"flops_per_unit": round(fl / units, 1), "flops_per_launch": fl, "units_per_launch": units,
               "fp64_pipe_active_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
               "source": "profiles/%s_%s_ncu_summary.txt (ncu --set full, one launch; thread-level 2 DFMA + DMUL + DADD)" % (tag, stem)}
+    if att:
+        ex[wl]["attempted_steps_per_unit"] = att
     tr[wl] = int(by)
 ex["_comment"] = ("FP64 work actually executed by the dominant kernel of each workload, from the committed ncu captures; bench.py reports it as "
                   "roofline.executed next to the algorithmic count (profiles/flops_per_unit.json)")
