@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INC = os.path.join(HERE, "..", "include")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "liblto_b200.so")
+OBJ = os.environ.get("LTO_OBJ_DIR") or os.path.join(HERE, "_build")
+LIB = os.environ.get("LTO_LIB_OUT") or os.path.join(HERE, "liblto_b200.so")     # (LTO_LIB_OUT, LTO_EXTRA_SOURCES: tools/experiments/build_variant.sh)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
               "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"] + os.environ.get("LTO_NVCC_EXTRA", "").split()   # (development: -D switches)
@@ -29,7 +29,8 @@ def _nvcc():
 
 
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    extra = [os.path.abspath(f) for f in os.environ.get("LTO_EXTRA_SOURCES", "").split(":") if f]
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")) + extra
 
 
 def _headers():
@@ -57,7 +58,7 @@ def build_lib(force=False, verbose=False):
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-I", INC, "-c", src, "-o", obj]
+        cmd = [nvcc] + ARCH + NVCC_FLAGS + ["-I", INC, "-I", CSRC, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:

@@ -117,7 +117,9 @@ __device__ __forceinline__ void col_stage(K3& K, const double (&p)[3], const dou
 
 // (Measured and switched off: re-converging the 8 column warps a few times per attempt with a named barrier, which kept the round-1
 // kernel's instruction-fetch windows together, costs 18 % here -- the instruction-cache misses came from the state warps' code size.)
-#ifdef LTO_IHC_LOCKSTEP_ON
+#if defined(LTO_IHC_LOCKSTEP_PAIR)        // the two column warps of one SM sub-partition (cw, cw + 4) only: they then share their instruction fetches
+#define LTO_IHC_LOCKSTEP() asm volatile("bar.sync %0, 64;" ::"r"(lsid) : "memory")
+#elif defined(LTO_IHC_LOCKSTEP_ON)
 #define LTO_IHC_LOCKSTEP() asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory")
 #else
 #define LTO_IHC_LOCKSTEP()
@@ -125,8 +127,9 @@ __device__ __forceinline__ void col_stage(K3& K, const double (&p)[3], const dou
 
 template <bool ERR>
 __device__ __forceinline__ double col_attempt(const double (&p)[3], const double (&pd)[3], double h, double w2, const double2* __restrict__ rec,
-                                              int half, double atol, double rtol, double (&pn)[3], double (&pdn)[3]) {
+                                              int half, double atol, double rtol, double (&pn)[3], double (&pdn)[3], int lsid = 1) {
     const double h2 = h * h;
+    (void)lsid;
     const int xoff = half ? 3 * TS : 6 * TS;                            // W for the dlv-half, G for the dr-half
     K3 K;
     LTO_IHC_LOCKSTEP();
@@ -215,7 +218,7 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 if (done) continue;
                 double pn[3], pdn[3];
                 const long long ca = a.prof ? clock64() : 0;
-                double es = col_attempt<JOINT>(p, pd, h, w2, S.rec + slot, half, atol, rtol, pn, pdn);
+                double es = col_attempt<JOINT>(p, pd, h, w2, S.rec + slot, half, atol, rtol, pn, pdn, 1 + (cw & 3));
                 if (a.prof) c_att += clock64() - ca;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) { __stcg(cnd + q * 32, pn[q]); __stcg(cnd + (3 + q) * 32, pdn[q]); }

@@ -188,11 +188,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_wl(const __grid_consta
     long long seg = -1, ia = 0;
     int na = 0, nt = 0, status = 0, par = 0;
     bool active = false, exhausted = false, lastrej = false, fresh = false;
+    long long c_refill = 0, c_state = 0, c_cols = 0, c_dec = 0, n_att = 0, n_refill = 0;     // diagnostics (a.prof)
+    const long long c_begin = clock64();
 
     while (true) {
+        const long long k0 = clock64();
         // ---- refill: every idle slot pulls its next segment from the work queue (lane s8 is the slot's g = 0 lane)
         const bool want = !active && !exhausted;
         if (__any_sync(fullmask, want)) {
+            ++n_refill;
             long long idx = -1;
             if (want && g == 0) idx = (long long)atomicAdd(a.counter, 1ull);
             idx = __shfl_sync(fullmask, idx, s8);
@@ -260,6 +264,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_wl(const __grid_consta
             }
         }
         if (!__any_sync(fullmask, active)) break;
+        const long long k1 = clock64();
+        c_refill += k1 - k0;
 
         // ---- one attempted step of the warp's 8 segments
         bool last = false;
@@ -274,6 +280,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_wl(const __grid_consta
         double es = state_attempt(zp, zpd, hh, a.c, w2, lw, half, csel == 0, ks, rec, atol, rtol, zn, znd);
         if (csel != 0) es = 0.0;                                         // the copy lanes carry the same state: counted once
         __syncwarp();                                                    // the records are complete
+        const long long k2 = clock64();
+        c_state += k2 - k1;
 #pragma unroll 1
         for (int c = 0; c < NPASS; ++c) {
             const int col = 2 * c + csel;
@@ -294,6 +302,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_wl(const __grid_consta
             for (int q = 0; q < 3; ++q) { __stcg(cnd + q * 32, pn[q]); __stcg(cnd + (3 + q) * 32, pdn[q]); }
         }
         fresh = false;
+        const long long k3 = clock64();
+        c_cols += k3 - k2; ++n_att;
 
         // ---- accept / reject, per slot (the slot's four lanes take the same decision from the same sum)
         es += __shfl_xor_sync(fullmask, es, 8);
@@ -370,6 +380,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_indirect_wl(const __grid_consta
             if (finished && bulk && g == 0) bulk_store(a.phi + seg * (long long)(ND * ND), smem_u32(stg), ND * ND * sizeof(double));
             if (finished) active = false;
         }
+        c_dec += clock64() - k3;
+    }
+    if (a.prof && lane == 0) {                                           // [CTA][warp][8]: refill, state pass, column passes, decision + output, attempts, refills, alive
+        unsigned long long* o = a.prof + ((size_t)blockIdx.x * NWARP + warp) * 8;
+        o[0] = c_refill; o[1] = c_state; o[2] = c_cols; o[3] = c_dec; o[4] = n_att; o[5] = n_refill; o[6] = clock64() - c_begin; o[7] = 0;
     }
     bulk_store_wait_all();                                               // the last bulk stores must have completed before the CTA retires
 }

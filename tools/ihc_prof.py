@@ -1,6 +1,7 @@
 """LTO_ICW_PROF=1 python tools/ihc_prof.py [state] : per-warp cycle split of the half-column K3 (lto_indirect_hc.cu)."""
 import os, sys
-os.environ["LTO_ICW_PROF"] = "1"
+os.environ["LTO_ICW_PROF"] = "1"; os.environ.setdefault("LTO_K3", "hc")
+os.environ.setdefault("LTO_B200_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "lib", "liblto_k3x.so"))   # bash tools/experiments/build_variant.sh k3x
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 import torch
