@@ -36,6 +36,8 @@ __device__ __forceinline__ void bulk_store(void* gptr, unsigned smem_addr, unsig
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the N most recent bulk stores of this thread have been read out of shared memory
+template <int N> __device__ __forceinline__ void bulk_store_wait_read_but() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // try_wait with a suspend-time hint: the hardware parks the thread instead of spinning on the issue port

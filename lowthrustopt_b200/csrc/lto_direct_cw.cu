@@ -265,7 +265,11 @@ __device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_til
                     const long long seg0 = tile * 16;
                     double* stage = outs + (size_t)t * (C::OUT_TILE_BYTES / sizeof(double));
                     const bool leader = (col == 0 && lane == 0);
-                    if (leader) bulk_store_wait_read();                          // the previous store from this buffer has been read out
+                    // the previous store from THIS buffer has been read out: it is the oldest of the NTILE stores in flight (one per tile and
+                    // pair, issued in tile order), so the younger ones -- the other tile's, issued a moment ago -- need not be waited for.
+                    // Matters when `jac` is peer memory behind a saturated NVLink port (8 GPUs delivering to one): a store then takes tens
+                    // of microseconds to leave, and waiting for all of them stalled the CTA once per tile.
+                    if (leader) bulk_store_wait_read_but<NTILE - 1>();
                     asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
                     col_store<NS>(stage, cs[t], col, lane);
                     fence_proxy_async();
@@ -502,7 +506,7 @@ __device__ __forceinline__ void column_warp_adapt(const DirectArgs& a, long long
             const long long seg0 = tile * 16;
             double* stage = outs + (size_t)t * (C::OUT_TILE_BYTES / sizeof(double));
             const bool leader = (col == 0 && lane == 0);
-            if (leader) bulk_store_wait_read();
+            if (leader) bulk_store_wait_read_but<NTILE - 1>();
             asm volatile("bar.sync 2, %0;" ::"n"(32 * C::NCOL) : "memory");
             col_store<NS>(stage, cs[t], col, lane);
             fence_proxy_async();

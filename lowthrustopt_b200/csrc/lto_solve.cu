@@ -125,12 +125,17 @@ __global__ void __launch_bounds__(1024) k_scan_active(const int* __restrict__ ac
 }
 
 // rows that stopped iterating leave the work set: their rows go to the caller-ordered result arrays
+// (flag != NULL: a retired row with a non-finite entry is reported as status_flag 2 -- the "over the whole trajectory" form of :339-341)
 __global__ void __launch_bounds__(256) k_retire_rows(const double* __restrict__ src, double* __restrict__ dst_full, const int* __restrict__ orig,
-                                                     const int* __restrict__ active, long long n_rows, long long len) {
+                                                     const int* __restrict__ active, long long n_rows, long long len, int* __restrict__ flag = nullptr) {
     const long long total = n_rows * len;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long j = i / len;
-        if (!active[j]) dst_full[(long long)orig[j] * len + (i - j * len)] = src[i];
+        if (!active[j]) {
+            const double v = src[i];
+            dst_full[(long long)orig[j] * len + (i - j * len)] = v;
+            if (flag && !(fabs(v) <= 1.7976931348623157e308)) flag[orig[j]] = 2;
+        }
     }
 }
 // the rows still iterating move to the front (into `dst`, same order)
@@ -570,7 +575,7 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
     auto iter_end = [&](int it, long long* n_next) -> int {
         CK(h, cudaMemsetAsync(dCount, 0, 8, st));
         slv::k_iter_end<<<slv::nblk(nc, 256), 256, 0, st>>>(dEr, dActive, dOrig, dIters, dFlag, dErOut, dCount, nc, it, max_iter);
-        slv::k_retire_rows<<<grid_for(nc * LX), 256, 0, st>>>(dXC, dXCout, dOrig, dActive, nc, LX);
+        slv::k_retire_rows<<<grid_for(nc * LX), 256, 0, st>>>(dXC, dXCout, dOrig, dActive, nc, LX, dFlag);
         slv::k_retire_rows<<<grid_for(nc * LD), 256, 0, st>>>(dDef, dDefOut, dOrig, dActive, nc, LD);
         h->launches += 3;
         unsigned long long na = 0;
@@ -642,13 +647,7 @@ int lto_indirect_solve_batch(lto_handle* h, const lto_indirect_params* p, int64_
     CK(h, cudaStreamSynchronize(st));
     float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
     if (status_flag) {
-        for (long long j = 0; j < T; ++j) {
-            int f = flag[(size_t)j];
-            if (f != 2)                                                                        // :339-341, over the whole trajectory
-                for (long long i = 0; i < (long long)N * ND; ++i)
-                    if (!std::isfinite(XC_all[(size_t)j * N * ND + i])) { f = 2; break; }
-            status_flag[j] = f;
-        }
+        for (long long j = 0; j < T; ++j) status_flag[j] = flag[(size_t)j];                    // (non-finite nodes were flagged when the row was retired)
     }
     return LTO_SUCCESS;
 }
