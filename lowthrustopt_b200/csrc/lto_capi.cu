@@ -135,6 +135,7 @@ void lto_destroy(lto_handle* h) {
     cudaStreamSynchronize(h->s_compute); cudaStreamSynchronize(h->s_copy); cudaStreamSynchronize(h->s_h2d);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->d_ctr) cudaFree(h->d_ctr);
     if (h->d_scr) cudaFree(h->d_scr);
     if (h->d_prof) cudaFree(h->d_prof);
@@ -300,13 +301,32 @@ static void plan_indirect(std::vector<long long>& plan, int n_sm, long long n_se
 }
 
 // ---------------------------------------------------------------------------
-// Pageable caller memory (what a Julia / numpy caller holds).  Measured on config 3 (bench.py e2e.pageable): with pageable INPUTS and
-// pinned result arrays the call runs at 73 % of the all-pinned rate (28.8 vs 39.5 M segments/s: the driver stages the 11.5 MB of
-// inputs and blocks the enqueueing thread meanwhile); with pageable RESULT arrays as well at 27 % (the 78 MB of Jacobian blocks are
-// staged too and the copy/compute overlap is gone).  Tried and not kept: staging the inputs through a pinned block of the handle by the
-// calling thread (26.3 M: one core's memcpy is no faster than the driver's staging on these hosts) and by a pool of worker threads
-// (28.2 M, no gain).  What pays is pinned RESULT arrays: lto_host_alloc; the Python and Julia bindings allocate theirs from a pool of
-// such blocks (capi.PinnedPool, julia/lto_b200.jl pinned_array).
+// Pageable caller memory (what a Julia / numpy caller holds; bench.py e2e.pageable, config 3).
+//   * pageable RESULT arrays: 27 % of the all-pinned rate (the 78 MB of Jacobian blocks are staged by the driver, the copy/compute overlap is
+//     gone).  What pays is pinned result arrays: lto_host_alloc; the Python and Julia bindings allocate theirs from a pool of such blocks
+//     (capi.PinnedPool, julia/lto_b200.jl pinned_array).
+//   * pageable INPUTS: a cudaMemcpyAsync from pageable memory blocks the enqueueing thread, so nothing of a chunk is enqueued before its inputs
+//     have crossed -- with K1's ramped schedule (last chunk = half the batch) the call ended one half-batch kernel + copy after the last input
+//     byte: 73 % of the all-pinned rate.  Direct calls therefore detect pageable inputs (cudaPointerGetAttributes), copy each chunk's rows into
+//     a pinned block of the handle themselves (so every CUDA call stays asynchronous) and use a schedule of EQUAL two-wave chunks: the staging of
+//     chunk k+1 overlaps the kernel and the copy-out of chunk k and only one small chunk is exposed at the end: 32.9 M segments/s = 84 % of
+//     the all-pinned rate (nstate 6: 92 %); what is left is one core's memcpy of the 11.5 MB.  (Measured and not kept: the same staging with
+//     the ramped schedule -- calling thread 26.3 M, worker threads 28.2 M: the schedule was the problem; two helper threads staging ahead of
+//     the enqueueing thread with the equal schedule -- 29.3 M: thread start-up and hand-over cost more than they hide on these hosts.)
+//     The indirect calls already run equal chunks and lose 4 % with pageable inputs.
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+static int ensure_host(lto_handle* h, void** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
+    const size_t want = need + need / 4;
+    if (cudaHostAlloc(p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); *p = nullptr; return 1; }   // caller falls back to the driver's staging
+    *cap = want;
+    return 0;
+}
 // ---------------------------------------------------------------------------
 
 // ---------------------------------------------------------------------------
@@ -392,12 +412,37 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
     // ---- chunked compute + D2H pipeline
     std::vector<long long> plan;
     plan_direct(plan, h->n_sm, n_seg, npt, nstate, nsteps, p->mode, want_jac);
+    // pageable inputs (see above): own pinned staging in CHUNK-major order (one host->device copy per chunk), equal two-wave chunks
+    char* hs = nullptr;
+    if (plan.size() > 1 && is_pageable(Xa) && ensure_host(h, &h->h_stage, &h->h_stage_cap, in_bytes) == 0) {
+        hs = (char*)h->h_stage;
+        const long long unit = npt > 0 ? npt - 1 : 1;
+        const long long c = std::max<long long>(unit, (2ll * h->n_sm * 32 + unit - 1) / unit * unit);
+        plan.clear();
+        for (long long left = n_seg; left > 0;) { const long long take = (left < c + c / 2) ? left : c; plan.push_back(take); left -= take; }
+    }
     long long s0 = 0;
+    size_t stage_off = 0;
     for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
         const long long ns = plan[ci];
         const long long r0 = lto_node_a(s0, npt);
-        {   // this chunk's input rows (trajectory form: whole trajectories, n_nodes rows each)
-            const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+        // this chunk's input rows (trajectory form: whole trajectories, n_nodes rows each)
+        const long long nr = npt > 0 ? ns / (npt - 1) * npt : ns;
+        if (hs) {
+            // [Xa | ua | ta ( | Xb | ub | tb )] of this chunk, contiguous in the pinned block and, at the same offset, in the device block
+            char* st = hs + stage_off;
+            double* dv = (double*)((char*)h->d_in + stage_off);
+            size_t o = 0;
+            auto add = [&](const double* src, size_t bytes) { memcpy(st + o, src, bytes); o += bytes; };
+            add(Xa + r0 * NS, nr * NS * 8); add(ua + r0 * 3, nr * 3 * 8); add(ta + r0, nr * 8);
+            a.Xa = dv; a.ua = a.Xa + nr * NS; a.ta = a.ua + nr * 3;
+            if (npt == 0) {
+                add(Xb + r0 * NS, nr * NS * 8); add(ub + r0 * 3, nr * 3 * 8); add(tb + r0, nr * 8);
+                a.Xb = a.ta + nr; a.ub = a.Xb + nr * NS; a.tb = a.ub + nr * 3;
+            } else { a.Xb = a.Xa + NS; a.ub = a.ua + 3; a.tb = a.ta + 1; }
+            CK(h, cudaMemcpyAsync(dv, st, o, cudaMemcpyHostToDevice, h->s_h2d));
+            stage_off += o;
+        } else {
             CK(h, cudaMemcpyAsync(dXa + r0 * NS, Xa + r0 * NS, nr * NS * 8, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaMemcpyAsync(dua + r0 * 3, ua + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
             CK(h, cudaMemcpyAsync(dta + r0, ta + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
@@ -406,10 +451,10 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
                 CK(h, cudaMemcpyAsync(dub + r0 * 3, ub + r0 * 3, nr * 3 * 8, cudaMemcpyHostToDevice, h->s_h2d));
                 CK(h, cudaMemcpyAsync(dtb + r0, tb + r0, nr * 8, cudaMemcpyHostToDevice, h->s_h2d));
             }
-            CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
-            CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
+            a.Xa = dXa + r0 * NS; a.Xb = dXb + r0 * NS; a.ua = dua + r0 * 3; a.ub = dub + r0 * 3; a.ta = dta + r0; a.tb = dtb + r0;
         }
-        a.Xa = dXa + r0 * NS; a.Xb = dXb + r0 * NS; a.ua = dua + r0 * 3; a.ub = dub + r0 * 3; a.ta = dta + r0; a.tb = dtb + r0;
+        CK(h, cudaEventRecord(h->ev_h2d[ci & 7], h->s_h2d));
+        CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_h2d[ci & 7], 0));
         a.defect = dD + s0 * NS; a.errors = dE + s0; a.status = dS + s0; a.jac = want_jac ? dJ + s0 * NS * NV : nullptr;
         a.n_seg = ns; a.npt = npt;
         rc = dispatch_direct(h, a, nstate, p->kernel); if (rc) return rc;

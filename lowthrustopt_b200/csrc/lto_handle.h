@@ -18,6 +18,7 @@ struct lto_handle {
     cudaEvent_t ev_chunk[8], ev_h2d[8];
     void* d_in; size_t d_in_cap;
     void* d_out; size_t d_out_cap;
+    void* h_stage; size_t h_stage_cap;          // pinned staging of PAGEABLE caller inputs (direct host calls), grow-only
     unsigned long long* d_ctr;
     void* d_scr; size_t d_scr_cap;
     unsigned long long* d_prof;                 // LTO_ICW_PROF=1: per-warp cycle counters of the last indirect throughput launch
