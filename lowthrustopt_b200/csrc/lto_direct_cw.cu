@@ -249,6 +249,13 @@ __device__ __forceinline__ void column_warp(const DirectArgs& a, long long n_til
         for (int t = 0; t < NTILE; ++t) col_init<NS>(cs[t], col);
         for (int k = 0; k < nstep; ++k, ++g) {
             const unsigned slot = g & (NSLOT - 1), par = (g / NSLOT) & 1;
+#ifndef LTO_K1_NO_PACE
+            // the column warps walk the ~25 KB step body together (shared instruction fetches): without this the column warp that shares its
+            // sub-partition with a state warp and no second column warp (nstate 6) runs ahead and the instruction-cache hit rate drops
+            // (78 % against 95 %).  Measured: nstate 6 0.707 -> 0.611 ms, nstate 7 unchanged (0.682 ms); a second barrier between the two
+            // tiles of a step is no better for 6 and costs 8 % for 7.
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * C::NCOL) : "memory");
+#endif
 #pragma unroll
             for (int t = 0; t < NTILE; ++t) {
                 const double* rec = recs + (size_t)(t * NSLOT + slot) * C::STEP_DOUBLES * 32 + lane;
