@@ -490,6 +490,9 @@ __device__ __forceinline__ void column_warp_adapt(const DirectArgs& a, long long
         for (int t = 0; t < NTILE; ++t) col_init<NS>(cs[t], col);
         unsigned alive = (1u << NTILE) - 1u, first = alive;
         while (alive) {
+#ifndef LTO_K1_NO_PACE
+            asm volatile("bar.sync 3, %0;" ::"n"(32 * C::NCOL) : "memory");     // keep the column warps on the same instructions (see column_warp)
+#endif
 #pragma unroll
             for (int t = 0; t < NTILE; ++t) {
                 if (!(alive & (1u << t))) continue;
