@@ -182,6 +182,9 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
             for (int ph = 0; ph < NPH; ++ph) {
                 const int task = ph * NCW + cw;
 #endif
+#ifdef LTO_IHC_PACE_TASK                  // one barrier per task: the column warps start every task's instruction stream together
+                asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
+#endif
                 const int col = 2 * (task >> 2) + csel;
                 const int slot = (task & 3) * 8 + s8;
                 const int2 hc = S.hctl[slot];
