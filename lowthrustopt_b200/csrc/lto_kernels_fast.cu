@@ -14,6 +14,8 @@ cudaError_t launch_indirect_hc(const IndirectArgs& a, cudaStream_t st, int* n_la
 size_t indirect_hc_scratch_bytes(int n_sm);
 cudaError_t launch_indirect_wl(const IndirectArgs& a, cudaStream_t st, int* n_launch);
 size_t indirect_wl_scratch_bytes(int n_sm);
+cudaError_t launch_indirect_hc2(const IndirectArgs& a, cudaStream_t st, int* n_launch);
+size_t indirect_hc2_scratch_bytes(int n_sm);
 #endif
 size_t indirect_cw14_scratch_bytes(int n_sm);
 size_t indirect_cwv2_scratch_bytes(int n_sm);
@@ -33,9 +35,10 @@ cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t s
 #ifdef LTO_K3_EXPERIMENTS
     if (a.phi != nullptr && a.cfg.controller == 0) {
         static int v = -1;
-        if (v < 0) { const char* e = getenv("LTO_K3"); v = !e ? 0 : strcmp(e, "hc") == 0 ? 1 : strcmp(e, "wl") == 0 ? 2 : 0; }
+        if (v < 0) { const char* e = getenv("LTO_K3"); v = !e ? 0 : strcmp(e, "hc") == 0 ? 1 : strcmp(e, "wl") == 0 ? 2 : strcmp(e, "hc2") == 0 ? 3 : 0; }
         if (v == 1) return launch_indirect_hc(a, st, n_launch);
         if (v == 2 && a.cfg.err_norm != 0) return launch_indirect_wl(a, st, n_launch);
+        if (v == 3) return launch_indirect_hc2(a, st, n_launch);
     }
 #endif
     return launch_indirect_cw(a, ndim, st, n_launch);
@@ -44,7 +47,7 @@ cudaError_t launch_indirect_fast(const IndirectArgs& a, int ndim, cudaStream_t s
 size_t indirect_cw_scratch_bytes(int n_sm) {
     size_t b = std::max(indirect_cwv2_scratch_bytes(n_sm), indirect_cw14_scratch_bytes(n_sm));
 #ifdef LTO_K3_EXPERIMENTS
-    b = std::max(b, std::max(indirect_hc_scratch_bytes(n_sm), indirect_wl_scratch_bytes(n_sm)));
+    b = std::max(b, std::max(indirect_hc_scratch_bytes(n_sm), std::max(indirect_wl_scratch_bytes(n_sm), indirect_hc2_scratch_bytes(n_sm))));
 #endif
     return b;
 }

@@ -171,7 +171,7 @@ h.close()
 """
 
 
-@pytest.mark.parametrize("layout", ["hc", "wl"])
+@pytest.mark.parametrize("layout", ["hc", "wl", "hc2"])
 def test_k3_experimental_layouts_match_default(layout, lto, oracle, tmp_path):
     """The two round-2 rebuilds of K3 that were measured and not adopted (hc = second-order half-column formulation with
     setmaxnreg and three tiles; wl = warp-local, every warp owns 8 slots) live in tools/experiments/ and are NOT in the product library; a library

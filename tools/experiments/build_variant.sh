@@ -7,5 +7,5 @@ cd "$(dirname "$0")/../.."
 name=$1; shift
 mkdir -p tools/experiments/lib
 LTO_LIB_OUT=$PWD/tools/experiments/lib/liblto_$name.so LTO_OBJ_DIR=/tmp/lto_build_$name \
-LTO_EXTRA_SOURCES=$PWD/tools/experiments/lto_indirect_hc.cu:$PWD/tools/experiments/lto_indirect_wl.cu \
+LTO_EXTRA_SOURCES=$PWD/tools/experiments/lto_indirect_hc.cu:$PWD/tools/experiments/lto_indirect_wl.cu:$PWD/tools/experiments/lto_indirect_hc2.cu \
 LTO_NVCC_EXTRA="-DLTO_K3_EXPERIMENTS $*" python -c "from lowthrustopt_b200 import build; print(build.build_lib(force=True))"

@@ -1,31 +1,12 @@
-// lto_indirect_hc.cu -- throughput kernel of the indirect method (K3), ndim = 12, "half-column" layout:
-// defectCalc + jacobianCalc of multiShoot_CRTBP_indirect.jl:63-124 for a whole batch in one launch.  Each segment integrates
-// [x | Phi] (12 + 144 components) with the adaptive order-8 pair and the OrdinaryDiffEq-style controller of lto_prop_generic.cuh
-// (drive_rk8); Phi replaces ForwardDiff.jacobian(f, x0) (:121).
-//
-// Why this layout (round 2).  The round-1 kernel gave a thread a whole STM column: 117 stage derivatives ->
-// 255 registers -> 8 warps per SM, two per sub-partition, the two state warps alone on the fourth sub-partition (a quarter of the
-// SM's FP64 pipe idle) and the state warp's chain exposed (FP64 pipe 48 % active).  Here the system is integrated in the
-// second-order variables (r, v, lv, lv') (lto_hc_math.cuh): every STM column splits into two 3-vector second-order halves of the
-// SAME shape, each advanced in Nystrom form with 39 stored doubles.  One thread = one half-column:
-//   * ~150 registers -> 12 warps per SM, three per sub-partition; all four FP64 pipes carry column work;
-//   * setmaxnreg moves registers from the 8 column warps (128) to the state warps (248), which keep their 78 stage derivatives
-//     in registers;
-//   * 3 tiles of 32 segment slots in flight (stage records 3 x 59.9 KB of shared memory), one state warp per tile, so a tile's
-//     next attempt has two column visits of the other tiles to be ready: the state warp's dependent chain is off the critical
-//     path.
-// Mapping:
-//   tile        = 32 segment slots owned by one state warp (lane = slot): nonlinear 12-dim system, step-size controller, work
-//                 queue (a slot that finishes its segment pulls the next one from a global counter).  Publishes per attempted
-//                 step the 13 stage linearisations U, W, G (18 doubles per stage and slot) + h + flags.
-//   column warp = 8 per CTA.  A tile visit is 24 warp-tasks = 6 column pairs x 4 slot octets, three per column warp.  In a task
-//                 lane = (g, s): g = 2 * (column of the pair) + half, s = slot of the octet; the two halves of a column sit 8 lanes
-//                 apart and swap their stage positions with one shfl.xor per component.  The four groups read the same U record
-//                 (one shared-memory wavefront per 128-bit load), G (dr-halves) and W (dlv-halves) two.
-//   columns between visits live in an L2-resident scratch, two buffers per (tile, task, lane); the state warp publishes which one
-//   holds the current (last accepted) column, so an accepted step is a flip and a rejected one re-reads the same buffer.
-// Step control: joint norm over x and Phi (LTO_NORM_STATE_SENS, the ForwardDiff semantics) or x alone (robust estimate + sharp-law
-// safeguard of the state-only controller, lto_prop_generic.cuh).  Errors are scaled in the reference's variables (r, v, lr, lv).
+// lto_indirect_hc2.cu -- K3-hc with what rounds of measurement asked for: the half-column layout of lto_indirect_hc.cu
+// (second-order variables, one thread per 3-vector Nystrom half-column, three tiles in flight, current / candidate columns in two L2 buffers)
+// with
+//   * the state warps' 13 stages ROLLED, their stage derivatives in SHARED memory (the 60 KB of unrolled state code was what evicted the
+//     column loop from the instruction caches; the tensor-memory version of this loop, lto_indirect_hc_tmem.cu, waited on tcgen05.ld),
+//   * tiles of 24 slots (the shared memory the stage derivatives need), 18 tasks per tile visit = 2 per column warp with NINE column warps,
+//   * no setmaxnreg (nothing needs more than 168 registers any more),
+//   * one named barrier per task that keeps the column warps on the same instructions (the K1 nstate-6 fix).
+// Experimental: built only by tools/experiments/build_variant.sh, selected with LTO_K3=hc2.
 #include "lto_internal.h"
 #include "lto_cw_common.cuh"
 #include "lto_hc_math.cuh"
@@ -33,37 +14,34 @@
 #include <cstdlib>
 
 namespace lto {
-namespace ihc {
+namespace ihc2 {
 
 using namespace cwc;
 using namespace hcm;
 
 constexpr int ND = 12;
 constexpr int NTILE = 3;          // tiles in flight = state warps at work
-constexpr int TS = 32;            // segment slots per tile
-#ifdef LTO_IHC_ISO                // experiment: state warps alone on SM sub-partition 3 (warps 3, 7, 11), nine column warps on the other three,
-constexpr int NCW = 9;            // no register reallocation; a tile visit's 24 tasks are dealt round-robin over the 9 column warps ACROSS visits
-#else
-constexpr int NCW = 8;            // column warps (warp groups 0 and 1)
-#endif
+constexpr int TS = 24;            // segment slots per tile (lanes 24..31 of a state warp stay idle: the stage derivatives need the shared memory)
+constexpr int TL = 32;            // lanes: the small per-lane arrays are sized for the whole warp
+constexpr int NCW = 9;            // column warps
 constexpr int NCT = 32 * NCW;     // column threads
 constexpr int NW = 12;            // + warp group 2: 3 state warps and one idle warp
 constexpr int NTHREADS = 32 * NW;
-constexpr int NTASK = 24;         // warp-tasks per tile visit: 6 column pairs x 4 slot octets
-constexpr int NPH = NTASK / NCW;  // tasks per column warp and tile visit (default layout)
+constexpr int NTASK = 18;         // warp-tasks per tile visit: 6 column pairs x 3 slot octets
+constexpr int NPH = NTASK / NCW;  // tasks per column warp and tile visit
 constexpr int NC2 = 9;            // double2 per stage record: U[6] W[6] G[6]
-constexpr int REG_COL = 128, REG_STATE = 248;   // setmaxnreg: launched at 168; the 8 column warps release 8 x 40 registers per lane, the 4 warps of the state group claim 4 x 80 -- only what was released inside the CTA can be claimed (a larger claim spins forever)
 
 enum { F_STORE = 2, F_RESET = 4, F_ACTIVE = 8, F_PAR = 16 };
 
 // ---- shared-memory plan ------------------------------------------------------
 constexpr size_t REC_BYTES = (size_t)13 * NC2 * TS * sizeof(double2);      // stage records of one tile
-constexpr size_t HDR_BYTES = (size_t)TS * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
-constexpr size_t ERR_BYTES = (size_t)ND * TS * sizeof(double);             // error partials per column and slot (both halves summed)
+constexpr size_t HDR_BYTES = (size_t)TL * (sizeof(double) + sizeof(int2)); // h, {flags, segment}
+constexpr size_t ERR_BYTES = (size_t)ND * TL * sizeof(double);             // error partials per column and slot (both halves summed)
 constexpr int NXW = ND + 7;                                                // next-segment stash: x0, t0, tf, aL, 1/rho, aL/(4 rho), h0, tol scale
-constexpr size_t NXT_BYTES = (size_t)NXW * TS * sizeof(double);
-constexpr size_t ZN_BYTES = (size_t)2 * ND * TS * sizeof(double);           // the state z and the candidate of the attempt in flight (double buffer; not live in registers across the right-hand-side calls)
-constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + ERR_BYTES + ZN_BYTES + NXT_BYTES;
+constexpr size_t NXT_BYTES = (size_t)NXW * TL * sizeof(double);
+constexpr int KST = TS + 1;                                                // stage derivatives of the state: [stage][component][slot], one spare column for the idle lanes
+constexpr size_t KS_BYTES = (size_t)13 * 6 * KST * sizeof(double);
+constexpr size_t TILE_BYTES = REC_BYTES + HDR_BYTES + ERR_BYTES + NXT_BYTES + KS_BYTES;
 constexpr size_t BAR_BYTES = 32;                                           // full, done, tile_done
 constexpr size_t SMEM = NTILE * TILE_BYTES + NTILE * BAR_BYTES;
 static_assert(SMEM <= 232448, "three tiles must fit the 227 KB of shared memory per CTA");
@@ -71,28 +49,25 @@ static_assert(TILE_BYTES % 16 == 0, "tiles must stay 16-byte aligned");
 constexpr size_t SCR_DOUBLES_PER_CTA = (size_t)NTILE * 2 * NTASK * 6 * 32; // [tile][parity][task][component][lane]
 
 struct TileSmem {
-    double2* rec; double* hval; int2* hctl; double* errp; double* zn; double* nx;
-    unsigned bar_full, bar_done; volatile int* tile_done; int* task_ctr;
+    double2* rec; double* hval; int2* hctl; double* errp; double* nx; double* ks;
+    unsigned bar_full, bar_done; volatile int* tile_done;
 };
 
 __device__ __forceinline__ TileSmem tile_smem(unsigned char* base, int t) {
     unsigned char* p = base + (size_t)t * TILE_BYTES;
     TileSmem s;
     s.rec = reinterpret_cast<double2*>(p); p += REC_BYTES;
-    s.hval = reinterpret_cast<double*>(p); p += TS * sizeof(double);
-    s.hctl = reinterpret_cast<int2*>(p); p += TS * sizeof(int2);
+    s.hval = reinterpret_cast<double*>(p); p += TL * sizeof(double);
+    s.hctl = reinterpret_cast<int2*>(p); p += TL * sizeof(int2);
     s.errp = reinterpret_cast<double*>(p); p += ERR_BYTES;
-    s.zn = reinterpret_cast<double*>(p); p += ZN_BYTES;
-    s.nx = reinterpret_cast<double*>(p);
+    s.nx = reinterpret_cast<double*>(p); p += NXT_BYTES;
+    s.ks = reinterpret_cast<double*>(p);
     unsigned char* b = base + (size_t)NTILE * TILE_BYTES + (size_t)t * BAR_BYTES;
     s.bar_full = smem_u32(b); s.bar_done = smem_u32(b + 8);
     s.tile_done = reinterpret_cast<volatile int*>(b + 16);
-    s.task_ctr = reinterpret_cast<int*>(b + 24);                        // LTO_IHC_DYN: next task of the tile visit in flight
     return s;
 }
 
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---------------------------------------------------------------------------
 // Column thread: one attempted RK step of one half-column (p, pd) (lto_hc_math.cuh):
@@ -118,9 +93,7 @@ __device__ __forceinline__ void col_stage(K3& K, const double (&p)[3], const dou
 
 // (Measured and switched off: re-converging the 8 column warps a few times per attempt with a named barrier, which kept the round-1
 // kernel's instruction-fetch windows together, costs 18 % here -- the instruction-cache misses came from the state warps' code size.)
-#if defined(LTO_IHC_LOCKSTEP_PAIR)        // the two column warps of one SM sub-partition (cw, cw + 4) only: they then share their instruction fetches
-#define LTO_IHC_LOCKSTEP() asm volatile("bar.sync %0, 64;" ::"r"(lsid) : "memory")
-#elif defined(LTO_IHC_LOCKSTEP_ON)
+#ifdef LTO_IHC_LOCKSTEP_ON
 #define LTO_IHC_LOCKSTEP() asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory")
 #else
 #define LTO_IHC_LOCKSTEP()
@@ -128,9 +101,8 @@ __device__ __forceinline__ void col_stage(K3& K, const double (&p)[3], const dou
 
 template <bool ERR>
 __device__ __forceinline__ double col_attempt(const double (&p)[3], const double (&pd)[3], double h, double w2, const double2* __restrict__ rec,
-                                              int half, double atol, double rtol, double (&pn)[3], double (&pdn)[3], int lsid = 1) {
+                                              int half, double atol, double rtol, double (&pn)[3], double (&pdn)[3]) {
     const double h2 = h * h;
-    (void)lsid;
     const int xoff = half ? 3 * TS : 6 * TS;                            // W for the dlv-half, G for the dr-half
     K3 K;
     LTO_IHC_LOCKSTEP();
@@ -171,36 +143,12 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
             const long long c1 = clock64();
             c_wait += c1 - c0;
             const bool done = *S.tile_done != 0;
-#ifdef LTO_IHC_ISO
-            const int gv = (int)(visit * NTILE + t);
-            const int k0 = ((cw - (NTASK * gv) % NCW) % NCW + NCW) % NCW;
-            int n_my = 0;
-#pragma unroll 1
-            for (int task = k0; task < NTASK; task += NCW) {
-                ++n_my;
-#else
-#ifdef LTO_IHC_DYN
-            // Tasks are CLAIMED, not dealt: a column warp that shares its sub-partition's FP64 pipe with a state warp gets through fewer of
-            // them than one that does not, and a static deal makes everybody wait for the busiest sub-partition.
-            int n_my = 0;
-#pragma unroll 1
-            while (true) {
-                int task = 0;
-                if (lane == 0) task = atomicAdd(S.task_ctr, 1);
-                task = __shfl_sync(0xffffffffu, task, 0);
-                if (task >= NTASK) break;
-                ++n_my;
-#else
 #pragma unroll 1
             for (int ph = 0; ph < NPH; ++ph) {
+                asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");   // pace: the column warps start every task's instruction stream together
                 const int task = ph * NCW + cw;
-#endif
-#endif
-#ifdef LTO_IHC_PACE_TASK                  // one barrier per task: the column warps start every task's instruction stream together
-                asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
-#endif
-                const int col = 2 * (task >> 2) + csel;
-                const int slot = (task & 3) * 8 + s8;
+                const int col = 2 * (task / 3) + csel;
+                const int slot = (task % 3) * 8 + s8;
                 const int2 hc = S.hctl[slot];
                 const double h = S.hval[slot];
                 const int par = (hc.x & F_PAR) ? 1 : 0;
@@ -235,26 +183,17 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
                 if (done) continue;
                 double pn[3], pdn[3];
                 const long long ca = a.prof ? clock64() : 0;
-                double es = col_attempt<JOINT>(p, pd, h, w2, S.rec + slot, half, atol, rtol, pn, pdn, 1 + (cw & 3));
+                double es = col_attempt<JOINT>(p, pd, h, w2, S.rec + slot, half, atol, rtol, pn, pdn);
                 if (a.prof) c_att += clock64() - ca;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) { __stcg(cnd + q * 32, pn[q]); __stcg(cnd + (3 + q) * 32, pdn[q]); }
                 if (JOINT) {
                     es += __shfl_xor_sync(0xffffffffu, es, 8);
-                    if (half == 0) S.errp[col * TS + slot] = es;
+                    if (half == 0) S.errp[col * TL + slot] = es;
                 }
             }
-#ifdef LTO_IHC_ISO
             if (done) alive &= ~(1u << t);
-            else { for (int i = 0; i < n_my; ++i) mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += n_my; }
-#else
-            if (done) alive &= ~(1u << t);
-#ifdef LTO_IHC_DYN
-            else { mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += n_my; }
-#else
             else { mbar_arrive(S.bar_done); c_work += clock64() - c1; n_work += NPH; }
-#endif
-#endif
         }
         ++visit;
     }
@@ -266,44 +205,28 @@ __device__ __forceinline__ void column_warp(const IndirectArgs& a, int cw, int l
 }
 
 // ---------------------------------------------------------------------------
-// State warp.  The 78 stage derivatives of z = (r, v, lv, lvd) stay in registers (13 unrolled stages, compile-time tableau
-// sparsity); ONE out-of-line copy of the right-hand side serves all 13 stages, and the claim of the next segment is inlined at
-// its one call site -- the state warps' code competes with the column warps' ~19 KB loop body for the instruction caches
-// (sm__icc_request_hit_rate, stall_no_instruction in profiles/), so every duplicate counts.  Measured alternative (kept in
-// tools/experiments/lto_indirect_hc_tmem.cu): stages rolled into a loop with the derivatives in the warp's lane quadrant of TENSOR
-// MEMORY (tcgen05.st / tcgen05.ld) -- a third of the code, correct results, but the dependent load -> wait -> FMA rounds of the
-// stage-input loop cost 24 k cycles per attempt (48 k in all against 28 k here), so the state warps became the bound.
+// State warp.
+//
+// Code size matters as much as arithmetic here: the column warps stream a ~19 KB straight-line body, and every other instruction
+// stream on the SM competes with it for the instruction caches (round 2, first version: 13 unrolled stages with the 78 stage
+// derivatives in registers = 33 KB of state code, sm__icc_request_hit_rate 66 %, stall_no_instruction the top stall of BOTH warp
+// kinds, the columns 55 % slower than with idle state warps; profiles/r02_*).  So the state warp runs ROLLED loops over stages:
+//   * the stage derivatives k_J = (r'', lv'') live in the warp's own lane quadrant of TENSOR MEMORY (tcgen05.st / tcgen05.ld,
+//     16 columns per stage and lane; 12-cycle loads, dynamically addressed) -- TMEM is otherwise unused by this FP64 kernel and is
+//     the only on-chip store left: registers and shared memory are full;
+//   * tableau coefficients come from __constant__ tables (uniform loads), zero entries skipped by uniform branches;
+//   * the 8th-order update and the error estimate are accumulated stage by stage;
+//   * one out-of-line copy of the right-hand side serves all 13 stages, arguments and results in registers.
 // ---------------------------------------------------------------------------
-struct Out6 { double v[6]; };
-__device__ __noinline__ Out6 sc_eval2_call(double r0, double r1, double r2, double v0, double v1, double m0, double m1, double m2, double n0, double n1,
-                                           double mu, double mu1, double w2, double pexp, double aL, double rho_inv, double rq, double2* w) {
-    const double R[3] = {r0, r1, r2}, V[3] = {v0, v1, 0.0}, M[3] = {m0, m1, m2}, N[3] = {n0, n1, 0.0};
-    Law lw; lw.aL = aL; lw.rho_inv = rho_inv; lw.rq = rq;
-    double kr[3], kl[3], U[6], W[6], G[6];
-    sc_eval2<true>(R, V, M, N, mu, mu1, w2, pexp, lw, kr, kl, U, W, G);
-    w[0 * TS] = make_double2(U[0], U[1]); w[1 * TS] = make_double2(U[2], U[3]); w[2 * TS] = make_double2(U[4], U[5]);
-    w[3 * TS] = make_double2(W[0], W[1]); w[4 * TS] = make_double2(W[2], W[3]); w[5 * TS] = make_double2(W[4], W[5]);
-    w[6 * TS] = make_double2(G[0], G[1]); w[7 * TS] = make_double2(G[2], G[3]); w[8 * TS] = make_double2(G[4], G[5]);
-    Out6 o;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { o.v[q] = kr[q]; o.v[3 + q] = kl[q]; }
-    return o;
-}
-
-// one stage of the state: inputs from the stage derivatives in REGISTERS (compile-time tableau sparsity), right-hand side + record
-template <int J>
-__device__ __forceinline__ void state_stage(K3& Kr, K3& Kl, const double* __restrict__ z, double h, double h2, const SCConst& c, double w2,
-                                            const Law& lw, double2* __restrict__ rec) {
-    const double r[3] = {z[0 * TS], z[1 * TS], z[2 * TS]}, v[3] = {z[3 * TS], z[4 * TS], z[5 * TS]}, lv[3] = {z[6 * TS], z[7 * TS], z[8 * TS]},
-                 lvd[3] = {z[9 * TS], z[10 * TS], z[11 * TS]};
-    double R[3], V[3], M[3], N[3];
-    stage_in<J>(Kr, r, v, h, h2, R, V);
-    stage_in<J>(Kl, lv, lvd, h, h2, M, N);
-    const Out6 o = sc_eval2_call(R[0], R[1], R[2], V[0], V[1], M[0], M[1], M[2], N[0], N[1], c.mu, c.m1, w2, c.p, lw.aL, lw.rho_inv, lw.rq,
-                                 rec + J * NC2 * TS);
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { Kr.k[J][q] = o.v[q]; Kl.k[J][q] = o.v[3 + q]; }
-}
+__constant__ double tB[13][13] = LTO_TAB_B_INIT;
+__constant__ double tG[13][13] = LTO_TAB_G_INIT;
+__constant__ double tB11[13] = {lto_tab::Bf(11, 0), lto_tab::Bf(11, 1), lto_tab::Bf(11, 2), lto_tab::Bf(11, 3), lto_tab::Bf(11, 4), lto_tab::Bf(11, 5), lto_tab::Bf(11, 6),
+                                lto_tab::Bf(11, 7), lto_tab::Bf(11, 8), lto_tab::Bf(11, 9), lto_tab::Bf(11, 10), 0.0, 0.0};
+__constant__ double tC[13] = LTO_TAB_C_INIT;
+__constant__ double tCHI[13] = LTO_TAB_CHI_INIT;
+__constant__ double tCHIB[13] = LTO_TAB_CHIB_INIT;
+__constant__ double tPSI[13] = LTO_TAB_PSI_INIT;
+__constant__ double tPSIB[13] = LTO_TAB_PSIB_INIT;
 
 __device__ __forceinline__ double rms12(const double (&e)[ND], const double (&y)[ND], double atol, double rtol) {
     double s = 0.0;
@@ -383,10 +306,10 @@ __device__ __forceinline__ Claim prepare_next(const IndirectArgs& a, double* nxs
     }
     if (got) {
 #pragma unroll
-        for (int i = 0; i < ND; ++i) nxs[i * TS] = x[i];
-        nxs[(ND + 0) * TS] = t0; nxs[(ND + 1) * TS] = tf; nxs[(ND + 2) * TS] = lw.aL; nxs[(ND + 3) * TS] = lw.rho_inv; nxs[(ND + 4) * TS] = lw.rq;
-        nxs[(ND + 5) * TS] = fmin(fmin(100.0 * h0, h1), span);
-        nxs[(ND + 6) * TS] = ts;
+        for (int i = 0; i < ND; ++i) nxs[i * TL] = x[i];
+        nxs[(ND + 0) * TL] = t0; nxs[(ND + 1) * TL] = tf; nxs[(ND + 2) * TL] = lw.aL; nxs[(ND + 3) * TL] = lw.rho_inv; nxs[(ND + 4) * TL] = lw.rq;
+        nxs[(ND + 5) * TL] = fmin(fmin(100.0 * h0, h1), span);
+        nxs[(ND + 6) * TL] = ts;
     }
     return c;
 }
@@ -397,23 +320,24 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
     const int slot = lane;
     const unsigned fullmask = 0xffffffffu;
     const double w2 = 2.0 * a.c.omega;
+    double* const ks = S.ks + ((lane < TS) ? lane : TS);                  // this slot's stage derivatives (idle lanes share the spare column)
     double atol = a.cfg.atol, rtol = a.cfg.rtol;                          // per slot when the norm is the state's alone (state_tol_scale)
     const double inv_ne = JOINT ? 1.0 / (double)(ND * (ND + 1)) : 1.0 / (double)ND;
     int par = 0;                                                          // which scratch buffer holds the slot's current columns
-    int zi = 0;                                                           // which half of the double buffer holds z = (r, v, lv, lvd)
-    double* const zbuf = S.zn + slot;
+    double z[ND], zn[ND];                                                 // z = (r, v, lv, lvd) and the candidate of the attempt in flight
 #pragma unroll
-    for (int i = 0; i < ND; ++i) { zbuf[i * TS] = 0.0; zbuf[(ND + i) * TS] = 0.0; }
+    for (int i = 0; i < ND; ++i) { z[i] = 0.0; zn[i] = 0.0; }
     double tcur = 0.0, tf = 0.0, h = 0.0, span = 1.0, esum = 0.0;
     Law lw; lw.aL = 0.0; lw.rho_inv = 1.0; lw.rq = 0.0;
     long long seg = -1, ia = 0;
     int na = 0, nt = 0, status = 0;
     bool active = false, lastrej = false, last = false, have = false;
-    Claim nxt; nxt.nseg = -1; nxt.exhausted = 0;                          // successor segment claimed and staged by prepare_next()
+    Claim nxt; nxt.nseg = -1; nxt.exhausted = (lane >= TS) ? 1 : 0;   // (lanes without a slot never claim)
+    //                          // successor segment claimed and staged by prepare_next()
     unsigned visit = 0;
     double2* rec = S.rec + slot;
     double* const nxs = S.nx + slot;
-    long long c_wait = 0, c_work = 0, c_pre = 0;
+    long long c_wait = 0, c_work = 0, c_pre = 0, c_qin = 0, c_qev = 0, c_qst = 0;
     const long long c_begin = clock64();
     bool soon = true, retried = false;
     int flags = 0, store_seg = 0;                                         // published with the next attempt
@@ -431,7 +355,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                 double s2 = esum;
                 if (JOINT) {
 #pragma unroll
-                    for (int c = 0; c < ND; ++c) s2 += S.errp[c * TS + slot];
+                    for (int c = 0; c < ND; ++c) s2 += S.errp[c * TL + slot];
                 }
                 const double u = s2 * inv_ne;                           // eest^2: eest <= 1 <=> u <= 1, eest^(-1/8) = u^(-1/16)
                 if (!(u == u)) { status = LTO_ST_NAN; finished = true; }
@@ -440,7 +364,9 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
                     q = fmin(5.0, fmax(0.2, q));
                     if (u <= 1.0) {
                         ++na;
-                        par ^= 1; zi ^= 1;                                // the candidates become z and the current columns
+                        par ^= 1;                                         // the candidates become z and the current columns
+#pragma unroll
+                        for (int i = 0; i < ND; ++i) z[i] = zn[i];
                         if (last) { tcur = tf; finished = true; }
                         else { tcur += h; if (lastrej) q = fmin(q, 1.0); lastrej = false; }
                     } else {
@@ -456,11 +382,10 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         }
         if (active && finished) {
             // ---- defect = x(t1) - XC_all[:, i+1] (multiShoot_CRTBP_indirect.jl:82), back in the reference's variables
-            const double* zs = zbuf + zi * ND * TS;
             double xv[ND];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { xv[q] = zs[q * TS]; xv[3 + q] = zs[(3 + q) * TS]; xv[9 + q] = zs[(6 + q) * TS]; }
-            xv[6] = fma(w2, xv[10], -zs[9 * TS]); xv[7] = fma(-w2, xv[9], -zs[10 * TS]); xv[8] = -zs[11 * TS];
+            for (int q = 0; q < 3; ++q) { xv[q] = z[q]; xv[3 + q] = z[3 + q]; xv[9 + q] = z[6 + q]; }
+            xv[6] = fma(w2, z[7], -z[9]); xv[7] = fma(-w2, z[6], -z[10]); xv[8] = -z[11];
             bool nan = false;
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
@@ -475,15 +400,14 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         }
         if (!active && nxt.nseg >= 0) {                                  // take the successor prepared by prepare_next()
             seg = nxt.nseg; nxt.nseg = -1; ia = lto_node_a(seg, a.npt);
-            double* zs = zbuf + zi * ND * TS;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { zs[q * TS] = nxs[q * TS]; zs[(3 + q) * TS] = nxs[(3 + q) * TS]; zs[(6 + q) * TS] = nxs[(9 + q) * TS]; }
-            zs[9 * TS] = fma(w2, nxs[10 * TS], -nxs[6 * TS]); zs[10 * TS] = fma(-w2, nxs[9 * TS], -nxs[7 * TS]); zs[11 * TS] = -nxs[8 * TS];
-            tcur = nxs[(ND + 0) * TS]; tf = nxs[(ND + 1) * TS];
+            for (int q = 0; q < 3; ++q) { z[q] = nxs[q * TL]; z[3 + q] = nxs[(3 + q) * TL]; z[6 + q] = nxs[(9 + q) * TL]; }
+            z[9] = fma(w2, nxs[10 * TL], -nxs[6 * TL]); z[10] = fma(-w2, nxs[9 * TL], -nxs[7 * TL]); z[11] = -nxs[8 * TL];
+            tcur = nxs[(ND + 0) * TL]; tf = nxs[(ND + 1) * TL];
             span = tf - tcur;
-            lw.aL = nxs[(ND + 2) * TS]; lw.rho_inv = nxs[(ND + 3) * TS]; lw.rq = nxs[(ND + 4) * TS];
-            h = nxs[(ND + 5) * TS];
-            if (!JOINT) { const double ts = nxs[(ND + 6) * TS]; atol = a.cfg.atol * ts; rtol = a.cfg.rtol * ts; }
+            lw.aL = nxs[(ND + 2) * TL]; lw.rho_inv = nxs[(ND + 3) * TL]; lw.rq = nxs[(ND + 4) * TL];
+            h = nxs[(ND + 5) * TL];
+            if (!JOINT) { const double ts = nxs[(ND + 6) * TL]; atol = a.cfg.atol * ts; rtol = a.cfg.rtol * ts; }
             na = 0; nt = 0; status = 0; lastrej = false;
             active = true; flags |= F_RESET;
         }
@@ -494,7 +418,7 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         retried = false;
         if (!__any_sync(fullmask, active)) {
             S.hval[slot] = 0.0; S.hctl[slot] = make_int2(flags | (par ? F_PAR : 0), store_seg);
-            if (lane == 0) { *S.tile_done = 1; *S.task_ctr = 0; }
+            if (lane == 0) *S.tile_done = 1;
             mbar_arrive(S.bar_full);
             break;
         }
@@ -506,25 +430,70 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         if (active) ++nt;
         S.hval[slot] = h; S.hctl[slot] = make_int2(flags | (active ? F_ACTIVE : 0) | (par ? F_PAR : 0), store_seg);
         const double h2 = h * h;
-        K3 Kr, Kl;
-        const double* z = zbuf + zi * ND * TS;
-        state_stage<0>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<1>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<2>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<3>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<4>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<5>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<6>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<7>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<8>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<9>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);   state_stage<10>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);  state_stage<11>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        state_stage<12>(Kr, Kl, z, h, h2, a.c, w2, lw, rec);
-        {
-            const double r[3] = {z[0 * TS], z[1 * TS], z[2 * TS]}, v[3] = {z[3 * TS], z[4 * TS], z[5 * TS]}, lv[3] = {z[6 * TS], z[7 * TS], z[8 * TS]},
-                         lvd[3] = {z[9 * TS], z[10 * TS], z[11 * TS]};
-            double rn[3], vn[3], lvn[3], lvdn[3];
-            step_update(Kr, r, v, h, h2, rn, vn);
-            step_update(Kl, lv, lvd, h, h2, lvn, lvdn);
-            esum = state_err_sumsq<!JOINT>(Kr, Kl, w2, h, h2, r, v, lv, lvd, rn, vn, lvn, lvdn, atol, rtol);
-            double* zc = zbuf + (zi ^ 1) * ND * TS;
+        long long q_in = 0, q_ev = 0, q_st = 0;
+        double kp[6];                                                    // k_{J-1}: used from registers, every older one comes back from tensor memory
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { zc[q * TS] = rn[q]; zc[(3 + q) * TS] = vn[q]; zc[(6 + q) * TS] = lvn[q]; zc[(9 + q) * TS] = lvdn[q]; }
+        for (int c = 0; c < 6; ++c) kp[c] = 0.0;
+#pragma unroll 1
+        for (int J = 0; J < 13; ++J) {
+            double sb[6], sg[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { sb[c] = 0.0; sg[c] = 0.0; }
+            const long long q0 = a.prof ? clock64() : 0;
+#pragma unroll 4
+            for (int l = 0; l < J; ++l) {
+                const double b = tB[J][l], g = tG[J][l];                 // (zero coefficients cost an FMA, not a branch)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) { const double k = ks[(l * 6 + c) * KST]; sb[c] = fma(b, k, sb[c]); sg[c] = fma(g, k, sg[c]); }
+            }
+            const long long q1 = a.prof ? clock64() : 0;
+            const double ch = h * tC[J];
+            const double R[3] = {fma(h2, sg[0], fma(ch, z[3], z[0])), fma(h2, sg[1], fma(ch, z[4], z[1])), fma(h2, sg[2], fma(ch, z[5], z[2]))};
+            const double M[3] = {fma(h2, sg[3], fma(ch, z[9], z[6])), fma(h2, sg[4], fma(ch, z[10], z[7])), fma(h2, sg[5], fma(ch, z[11], z[8]))};
+            const double V[3] = {fma(h, sb[0], z[3]), fma(h, sb[1], z[4]), 0.0}, N[3] = {fma(h, sb[3], z[9]), fma(h, sb[4], z[10]), 0.0};
+            double U[6], W[6], G[6];
+            {   // right-hand side + stage record: ONE inlined copy (the stage loop is rolled)
+                double kr[3], kl[3];
+                sc_eval2<true>(R, V, M, N, a.c.mu, a.c.m1, w2, a.c.p, lw, kr, kl, U, W, G);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { kp[q] = kr[q]; kp[3 + q] = kl[q]; }
+            }
+            const long long q2 = a.prof ? clock64() : 0;
+            double2* w = rec + J * NC2 * TS;
+            if (lane < TS) {
+            w[0 * TS] = make_double2(U[0], U[1]); w[1 * TS] = make_double2(U[2], U[3]); w[2 * TS] = make_double2(U[4], U[5]);
+            w[3 * TS] = make_double2(W[0], W[1]); w[4 * TS] = make_double2(W[2], W[3]); w[5 * TS] = make_double2(W[4], W[5]);
+            w[6 * TS] = make_double2(G[0], G[1]); w[7 * TS] = make_double2(G[2], G[3]); w[8 * TS] = make_double2(G[4], G[5]);
+            }
+#pragma unroll
+            for (int c = 0; c < 6; ++c) ks[(J * 6 + c) * KST] = kp[c];
+            if (a.prof) { const long long q3 = clock64(); q_in += q1 - q0; q_ev += q2 - q1; q_st += q3 - q2; }
         }
-        if (lane == 0) *S.task_ctr = 0;
+        if (a.prof) { c_qin += q_in; c_qev += q_ev; c_qst += q_st; }
+        // update (chi, chi^T B) and error (psi, psi^T B; ROB: -B[11], k_1 - k_12) sums, from the stage derivatives in shared memory: keeping
+        // them as running sums through the stage loop costs 48 registers the right-hand side needs
+        double su[6], sp[6], e1[6], e2[6], g1[6], g2[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { su[c] = 0.0; sp[c] = 0.0; e1[c] = 0.0; e2[c] = 0.0; g1[c] = 0.0; g2[c] = 0.0; }
+#pragma unroll 1
+        for (int l = 0; l < 13; ++l) {
+            const double wc = tCHI[l], wb = tCHIB[l], wp = tPSI[l], wq = tPSIB[l];
+            const double wa = -tB11[l], wd = (l == 0) ? 1.0 : (l == 11) ? -1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const double k = ks[(l * 6 + c) * KST];
+                su[c] = fma(wc, k, su[c]); sp[c] = fma(wb, k, sp[c]); e2[c] = fma(wp, k, e2[c]); e1[c] = fma(wq, k, e1[c]);
+                if (!JOINT) { g1[c] = fma(wa, k, g1[c]); g2[c] = fma(wd, k, g2[c]); }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {                                    // 8th-order update (ode.jl:937)
+            zn[q] = fma(h2, sp[q], fma(h, z[3 + q], z[q]));
+            zn[3 + q] = fma(h, su[q], z[3 + q]);
+            zn[6 + q] = fma(h2, sp[3 + q], fma(h, z[9 + q], z[6 + q]));
+            zn[9 + q] = fma(h, su[3 + q], z[9 + q]);
+        }
+        esum = state_err_sumsq_acc<!JOINT>(e1, e2, g1, g2, w2, h, h2, z, zn, atol, rtol);
         mbar_arrive(S.bar_full);                                         // the whole attempt's record
         c_work += clock64() - c2;
         have = true; ++visit;
@@ -535,47 +504,33 @@ __device__ __forceinline__ void state_warp(const IndirectArgs& a, int t, int lan
         unsigned long long* o = a.prof + ((size_t)blockIdx.x * NW + NCW + t) * 4;
         o[0] = c_work; o[1] = c_wait; o[2] = visit; o[3] = clock64() - c_begin;
         a.prof[(size_t)gridDim.x * NW * 4 + (size_t)blockIdx.x * NTILE + t] = c_pre;
+        unsigned long long* q = a.prof + (size_t)gridDim.x * (NW * 4 + NTILE + NCW) + ((size_t)blockIdx.x * NTILE + t) * 3;
+        q[0] = c_qin; q[1] = c_qev; q[2] = c_qst;                        // stage-input loop | right-hand side | record + tensor-memory store + sums
     }
 }
 
-template <bool JOINT, int RC = REG_COL, int RS = REG_STATE>
-__global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc(const __grid_constant__ IndirectArgs a) {   // (grid constant: out-of-line callees take its address without a local copy)
+template <bool JOINT>
+__global__ void __launch_bounds__(NTHREADS, 1) k_indirect_hc2(const __grid_constant__ IndirectArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < NTILE) {
         const TileSmem S = tile_smem(smem_raw, threadIdx.x);
         mbar_init(S.bar_full, 32);
-#ifdef LTO_IHC_ISO
-        mbar_init(S.bar_done, NTASK * 32);
-#else
         mbar_init(S.bar_done, NCT);
-#endif
         *S.tile_done = 0;
-        *S.task_ctr = 0;
     }
     __syncthreads();
-    // warp groups 0 and 1 (warps 0..7, two per SM sub-partition): column warps, give registers away;
-    // warp group 2 (warps 8..11, one per sub-partition): state warps of tiles 0..2 take them (warp 11 has no tile)
-#ifdef LTO_IHC_ISO
-    if ((warp & 3) == 3) state_warp<JOINT>(a, warp >> 2, lane, smem_raw);
-    else column_warp<JOINT>(a, warp - (warp >> 2), lane, smem_raw);
-#else
-    if (warp < NCW) {
-        reg_dec<RC>();
-        column_warp<JOINT>(a, warp, lane, smem_raw);
-    } else {
-        reg_inc<RS>();
-        if (warp - NCW < NTILE) state_warp<JOINT>(a, warp - NCW, lane, smem_raw);
-    }
-#endif
+    // warps 0..8: column warps (sub-partitions 0 1 2 3 0 1 2 3 0); warps 9..11: the state warps of tiles 0..2 (sub-partitions 1, 2, 3)
+    if (warp < NCW) column_warp<JOINT>(a, warp, lane, smem_raw);
+    else state_warp<JOINT>(a, warp - NCW, lane, smem_raw);
 }
 
-}  // namespace ihc
+}  // namespace ihc2
 
-size_t indirect_hc_scratch_bytes(int n_sm) { return (size_t)n_sm * ihc::SCR_DOUBLES_PER_CTA * sizeof(double); }
+size_t indirect_hc2_scratch_bytes(int n_sm) { return (size_t)n_sm * ihc2::SCR_DOUBLES_PER_CTA * sizeof(double); }
 
-template <bool JOINT, int RC = ihc::REG_COL, int RS = ihc::REG_STATE>
-static cudaError_t launch_ihc(const IndirectArgs& a, cudaStream_t st) {
+template <bool JOINT>
+static cudaError_t launch_ihc2(const IndirectArgs& a, cudaStream_t st) {
     // per device: a single process may drive several GPUs (lto_init_devices)
     static int n_sm_dev[64] = {0};
     static bool attr_dev[64] = {false};
@@ -584,33 +539,25 @@ static cudaError_t launch_ihc(const IndirectArgs& a, cudaStream_t st) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!attr_dev[dev]) {
         cudaError_t e = cudaDeviceGetAttribute(&n_sm_dev[dev], cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(ihc::k_indirect_hc<JOINT, RC, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ihc::SMEM);
+        e = cudaFuncSetAttribute(ihc2::k_indirect_hc2<JOINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ihc2::SMEM);
         if (e != cudaSuccess) return e;
         attr_dev[dev] = true;
     }
     const int n_sm = n_sm_dev[dev];
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    const long long per_cta = (long long)ihc::NTILE * ihc::TS;
+    const long long per_cta = (long long)ihc2::NTILE * ihc2::TS;
     const int grid = (int)std::min<long long>((a.n_seg + per_cta - 1) / per_cta, (long long)n_sm);
-    ihc::k_indirect_hc<JOINT, RC, RS><<<grid, ihc::NTHREADS, ihc::SMEM, st>>>(a);
+    ihc2::k_indirect_hc2<JOINT><<<grid, ihc2::NTHREADS, ihc2::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_indirect_hc(const IndirectArgs& a, cudaStream_t st, int* n_launch) {
+cudaError_t launch_indirect_hc2(const IndirectArgs& a, cudaStream_t st, int* n_launch) {
     *n_launch = 0;
     if (a.phi == nullptr || a.counter == nullptr || a.scratch == nullptr || a.cfg.controller != 0 || a.n_seg <= 0 || a.n_seg > 0x7fffffffll)
         return cudaErrorNotSupported;
     cudaError_t e;
-#ifdef LTO_HC_VARIANTS                                                  // development: register splits side by side (LTO_HC_REGS=152 | 144)
-    static int v = -1;
-    if (v < 0) { const char* s = getenv("LTO_HC_REGS"); v = s ? atoi(s) : 0; }
-    if (v == 152 && a.cfg.err_norm != 0) e = launch_ihc<true, 152, 200>(a, st);
-    else if (v == 144 && a.cfg.err_norm != 0) e = launch_ihc<true, 144, 216>(a, st);
-    else if (v == 136 && a.cfg.err_norm != 0) e = launch_ihc<true, 136, 232>(a, st);
-    else
-#endif
-    e = (a.cfg.err_norm != 0) ? launch_ihc<true>(a, st) : launch_ihc<false>(a, st);
+    e = (a.cfg.err_norm != 0) ? launch_ihc2<true>(a, st) : launch_ihc2<false>(a, st);
     if (e == cudaSuccess) *n_launch = 1;
     return e;
 }
