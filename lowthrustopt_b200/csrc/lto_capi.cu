@@ -421,6 +421,8 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
         plan.clear();
         for (long long left = n_seg; left > 0;) { const long long take = (left < c + c / 2) ? left : c; plan.push_back(take); left -= take; }
     }
+    static const bool tl = getenv("LTO_DEBUG_TIMELINE") != nullptr;
+    cudaEvent_t tl_k[16], tl_c0[16], tl_c1[16];
     long long s0 = 0;
     size_t stage_off = 0;
     for (int ci = 0; ci < (int)plan.size(); s0 += plan[ci], ++ci) {
@@ -461,15 +463,25 @@ static int direct_host(lto_handle* h, const lto_direct_params* p, long long n_se
         cudaEvent_t ev = h->ev_chunk[ci & 7];
         CK(h, cudaEventRecord(ev, h->s_compute));
         CK(h, cudaStreamWaitEvent(h->s_copy, ev, 0));
+        if (tl && ci < 16) { cudaEventCreate(&tl_k[ci]); cudaEventRecord(tl_k[ci], h->s_compute); cudaEventCreate(&tl_c0[ci]); cudaEventRecord(tl_c0[ci], h->s_copy); }
         CK(h, cudaMemcpyAsync(defect + s0 * NS, dD + s0 * NS, ns * NS * 8, cudaMemcpyDeviceToHost, h->s_copy));
         if (errors) CK(h, cudaMemcpyAsync(errors + s0, dE + s0, ns * 8, cudaMemcpyDeviceToHost, h->s_copy));
         if (status) CK(h, cudaMemcpyAsync(status + s0, dS + s0, ns * 4, cudaMemcpyDeviceToHost, h->s_copy));
         if (want_jac) CK(h, cudaMemcpyAsync(jac + s0 * NS * NV, dJ + s0 * NS * NV, ns * NS * NV * 8, cudaMemcpyDeviceToHost, h->s_copy));
+        if (tl && ci < 16) { cudaEventCreate(&tl_c1[ci]); cudaEventRecord(tl_c1[ci], h->s_copy); }
     }
     CK(h, cudaEventRecord(h->ev_t1, h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_copy));
     CK(h, cudaStreamSynchronize(h->s_compute));
     float ms = 0.f; CK(h, cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1)); h->last_ms = ms;
+    if (tl) {   // LTO_DEBUG_TIMELINE=1: when each chunk's kernel ended and when its copy-out started / ended, ms after the call's first enqueue
+        for (int ci = 0; ci < (int)plan.size() && ci < 16; ++ci) {
+            float a0 = 0, a1 = 0, a2 = 0;
+            cudaEventElapsedTime(&a0, h->ev_t0, tl_k[ci]); cudaEventElapsedTime(&a1, h->ev_t0, tl_c0[ci]); cudaEventElapsedTime(&a2, h->ev_t0, tl_c1[ci]);
+            fprintf(stderr, "[lto timeline] chunk %d: %lld segments, kernel done %.3f, copy-out %.3f .. %.3f ms\n", ci, plan[ci], a0, a1, a2);
+            cudaEventDestroy(tl_k[ci]); cudaEventDestroy(tl_c0[ci]); cudaEventDestroy(tl_c1[ci]);
+        }
+    }
     return LTO_SUCCESS;
 }
 
